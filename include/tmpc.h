@@ -1,0 +1,114 @@
+/* tmpc.h -- C ABI of the B200-native batched tuned-MPC feedback solver.
+ *
+ * One shared library per compiled model (libtmpc_<model>.so), every library exporting exactly these symbols --
+ * the same arrangement as the reference's only native solver path, where `Pmpc.generate` emits one shared
+ * library per model and binds it with ctypes through an opaque capsule
+ * (reference: external/acados/interfaces/acados_template/acados_template/acados_ocp_solver.py:752-801,
+ *  `*_acados_create_capsule / *_acados_create / *_acados_solve / *_acados_free`; used from tunempc/pmpc.py:425-472).
+ *
+ * What each entry point replaces in the reference's Python hot path:
+ *   tmpc_create / tmpc_set_tables   Pmpc.__init__ -> __construct_solver + __create_reference  (tunempc/pmpc.py:39-147, 162-369, 676-783)
+ *   tmpc_reset                      Pmpc.reset / __set_initial_guess                          (tunempc/pmpc.py:858-865, 930-948)
+ *   tmpc_step / tmpc_step_host      Pmpc.step -> Sqp.solve for B initial states at once       (tunempc/pmpc.py:371-423, tunempc/sqp_method.py:136-183)
+ *   tmpc_plant_step                 F(x0=x, p=u)['xf'] in closed_loop_sim                     (tunempc/closed_loop_tools.py:102)
+ *   tmpc_get_*                      Pmpc.w_sol / g_sol / log / index properties               (tunempc/pmpc.py:1120-1142, 785-831)
+ *
+ * Conventions: return 0 = success, non-zero = API error (message via tmpc_last_error); numerical failures never
+ * abort the batch, they are reported per instance in `status`.  All matrices row-major unless stated.  Pointers
+ * named *_dev are device pointers on the handle's device, *_host are host pointers.  The caller owns every buffer
+ * it passes; the library owns its workspace.  Calls on one handle are not re-entrant.  fp64 throughout.
+ */
+#ifndef TMPC_H
+#define TMPC_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tmpc_handle tmpc_handle;
+
+/* per-instance status (SURVEY.md section 5 "failure detection") */
+#define TMPC_OK 0              /* converged: infeasibility < tol and |grad L|_inf < tol (sqp_method.py:276-277)   */
+#define TMPC_MAX_ITER 1        /* stopped at k == max_iter (sqp_method.py:281)                                     */
+#define TMPC_QP_INFEASIBLE 2   /* QP infeasible / working set overflow (reference: CasADi conic raises)            */
+#define TMPC_NOT_PD 3          /* reduced Hessian not positive definite (reference: AssertionError sqp_method.py:201) */
+#define TMPC_NAN 4             /* non-finite iterate                                                                */
+/* flag bits OR-ed into `flags` output */
+#define TMPC_FLAG_GN_FALLBACK 1  /* >=1 iteration used the Gauss-Newton Hessian because the exact one was not PD on the
+                                    dynamics null space (the reference would eigen-clip, sqp_method.py:345-376)   */
+#define TMPC_FLAG_DAMPED 2       /* >=1 line-search backtrack (alpha < 1)                                           */
+
+typedef struct {
+  int32_t nx, nu;        /* must equal the compiled model's (checked) */
+  int32_t nh;            /* rows of h(x,u) = C z + c >= 0 */
+  int32_t nx_term;       /* rows of the terminal operator (selection of states) */
+  int32_t N;             /* horizon */
+  int32_t p;             /* period of the reference tables */
+} tmpc_dims;
+
+typedef struct {
+  int32_t hessian_exact;   /* 1: exact Lagrangian Hessian (pmpc.py:153 default), 0: gauss_newton (pmpc.py:327-333) */
+  int32_t max_iter;        /* pmpc.py:155 (2000) */
+  int32_t max_ls_iter;     /* sqp_method.py:57 (300) */
+  double tol;              /* sqp_method.py:55 (1e-6) */
+  double lam_tresh;        /* sqp_method.py:56 (1e-8) */
+  double ls_step_factor;   /* sqp_method.py:58 (0.8) */
+  double reg_tol;          /* sqp_method.py:54 (1e-8): pivot threshold of the reduced-Hessian PD test */
+  double term_penalty;     /* rho of the exact terminal penalty used inside the Riccati base factorisation */
+} tmpc_opts;
+
+void tmpc_default_opts(tmpc_opts* o);
+/* compiled model: name, nx, nu, RK4 steps (0 for a discrete map), step length */
+const char* tmpc_model_info(int32_t* nx, int32_t* nu, int32_t* rk_steps, double* dt);
+
+int tmpc_create(tmpc_handle** h, const tmpc_dims* dims, const tmpc_opts* opts, int device);
+void tmpc_destroy(tmpc_handle* h);
+const char* tmpc_last_error(const tmpc_handle* h);
+
+/* host pointers, copied.  wref (p*nz) | H (p*nz*nz) | q (p*nz) per phase; ref_du (p*n_g) dual reference window per
+ * phase in g-order; C (nh*nz), c (nh); term_idx (nx_term); relax0 (nh) 1 = row dropped at stage 0 (pmpc.py:293-294) */
+int tmpc_set_tables(tmpc_handle* h, const double* wref, const double* H, const double* q, const double* ref_du,
+                    const double* C, const double* c, const int32_t* term_idx, const int32_t* relax0);
+
+/* size the workspace for B instances, phase index <- 0, warm start <- reference (pmpc.py:858-865, 930-942) */
+int tmpc_reset(tmpc_handle* h, int64_t B);
+int tmpc_get_index(const tmpc_handle* h, int64_t* index);
+
+/* One batched Pmpc.step: X0_dev (B*nx) -> U0_dev (B*nu).  Optional outputs (may be NULL): W_dev (B*n_w) primal
+ * solution, LAM_dev (B*n_g) multipliers, G_dev (B*n_g) constraint values at the solution, status/iter/flags (B).
+ * Side effects as in the reference: index += 1, warm start <- shifted solution (pmpc.py:415-421, 867-906).
+ * Runs on `cuda_stream` (cudaStream_t, NULL = default) and returns after the SQP loop has finished. */
+int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, double* W_dev, double* LAM_dev,
+              double* G_dev, int32_t* status_dev, int32_t* iter_dev, int32_t* flags_dev, void* cuda_stream);
+/* same call with HOST buffers (pinned or pageable): H2D of X0, solve, D2H of the requested outputs */
+int tmpc_step_host(tmpc_handle* h, const double* X0_host, int64_t B, double* U0_host, double* W_host,
+                   double* LAM_host, double* G_host, int32_t* status_host, int32_t* iter_host, int32_t* flags_host);
+
+/* plant = model integrator: Xn_dev[b] = F(X_dev[b], U_dev[b])   (closed_loop_tools.py:102) */
+int tmpc_plant_step(tmpc_handle* h, const double* X_dev, const double* U_dev, int64_t B, double* Xn_dev,
+                    void* cuda_stream);
+
+/* per-step log tensors of the last tmpc_step, device pointers owned by the library, valid until the next call:
+ * f (B) objective, nAS (B) active inequality rows, nACtot (B) active-set changes vs the initial guess,
+ * nAC (B) stage-0 active-set changes vs the reference multipliers   (pmpc.py:815-856, sqp_method.py:203-219) */
+int tmpc_get_log(tmpc_handle* h, const double** f_dev, const int32_t** nAS_dev, const int32_t** nACtot_dev,
+                 const int32_t** nAC_dev);
+/* counters of the last tmpc_step: [0] SQP iterations summed over the batch, [1] kernel launches, [2] QP solves,
+ * [3] stage linearisations (instance*stage), [4] plain dynamics evaluations (instance*stage) in the line search */
+int tmpc_get_counters(const tmpc_handle* h, int64_t out[8]);
+/* duration in ms of the last step's kernels by kind (CUDA events on the launch stream): [0] linearise, [1] qp,
+ * [2] line search + convergence, [3] whole step */
+int tmpc_get_timing(const tmpc_handle* h, double out_ms[4]);
+
+/* host evaluation of the compiled model's one-interval map and derivatives (offline tuning only, not the solve
+ * path): n stages, order 0/1/2 -> xf (n*nx), S (n*nx*nz), T (n*nx*nz*nz) */
+int tmpc_stage_eval_host(int32_t n, const double* x, const double* u, int32_t order, double* xf, double* S,
+                         double* T);
+
+/* in-run FP64 FMA peak micro-benchmark on the handle's device: returns TFLOP/s (2 flops per DFMA) */
+int tmpc_fp64_peak(tmpc_handle* h, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,107 @@
+// CPU twin of the device routines -- TEST INFRASTRUCTURE ONLY (never loaded by the product package).
+// Compiles tunempc_b200/csrc/tmpc_core.cuh with g++ as a 1-lane sequential program (TM_NL = 1) and runs the same
+// SQP loop the CUDA host code runs, instance by instance.  Used by the CPU-only tests to check the algorithm
+// (stage linearisation, Riccati + dual active set QP, filter line search, convergence, shift) against the oracle
+// without a GPU; on the GPU box the same comparison runs against the real kernels.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "tmpc_core.cuh"
+
+extern "C" {
+
+void twin_model_info(int* nx, int* nu) { *nx = NX; *nu = NU; }
+
+// stage evaluation through the pair-wise integrator (same code path as tmpc_stage_eval_host)
+void twin_stage_eval(int n, const double* x, const double* u, int order, double* xf, double* S, double* T) {
+  for (int s = 0; s < n; ++s) {
+    const double* xs = x + (size_t)s * NX;
+    const double* us = u + (size_t)s * NU;
+    if (order == 0) {
+      double t1[NX], t2[NX], t3[NX];
+      tm_integrate<0>(xs, us, 0, 0, xf + (size_t)s * NX, t1, t2, t3);
+      continue;
+    }
+    for (int i = 0; i < NZ; ++i)
+      for (int j = i; j < NZ; ++j) {
+        if (order == 1 && j != i) continue;
+        double X[NX], Si[NX], Sj[NX], Tt[NX];
+        if (order == 1) tm_integrate<1>(xs, us, i, j, X, Si, Sj, Tt);
+        else tm_integrate<2>(xs, us, i, j, X, Si, Sj, Tt);
+        for (int a = 0; a < NX; ++a) {
+          xf[(size_t)s * NX + a] = X[a];
+          if (i == j) S[((size_t)s * NX + a) * NZ + i] = Si[a];
+          if (order == 2) {
+            T[(((size_t)s * NX + a) * NZ + i) * NZ + j] = Tt[a];
+            T[(((size_t)s * NX + a) * NZ + j) * NZ + i] = Tt[a];
+          }
+        }
+      }
+  }
+}
+
+// dims: N nh nxt p ; iopts: hessian_exact max_iter max_ls maxact ; dopts: tol lam_tresh beta reg_tol rho al_gamma
+int twin_step(const int* dims, const int* iopts, const double* dopts, const double* wref, const double* H,
+              const double* q, const double* ref_du, const double* C, const double* c, const int* term_idx,
+              const int* relax0, int phase, long long B, const double* X0, double* W, double* LAM, double* G,
+              int* status, int* iter, int* flags, double* fval, int* nAS, int* nACtot, int* nAC, double* Wsh,
+              double* Lsh, long long* counters_out) {
+  TmProb P;
+  P.N = dims[0]; P.nh = dims[1]; P.nxt = dims[2]; P.p = dims[3];
+  P.n_w = P.N * NZ + NX;
+  P.n_g = NX + P.N * (NX + P.nh) + P.nxt;
+  P.hessian_exact = iopts[0];
+  P.filter_cap = 64;
+  P.max_iter = iopts[1] < P.filter_cap - 1 ? iopts[1] : P.filter_cap - 1;
+  P.max_ls = iopts[2];
+  P.maxact = iopts[3];
+  P.tol = dopts[0]; P.lam_tresh = dopts[1]; P.beta = dopts[2]; P.reg_tol = dopts[3]; P.rho = dopts[4]; P.al_gamma = dopts[5];
+  P.wref = wref; P.H = H; P.q = q; P.ref_du = ref_du; P.C = C; P.c = c; P.term_idx = term_idx; P.relax0 = relax0;
+  TmState S;
+  memset(&S, 0, sizeof S);
+  S.B = B; S.phase = phase; S.X0 = X0; S.W = W; S.LAM = LAM; S.G = G;
+  S.status = status; S.iter = iter; S.flags = flags; S.fval = fval; S.nAS = nAS; S.nACtot = nACtot; S.nAC = nAC;
+  std::vector<double> D((size_t)B * P.n_w), LQ((size_t)B * P.n_g), LIN((size_t)B * P.N * TM_LSZ),
+      FILT((size_t)B * P.filter_cap * 2);
+  std::vector<int> nfilt(B), qpstat(B, 0), la(B), lb(B), lrel(B);
+  S.aswords = (P.N * P.nh + 31) / 32; if (S.aswords < 1) S.aswords = 1;
+  std::vector<unsigned> asinit((size_t)B * S.aswords);
+  unsigned long long counters[8] = {0};
+  int cnts[2] = {0, 0};
+  S.D = D.data(); S.LAMQ = LQ.data(); S.LIN = LIN.data(); S.FILT = FILT.data(); S.nfilt = nfilt.data();
+  S.qpstat = qpstat.data(); S.asinit = asinit.data(); S.counters = counters;
+  S.cnt_next = &cnts[0]; S.cnt_relin = &cnts[1]; S.list_relin = lrel.data();
+  const int per = P.hessian_exact ? TM_NPAIR : NZ;
+  std::vector<double> wsbuf(tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact));
+  TmQpWs ws;
+  tm_qpws_carve(wsbuf.data(), P.N, P.nh, P.nxt, P.maxact, ws);
+
+  for (long long i = 0; i < B; ++i) tm_prefilter(P, S, i);
+  for (long long i = 0; i < B; ++i) for (int k = 0; k < P.N; ++k) for (int pr = 0; pr < per; ++pr) tm_lin_task(P, S, i, k, pr, 0);
+  for (long long i = 0; i < B; ++i) tm_init(P, S, i);
+  std::vector<int>* cur = &la; std::vector<int>* nxt = &lb;
+  long long nact = B;
+  for (long long i = 0; i < B; ++i) la[i] = (int)i;
+  long long nqp = 0, nlin = B * P.N;
+  int guard = 0;
+  while (nact > 0) {
+    S.list_next = nxt->data();
+    cnts[0] = cnts[1] = 0;
+    for (long long s = 0; s < nact; ++s) tm_qp(P, S, (*cur)[s], ws);
+    for (long long s = 0; s < nact; ++s) for (int k = 0; k < P.N; ++k) for (int pr = 0; pr < per; ++pr) tm_lin_task(P, S, (*cur)[s], k, pr, 1);
+    for (long long s = 0; s < nact; ++s) tm_post(P, S, (*cur)[s]);
+    nqp += nact; nlin += nact * P.N;
+    const int nrel = cnts[1];
+    for (int s = 0; s < nrel; ++s) for (int k = 0; k < P.N; ++k) for (int pr = 0; pr < per; ++pr) tm_lin_task(P, S, lrel[s], k, pr, 0);
+    for (int s = 0; s < nrel; ++s) tm_conv(P, S, lrel[s]);
+    nlin += (long long)nrel * P.N;
+    std::swap(cur, nxt);
+    nact = cnts[0];
+    if (++guard > P.max_iter + 2) return 9;
+  }
+  for (long long i = 0; i < B; ++i) tm_shift(P, W + i * P.n_w, LAM + i * P.n_g, Wsh + i * P.n_w, Lsh + i * P.n_g);
+  if (counters_out) { counters_out[0] = (long long)counters[0]; counters_out[2] = nqp; counters_out[3] = nlin; counters_out[4] = (long long)counters[4]; }
+  return 0;
+}
+
+}  // extern "C"

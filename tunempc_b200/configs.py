@@ -1,0 +1,118 @@
+"""Model cards of the BASELINE.json configs, restated from the reference example scripts.
+
+Every constant cites the reference line it comes from.  Each card returns the sympy ODE (`OdeModel`),
+the economic stage cost l(x,u) as a sympy expression, the *linear* path constraints h(x,u) = C z + c >= 0
+(all non-AWE configs have linear h, so `preprocessing.input_formatting` (`tunempc/preprocessing.py:78-118`)
+would leave ns = 0), the OCP initial guess and the x0-perturbation scale of SURVEY.md section 8(d).
+"""
+from __future__ import annotations
+
+import numpy as np
+import sympy as sp
+
+from .modelgen import OdeModel
+
+
+def lq():
+    """examples/convex_lqr.py:40-46 -- discrete LQ system, indefinite stage cost, steady state 0."""
+    A = np.array([[-0.3319, 0.7595, 1.5399], [-0.3393, 0.1250, 0.4245], [-0.5090, 0.9388, 0.8864]])
+    B = np.array([[0.1060], [-1.3835], [-0.1496]])
+    Q = np.array([[-1.0029, -0.0896, 1.1050], [-0.0896, 1.6790, -0.5762], [1.1050, -0.5762, -0.4381]])
+    R = np.array([[0.6192]])
+    Nm = np.array([[-0.0420], [0.2112], [-0.2832]])
+    x = sp.symbols("x0:3")
+    u = sp.symbols("u0:1")
+    z = sp.Matrix(list(x) + list(u))
+    xdot = list(sp.Matrix(A) * sp.Matrix(x) + sp.Matrix(B) * sp.Matrix(u))
+    Hm = np.block([[Q, Nm], [Nm.T, R]])
+    cost = sp.Rational(1, 2) * (z.T * sp.Matrix(Hm) * z)[0, 0]
+    model = OdeModel("lq", x, u, xdot, discrete=True)
+    return dict(model=model, cost=cost, C=np.zeros((0, 4)), c=np.zeros(0),
+                w_guess=np.zeros(4), period=1, A=A, B=B, Q=Q, R=R, Nmat=Nm,
+                x0_scale=np.array([1.0, 1.0, 1.0]), N=10, term_idx=[0, 1, 2])
+
+
+def cstr():
+    """examples/cstr/cstr_model.py:34-168 -- CSTR, nx=4, nu=2, RK4 x 20 over 20 s, four input bounds."""
+    k10, k20, k30 = 1.287e12, 1.287e12, 9.043e9           # :41-43
+    E1, E2, E3 = -9758.3, -9758.3, -8560.0                # :44-46
+    DH_AB, DH_BC, DH_AD = 4.2, -11.0, -41.85              # :47-49
+    rho, Cp, kw, AR, VR = 0.9342, 3.01, 4032.0, 0.215, 10.0   # :50-54
+    mK, CPK, cA0, theta0 = 5.0, 2.0, 5.10, 104.9          # :55-58
+    rhoJ = 1e-1                                           # examples/cstr/main.py:57
+    cA, cB, th, thK = sp.symbols("cA cB theta thetaK")
+    Vd, QK = sp.symbols("Vdot QdotK")
+    k1 = k10 * sp.exp(E1 / (th + 273.15))                 # :68-74
+    k2 = k20 * sp.exp(E2 / (th + 273.15))
+    k3 = k30 * sp.exp(E3 / (th + 273.15))
+    xdot = [                                              # :82-91, divided by 3600 at :94
+        (Vd * (cA0 - cA) - k1 * cA - k3 * cA * cA) / 3600,
+        (-Vd * cB + k1 * cA - k2 * cB) / 3600,
+        (Vd * (theta0 - th) - 1.0 / (rho * Cp) * (k1 * cA * DH_AB + k2 * cB * DH_BC + k3 * cA * cA * DH_AD)
+         + kw * AR / (rho * Cp * VR) * (thK - th)) / 3600,
+        (1.0 / (mK * CPK) * (QK + kw * AR * (th - thK))) / 3600,
+    ]
+    cost = 100 * (-cB / cA0 + rhoJ * (1e-4 * (Vd - 14.19) ** 2 + 1e-4 * (QK + 1113.5) ** 2))  # :117-129
+    # h >= 0 (:154-159): Vdot-5, 35-Vdot, QdotK+9000, -QdotK
+    C = np.zeros((4, 6))
+    C[0, 4], C[1, 4], C[2, 5], C[3, 5] = 1.0, -1.0, 1.0, -1.0
+    c = np.array([-5.0, 35.0, 9000.0, 0.0])
+    model = OdeModel("cstr", (cA, cB, th, thK), (Vd, QK), xdot, rk_steps=20, tf=20.0)   # :62-64,97
+    w_guess = np.array([2.1402, 1.0903, 114.191, 112.9066, 14.19, -1113.5])               # :168
+    return dict(model=model, cost=cost, C=C, c=c, w_guess=w_guess, period=1, N=20,
+                term_idx=[0, 1, 2, 3])
+
+
+def unicycle():
+    """examples/unicycle/main.py:40-129 -- periodic unicycle, nx=4, nu=1, RK4 x 50 over T/N, p=N=30."""
+    rho_, v = 0.001, 1.0                                  # :46-47
+    T, Np = 5.0, 30                                       # :87-88,97-99
+    z_, y_, ez, ey = sp.symbols("z y ez ey")
+    uu = sp.symbols("u")
+    xdot = [                                              # :56-61
+        v * ez,
+        v * ey,
+        -uu * ey - rho_ * ez * (ez ** 2 + ey ** 2 - 1),
+        uu * ez - rho_ * ey * (ez ** 2 + ey ** 2 - 1),
+    ]
+    cost = uu ** 2 + z_ ** 2 + 5 * y_ ** 2                # :82
+    model = OdeModel("unicycle", (z_, y_, ez, ey), (uu,), xdot, rk_steps=50, tf=T / Np)  # :67
+    # analytic circular initial guess (:103-114)
+    om = 2 * np.pi / T
+    tg = np.arange(Np) * T / Np
+    guess = np.stack([np.sin(om * tg) / om, -np.cos(om * tg) / om, np.cos(om * tg), np.sin(om * tg),
+                      om * np.ones(Np)], axis=1)
+    return dict(model=model, cost=cost, C=np.zeros((0, 5)), c=np.zeros(0), w_guess=guess, period=Np, N=Np,
+                term_idx=[0, 1, 2])
+
+
+CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle}
+
+
+def make_problem(name, stage_F, N=None, hessian_approximation="exact"):
+    """Run the offline pipeline (tuning.py) for a config and return (MpcProblem, info).
+
+    `stage_F(x, u, order)` evaluates the compiled model's one-interval map and derivatives on the host
+    (product: `tunempc_b200.lib.ModelLib.stage_eval`; tests may pass the oracle's).  Mirrors what
+    `Tuner(f,l,h,p).solve_ocp(w0); convexify(); create_mpc('tuned', N)` hands to `Pmpc` (tunempc/tuner.py:90-199).
+    """
+    from . import tuning
+    from .problem import MpcProblem
+
+    cfg = CONFIGS[name]()
+    model = cfg["model"]
+    nx, nu = model.nx, model.nu
+    N = cfg["N"] if N is None else N
+    if cfg["period"] != 1:
+        raise NotImplementedError("periodic OCP tuning (p > 1) is not built yet")
+    cost_funs = tuning.lambdify_cost(model, cfg["cost"])
+    z, lam_d, lam_h = tuning.solve_steady_state(stage_F, cost_funs, cfg["C"], cfg["c"], cfg["w_guess"], nx)
+    S = tuning.sensitivities(stage_F, cost_funs, cfg["C"], z, lam_d, lam_h, nx)
+    Hc, dH = tuning.convexify_dare(S["A"][0], S["B"][0], S["H"][0], C_As=S["C_As"][0], scale=z)
+    pb = MpcProblem(name=name, nx=nx, nu=nu, N=N, p=1, wref=z[None, :].copy(), H=Hc[None], q=S["q"][0][None, :],
+                    C=cfg["C"], c=cfg["c"], lam_h_ref=lam_h[None, :], lam_dyn_ref=np.zeros((1, nx)),
+                    term_idx=list(cfg["term_idx"]), S_A=np.array(S["A"]), S_B=np.array(S["B"]),
+                    hessian_approximation=hessian_approximation)
+    info = {"z_ss": z, "lam_dyn_ocp": lam_d, "lam_h_ocp": lam_h, "H_ocp": S["H"][0], "Hc": Hc,
+            "eig_H": np.linalg.eigvalsh(S["H"][0]), "eig_Hc": np.linalg.eigvalsh(Hc), "cfg": cfg}
+    return pb, info

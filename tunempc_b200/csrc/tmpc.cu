@@ -1,0 +1,542 @@
+// tmpc.cu -- kernels, SQP host loop and the C ABI (include/tmpc.h) of libtmpc_<model>.so.   sm_100a, fp64.
+//
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC \
+//        -DTMPC_MODEL_HEADER='"gen/model_cstr.h"' -Iinclude -Itunempc_b200/csrc tmpc.cu -o libtmpc_cstr.so
+//
+// Kernel inventory:
+//   k_lin      K1  one thread per (instance, stage, sensitivity pair): RK4 + 1st/2nd-order sensitivities, exact
+//                  Lagrangian-Hessian block lam' d2F contracted in registers; FP64-FMA bound
+//   k_qp       K3+K4  one warp per instance: Riccati base factorisation in shared memory + dual active set
+//   k_post     K5+K2  one warp per instance: filter line search, primal/dual update, KKT residual, convergence
+//   k_conv     K2  convergence for instances that were re-linearised after a damped step
+//   k_prefilter, k_init, k_shift, k_gather, k_plant   K6 bookkeeping
+// There is no CPU solve path in this library: if the device is unusable every entry point returns an error.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "tmpc.h"
+#include "tmpc_core.cuh"
+
+#define QP_WARPS 4          /* warps (instances) per CTA in the warp-per-instance kernels */
+#define LIN_THREADS 128
+
+struct tmpc_handle {
+  int device = 0;
+  tmpc_dims dims{};
+  tmpc_opts opts{};
+  TmProb P{};
+  TmState S{};
+  int64_t cap = 0;           // allocated instance capacity
+  int64_t index = 0;         // Pmpc.__index
+  bool tables_set = false;
+  std::string err;
+  std::vector<void*> tab_allocs, ws_allocs;
+  int *list_a = nullptr, *list_b = nullptr, *cnts = nullptr;   // cnts[0] next, cnts[1] relin
+  double *Wsh = nullptr, *Lsh = nullptr;                       // shift targets
+  double* X0buf = nullptr;                                     // device staging for tmpc_step_host
+  int64_t counters_host[8] = {0};
+  double timing_ms[4] = {0};
+  cudaEvent_t ev[8];
+  bool ev_ok = false;
+  size_t qp_smem = 0;
+};
+
+static int fail(tmpc_handle* h, const char* what, cudaError_t e) {
+  if (h) h->err = std::string(what) + ": " + cudaGetErrorString(e);
+  return 1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, #call, e_); } while (0)
+
+// ------------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LIN_THREADS) k_lin(TmProb P, TmState S, const int* list, const int* cnt_dev, int cnt,
+                                                     int trial, int per) {
+  if (cnt_dev) cnt = *cnt_dev;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)cnt * P.N * per;
+  if (t >= total) return;
+  const int pr = (int)(t % per);
+  const int k = (int)((t / per) % P.N);
+  const int64_t slot = t / ((int64_t)per * P.N);
+  const int64_t inst = list ? list[slot] : slot;
+  tm_lin_task(P, S, inst, k, pr, trial);
+}
+
+__global__ void k_prefilter(TmProb P, TmState S) {
+  const int64_t inst = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (inst >= S.B) return;
+  tm_prefilter(P, S, inst);
+}
+
+__global__ void k_init(TmProb P, TmState S) {
+  const int64_t inst = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (inst >= S.B) return;
+  tm_init(P, S, inst);
+}
+
+__global__ void __launch_bounds__(QP_WARPS * 32) k_qp(TmProb P, TmState S, const int* list, int cnt) {
+  extern __shared__ double smem[];
+  const int wid = threadIdx.x / 32;
+  const int64_t slot = (int64_t)blockIdx.x * QP_WARPS + wid;
+  if (slot >= cnt) return;
+  const int64_t inst = list ? list[slot] : slot;
+  const size_t per = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact);
+  TmQpWs ws;
+  tm_qpws_carve(smem + (size_t)wid * per, P.N, P.nh, P.nxt, P.maxact, ws);
+  tm_qp(P, S, inst, ws);
+}
+
+__global__ void __launch_bounds__(QP_WARPS * 32) k_post(TmProb P, TmState S, const int* list, int cnt) {
+  const int64_t slot = (int64_t)blockIdx.x * QP_WARPS + threadIdx.x / 32;
+  if (slot >= cnt) return;
+  const int64_t inst = list ? list[slot] : slot;
+  tm_post(P, S, inst);
+}
+
+__global__ void __launch_bounds__(QP_WARPS * 32) k_conv(TmProb P, TmState S, const int* list, const int* cnt_dev) {
+  const int64_t slot = (int64_t)blockIdx.x * QP_WARPS + threadIdx.x / 32;
+  if (slot >= *cnt_dev) return;
+  tm_conv(P, S, list[slot]);
+}
+
+__global__ void k_shift(TmProb P, TmState S, double* Ws, double* Ls) {
+  const int64_t inst = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (inst >= S.B) return;
+  tm_shift(P, S.W + inst * P.n_w, S.LAM + inst * P.n_g, Ws + inst * P.n_w, Ls + inst * P.n_g);
+}
+
+__global__ void k_gather_u0(TmProb P, TmState S, double* U0) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S.B * NU) return;
+  U0[t] = S.W[(t / NU) * P.n_w + NX + (t % NU)];
+}
+
+__global__ void k_bcast(double* dst, const double* row, int64_t B, int n) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * n) return;
+  dst[t] = row[t % n];
+}
+
+__global__ void k_plant(const double* X, const double* U, int64_t B, double* Xn) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[NX], u[NU], xf[NX], t1[NX], t2[NX], t3[NX];
+#pragma unroll
+  for (int a = 0; a < NX; ++a) x[a] = X[b * NX + a];
+#pragma unroll
+  for (int a = 0; a < NU; ++a) u[a] = U[b * NU + a];
+  tm_integrate<0>(x, u, 0, 0, xf, t1, t2, t3);
+#pragma unroll
+  for (int a = 0; a < NX; ++a) Xn[b * NX + a] = xf[a];
+}
+
+// dependent-chain-free DFMA loop: 8 independent accumulators per thread
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+void tmpc_default_opts(tmpc_opts* o) {
+  o->hessian_exact = 1;
+  o->max_iter = 2000;
+  o->max_ls_iter = 300;
+  o->tol = 1e-6;
+  o->lam_tresh = 1e-8;
+  o->ls_step_factor = 0.8;
+  o->reg_tol = 1e-8;
+  o->term_penalty = 1.0;
+}
+
+const char* tmpc_model_info(int32_t* nx, int32_t* nu, int32_t* rk_steps, double* dt) {
+  if (nx) *nx = NX;
+  if (nu) *nu = NU;
+  if (rk_steps) *rk_steps = TMPC_DISCRETE ? 0 : TMPC_RK_STEPS;
+  if (dt) *dt = TMPC_RK_DT;
+  return TMPC_MODEL_NAME;
+}
+
+const char* tmpc_last_error(const tmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts, int device) {
+  if (!out || !dims) return 1;
+  *out = nullptr;
+  tmpc_handle* h = new tmpc_handle();
+  h->device = device;
+  h->dims = *dims;
+  if (opts) h->opts = *opts; else tmpc_default_opts(&h->opts);
+  if (dims->nx != NX || dims->nu != NU) {
+    fprintf(stderr, "tmpc_create: dims (%d,%d) do not match compiled model %s (%d,%d)\n", dims->nx, dims->nu,
+            TMPC_MODEL_NAME, NX, NU);
+    delete h;
+    return 2;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device >= ndev) {
+    fprintf(stderr, "tmpc_create: no usable CUDA device %d (%s) -- this library has no CPU path\n", device,
+            e != cudaSuccess ? cudaGetErrorString(e) : "index out of range");
+    delete h;
+    return 3;
+  }
+  cudaSetDevice(device);
+  TmProb& P = h->P;
+  P.N = dims->N; P.nh = dims->nh; P.nxt = dims->nx_term; P.p = dims->p;
+  P.n_w = dims->N * NZ + NX;
+  P.n_g = NX + dims->N * (NX + dims->nh) + dims->nx_term;
+  P.hessian_exact = h->opts.hessian_exact;
+  P.filter_cap = 64;
+  P.max_iter = h->opts.max_iter < P.filter_cap - 1 ? h->opts.max_iter : P.filter_cap - 1;
+  P.max_ls = h->opts.max_ls_iter;
+  P.maxact = 32;
+  if (P.maxact < P.nxt + 4) P.maxact = P.nxt + 4;
+  P.tol = h->opts.tol; P.lam_tresh = h->opts.lam_tresh; P.beta = h->opts.ls_step_factor;
+  P.reg_tol = h->opts.reg_tol; P.rho = h->opts.term_penalty;
+  h->qp_smem = QP_WARPS * tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact) * sizeof(double);
+  if (h->qp_smem > 227 * 1024) {
+    fprintf(stderr, "tmpc_create: QP workspace %zu B exceeds shared memory\n", h->qp_smem);
+    delete h;
+    return 4;
+  }
+  if (cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem) != cudaSuccess) {
+    fprintf(stderr, "tmpc_create: cannot reserve %zu B of shared memory\n", h->qp_smem);
+    delete h;
+    return 4;
+  }
+  for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
+  h->ev_ok = true;
+  *out = h;
+  return 0;
+}
+
+static void free_list(std::vector<void*>& v) {
+  for (void* p : v) cudaFree(p);
+  v.clear();
+}
+
+void tmpc_destroy(tmpc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  free_list(h->tab_allocs);
+  free_list(h->ws_allocs);
+  if (h->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
+  delete h;
+}
+
+template <typename T>
+static int upload(tmpc_handle* h, std::vector<void*>& owner, const T* src, size_t n, const T** dst) {
+  T* d = nullptr;
+  CK(cudaMalloc(&d, (n ? n : 1) * sizeof(T)));
+  owner.push_back(d);
+  if (n) CK(cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = d;
+  return 0;
+}
+
+int tmpc_set_tables(tmpc_handle* h, const double* wref, const double* H, const double* q, const double* ref_du,
+                    const double* C, const double* c, const int32_t* term_idx, const int32_t* relax0) {
+  if (!h) return 1;
+  cudaSetDevice(h->device);
+  free_list(h->tab_allocs);
+  TmProb& P = h->P;
+  // symmetrise H on the way in (the reference's H blocks are symmetric, convexifier.py:206)
+  std::vector<double> Hs((size_t)P.p * NZ * NZ);
+  for (int ph = 0; ph < P.p; ++ph)
+    for (int i = 0; i < NZ; ++i)
+      for (int j = 0; j < NZ; ++j)
+        Hs[((size_t)ph * NZ + i) * NZ + j] = 0.5 * (H[((size_t)ph * NZ + i) * NZ + j] + H[((size_t)ph * NZ + j) * NZ + i]);
+  if (upload(h, h->tab_allocs, wref, (size_t)P.p * NZ, &P.wref)) return 1;
+  if (upload(h, h->tab_allocs, Hs.data(), Hs.size(), &P.H)) return 1;
+  if (upload(h, h->tab_allocs, q, (size_t)P.p * NZ, &P.q)) return 1;
+  if (upload(h, h->tab_allocs, ref_du, (size_t)P.p * P.n_g, &P.ref_du)) return 1;
+  if (upload(h, h->tab_allocs, C, (size_t)P.nh * NZ, &P.C)) return 1;
+  if (upload(h, h->tab_allocs, c, (size_t)P.nh, &P.c)) return 1;
+  if (upload(h, h->tab_allocs, (const int*)term_idx, (size_t)P.nxt, &P.term_idx)) return 1;
+  if (upload(h, h->tab_allocs, (const int*)relax0, (size_t)P.nh, &P.relax0)) return 1;
+  h->tables_set = true;
+  return 0;
+}
+
+template <typename T>
+static int dalloc(tmpc_handle* h, T** p, size_t n) {
+  CK(cudaMalloc(p, (n ? n : 1) * sizeof(T)));
+  h->ws_allocs.push_back(*p);
+  return 0;
+}
+
+static int ensure_capacity(tmpc_handle* h, int64_t B) {
+  if (B <= h->cap) return 0;
+  free_list(h->ws_allocs);
+  h->cap = 0;
+  TmProb& P = h->P;
+  TmState& S = h->S;
+  S.aswords = (P.N * P.nh + 31) / 32;
+  if (S.aswords < 1) S.aswords = 1;
+  const size_t b = (size_t)B;
+  if (dalloc(h, &S.W, b * P.n_w) || dalloc(h, &S.LAM, b * P.n_g) || dalloc(h, &S.D, b * P.n_w) ||
+      dalloc(h, &S.LAMQ, b * P.n_g) || dalloc(h, &S.LIN, b * P.N * TM_LSZ) || dalloc(h, &S.G, b * P.n_g) ||
+      dalloc(h, &S.FILT, b * P.filter_cap * 2) || dalloc(h, &S.fval, b) || dalloc(h, &S.nfilt, b) ||
+      dalloc(h, &S.iter, b) || dalloc(h, &S.status, b) || dalloc(h, &S.flags, b) || dalloc(h, &S.nAS, b) ||
+      dalloc(h, &S.nACtot, b) || dalloc(h, &S.nAC, b) || dalloc(h, &S.qpstat, b) ||
+      dalloc(h, &S.asinit, b * S.aswords) || dalloc(h, &h->list_a, b) || dalloc(h, &h->list_b, b) ||
+      dalloc(h, &S.list_relin, b) || dalloc(h, &h->cnts, 4) || dalloc(h, &S.counters, 8) ||
+      dalloc(h, &h->Wsh, b * P.n_w) || dalloc(h, &h->Lsh, b * P.n_g) || dalloc(h, &h->X0buf, b * NX))
+    return 1;
+  h->cap = B;
+  return 0;
+}
+
+int tmpc_reset(tmpc_handle* h, int64_t B) {
+  if (!h) return 1;
+  if (!h->tables_set) { h->err = "tmpc_reset: tables not set"; return 1; }
+  cudaSetDevice(h->device);
+  if (ensure_capacity(h, B)) return 1;
+  h->index = 0;
+  h->S.B = B;
+  TmProb& P = h->P;
+  // w0 <- reference window at phase 0, lam0 <- ref_du[0]   (pmpc.py:930-942)
+  std::vector<double> w0(P.n_w);
+  std::vector<double> wr((size_t)P.p * NZ);
+  CK(cudaMemcpy(wr.data(), P.wref, wr.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < P.N; ++k)
+    for (int i = 0; i < NZ; ++i) w0[k * NZ + i] = wr[(size_t)(k % P.p) * NZ + i];
+  for (int i = 0; i < NX; ++i) w0[P.N * NZ + i] = wr[(size_t)(P.N % P.p) * NZ + i];
+  CK(cudaMemcpy(h->Wsh, w0.data(), P.n_w * sizeof(double), cudaMemcpyHostToDevice));
+  const int64_t nw = B * P.n_w, ng = B * P.n_g;
+  k_bcast<<<(unsigned)((nw + 255) / 256), 256>>>(h->S.W, h->Wsh, B, P.n_w);
+  CK(cudaDeviceSynchronize());   // Wsh row is overwritten below only by later steps; keep ordering simple
+  k_bcast<<<(unsigned)((ng + 255) / 256), 256>>>(h->S.LAM, P.ref_du, B, P.n_g);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int tmpc_get_index(const tmpc_handle* h, int64_t* index) {
+  if (!h || !index) return 1;
+  *index = h->index;
+  return 0;
+}
+
+int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, double* W_dev, double* LAM_dev,
+              double* G_dev, int32_t* status_dev, int32_t* iter_dev, int32_t* flags_dev, void* cuda_stream) {
+  if (!h) return 1;
+  if (!h->tables_set || h->cap < B || h->S.B != B) { h->err = "tmpc_step: call tmpc_reset(B) first"; return 1; }
+  cudaSetDevice(h->device);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  TmProb& P = h->P;
+  TmState& S = h->S;
+  S.X0 = X0_dev;
+  S.phase = (int)(h->index % P.p);                           // pmpc.py:377
+  S.list_next = h->list_a;
+  S.cnt_next = h->cnts;
+  S.cnt_relin = h->cnts + 1;
+  const int per = P.hessian_exact ? TM_NPAIR : NZ;
+  int64_t launches = 0, n_qp = 0, n_lin = 0;
+  float ms_lin = 0, ms_qp = 0, ms_post = 0, ms;
+  const unsigned wblocks = (unsigned)((B + QP_WARPS - 1) / QP_WARPS);
+  auto lin_grid = [&](int64_t cnt) { return (unsigned)((cnt * P.N * per + LIN_THREADS - 1) / LIN_THREADS); };
+
+  CK(cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long), st));
+  CK(cudaEventRecord(h->ev[6], st));
+  k_prefilter<<<wblocks, QP_WARPS * 32, 0, st>>>(P, S);
+  CK(cudaEventRecord(h->ev[0], st));
+  k_lin<<<lin_grid(B), LIN_THREADS, 0, st>>>(P, S, nullptr, nullptr, (int)B, 0, per);
+  CK(cudaEventRecord(h->ev[1], st));
+  k_init<<<wblocks, QP_WARPS * 32, 0, st>>>(P, S);
+  CK(cudaGetLastError());
+  launches += 3; n_lin += B * P.N;
+  CK(cudaEventSynchronize(h->ev[1]));
+  CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); ms_lin += ms;
+
+  const int* cur = nullptr;   // nullptr = identity list (all instances)
+  int64_t nact = B;
+  int hc[2];
+  int iter_guard = 0;
+  while (nact > 0) {
+    const unsigned wb = (unsigned)((nact + QP_WARPS - 1) / QP_WARPS);
+    S.list_next = (cur == h->list_a) ? h->list_b : h->list_a;
+    CK(cudaMemsetAsync(h->cnts, 0, 2 * sizeof(int), st));
+    CK(cudaEventRecord(h->ev[0], st));
+    k_qp<<<wb, QP_WARPS * 32, h->qp_smem, st>>>(P, S, cur, (int)nact);
+    CK(cudaEventRecord(h->ev[1], st));
+    k_lin<<<lin_grid(nact), LIN_THREADS, 0, st>>>(P, S, cur, nullptr, (int)nact, 1, per);
+    CK(cudaEventRecord(h->ev[2], st));
+    k_post<<<wb, QP_WARPS * 32, 0, st>>>(P, S, cur, (int)nact);
+    CK(cudaEventRecord(h->ev[3], st));
+    CK(cudaGetLastError());
+    launches += 3; n_qp += nact; n_lin += nact * P.N;
+    CK(cudaMemcpyAsync(hc, h->cnts, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); ms_qp += ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); ms_lin += ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); ms_post += ms;
+    if (hc[1] > 0) {   // damped steps: re-linearise at the accepted point, then test convergence
+      CK(cudaEventRecord(h->ev[0], st));
+      k_lin<<<lin_grid(hc[1]), LIN_THREADS, 0, st>>>(P, S, S.list_relin, nullptr, hc[1], 0, per);
+      CK(cudaEventRecord(h->ev[1], st));
+      k_conv<<<(unsigned)((hc[1] + QP_WARPS - 1) / QP_WARPS), QP_WARPS * 32, 0, st>>>(P, S, S.list_relin, S.cnt_relin);
+      CK(cudaEventRecord(h->ev[2], st));
+      CK(cudaGetLastError());
+      launches += 2; n_lin += (int64_t)hc[1] * P.N;
+      CK(cudaMemcpyAsync(hc, h->cnts, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); ms_lin += ms;
+      CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); ms_post += ms;
+    }
+    cur = S.list_next;
+    nact = hc[0];
+    if (++iter_guard > P.max_iter + 2) { h->err = "tmpc_step: iteration guard tripped"; return 1; }
+  }
+  // outputs, then the warm-start shift (pmpc.py:410-423)
+  const size_t b = (size_t)B;
+  if (U0_dev) { k_gather_u0<<<(unsigned)((B * NU + 255) / 256), 256, 0, st>>>(P, S, U0_dev); ++launches; }
+  if (W_dev) CK(cudaMemcpyAsync(W_dev, S.W, b * P.n_w * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (LAM_dev) CK(cudaMemcpyAsync(LAM_dev, S.LAM, b * P.n_g * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (G_dev) CK(cudaMemcpyAsync(G_dev, S.G, b * P.n_g * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (status_dev) CK(cudaMemcpyAsync(status_dev, S.status, b * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (iter_dev) CK(cudaMemcpyAsync(iter_dev, S.iter, b * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (flags_dev) CK(cudaMemcpyAsync(flags_dev, S.flags, b * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  k_shift<<<wblocks, QP_WARPS * 32, 0, st>>>(P, S, h->Wsh, h->Lsh);
+  ++launches;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev[7], st));
+  unsigned long long cnt_host[8];
+  CK(cudaMemcpyAsync(cnt_host, S.counters, sizeof cnt_host, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  { double* t = S.W; S.W = h->Wsh; h->Wsh = t; }
+  { double* t = S.LAM; S.LAM = h->Lsh; h->Lsh = t; }
+  h->index += 1;                                             // pmpc.py:415
+  CK(cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]));
+  h->timing_ms[0] = ms_lin; h->timing_ms[1] = ms_qp; h->timing_ms[2] = ms_post; h->timing_ms[3] = ms;
+  h->counters_host[0] = (int64_t)cnt_host[0];
+  h->counters_host[1] = launches;
+  h->counters_host[2] = n_qp;
+  h->counters_host[3] = n_lin;
+  h->counters_host[4] = (int64_t)cnt_host[4];
+  return 0;
+}
+
+int tmpc_step_host(tmpc_handle* h, const double* X0_host, int64_t B, double* U0_host, double* W_host,
+                   double* LAM_host, double* G_host, int32_t* status_host, int32_t* iter_host, int32_t* flags_host) {
+  if (!h) return 1;
+  if (h->cap < B) { h->err = "tmpc_step_host: call tmpc_reset(B) first"; return 1; }
+  cudaSetDevice(h->device);
+  TmProb& P = h->P;
+  const size_t b = (size_t)B;
+  CK(cudaMemcpy(h->X0buf, X0_host, b * NX * sizeof(double), cudaMemcpyHostToDevice));
+  // the solution lives in S.W / S.LAM until the shift swaps buffers: copy out of the pre-swap buffers
+  double *Wsol = h->S.W, *Lsol = h->S.LAM;
+  if (tmpc_step(h, h->X0buf, B, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) return 1;
+  // after the swap the solution buffers are h->Wsh / h->Lsh (== Wsol / Lsol)
+  if (U0_host) CK(cudaMemcpy2D(U0_host, NU * sizeof(double), Wsol + NX, P.n_w * sizeof(double), NU * sizeof(double), b,
+                               cudaMemcpyDeviceToHost));
+  if (W_host) CK(cudaMemcpy(W_host, Wsol, b * P.n_w * sizeof(double), cudaMemcpyDeviceToHost));
+  if (LAM_host) CK(cudaMemcpy(LAM_host, Lsol, b * P.n_g * sizeof(double), cudaMemcpyDeviceToHost));
+  if (G_host) CK(cudaMemcpy(G_host, h->S.G, b * P.n_g * sizeof(double), cudaMemcpyDeviceToHost));
+  if (status_host) CK(cudaMemcpy(status_host, h->S.status, b * sizeof(int), cudaMemcpyDeviceToHost));
+  if (iter_host) CK(cudaMemcpy(iter_host, h->S.iter, b * sizeof(int), cudaMemcpyDeviceToHost));
+  if (flags_host) CK(cudaMemcpy(flags_host, h->S.flags, b * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int tmpc_plant_step(tmpc_handle* h, const double* X_dev, const double* U_dev, int64_t B, double* Xn_dev,
+                    void* cuda_stream) {
+  if (!h) return 1;
+  cudaSetDevice(h->device);
+  k_plant<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(X_dev, U_dev, B, Xn_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int tmpc_get_log(tmpc_handle* h, const double** f_dev, const int32_t** nAS_dev, const int32_t** nACtot_dev,
+                 const int32_t** nAC_dev) {
+  if (!h) return 1;
+  if (f_dev) *f_dev = h->S.fval;
+  if (nAS_dev) *nAS_dev = h->S.nAS;
+  if (nACtot_dev) *nACtot_dev = h->S.nACtot;
+  if (nAC_dev) *nAC_dev = h->S.nAC;
+  return 0;
+}
+
+int tmpc_get_counters(const tmpc_handle* h, int64_t out[8]) {
+  if (!h) return 1;
+  memcpy(out, h->counters_host, sizeof h->counters_host);
+  return 0;
+}
+
+int tmpc_get_timing(const tmpc_handle* h, double out_ms[4]) {
+  if (!h) return 1;
+  memcpy(out_ms, h->timing_ms, sizeof h->timing_ms);
+  return 0;
+}
+
+int tmpc_stage_eval_host(int32_t n, const double* x, const double* u, int32_t order, double* xf, double* S, double* T) {
+  for (int s = 0; s < n; ++s) {
+    const double* xs = x + (size_t)s * NX;
+    const double* us = u + (size_t)s * NU;
+    if (order == 0) {
+      double t1[NX], t2[NX], t3[NX];
+      tm_integrate<0>(xs, us, 0, 0, xf + (size_t)s * NX, t1, t2, t3);
+      continue;
+    }
+    for (int i = 0; i < NZ; ++i)
+      for (int j = i; j < NZ; ++j) {
+        if (order == 1 && j != i) continue;
+        double X[NX], Si[NX], Sj[NX], Tt[NX];
+        if (order == 1) tm_integrate<1>(xs, us, i, j, X, Si, Sj, Tt);
+        else tm_integrate<2>(xs, us, i, j, X, Si, Sj, Tt);
+        for (int a = 0; a < NX; ++a) {
+          xf[(size_t)s * NX + a] = X[a];
+          if (i == j) S[((size_t)s * NX + a) * NZ + i] = Si[a];
+          if (order == 2) {
+            T[(((size_t)s * NX + a) * NZ + i) * NZ + j] = Tt[a];
+            T[(((size_t)s * NX + a) * NZ + j) * NZ + i] = Tt[a];
+          }
+        }
+      }
+  }
+  return 0;
+}
+
+int tmpc_fp64_peak(tmpc_handle* h, double* tflops) {
+  if (!h || !tflops) return 1;
+  cudaSetDevice(h->device);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double* out = nullptr;
+  CK(cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)));
+  k_fp64_peak<<<blocks, threads>>>(out, 1024);
+  CK(cudaDeviceSynchronize());
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(h->ev[4]));
+    k_fp64_peak<<<blocks, threads>>>(out, iters);
+    CK(cudaEventRecord(h->ev[5]));
+    CK(cudaEventSynchronize(h->ev[5]));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaFree(out);
+  *tflops = best;
+  return 0;
+}
+
+}  // extern "C"

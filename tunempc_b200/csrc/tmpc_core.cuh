@@ -1,0 +1,1155 @@
+// tmpc_core.cuh -- per-instance device routines of the batched tuned-MPC feedback solve (fp64).
+//
+// Everything here is written from scratch for this repository; the reference (jdeschut/tunempc) has no native
+// or GPU code on this path.  What each routine replaces in the reference's Python:
+//   tm_lin_pair      jacg_fun / H_fun evaluations through the RK4 integrator   tunempc/sqp_method.py:152,159,330
+//   tm_qp_solve      conic('qpoases') QP solve                                 tunempc/sqp_method.py:158-168
+//   tm_post          __linesearch (filter) + w/lam update                      tunempc/sqp_method.py:171-177,289-325
+//   tm_conv          __check_convergence + __postprocessing stats              tunempc/sqp_method.py:240-287,185-221
+//   tm_init          k = 0 bookkeeping of __check_convergence, __prefilter_lam_g   :223-238,248-261
+//   tm_shift         Pmpc.__shift_initial_guess                                tunempc/pmpc.py:867-906
+//
+// Execution model: one WARP per instance for the sequential parts (QP, line search, convergence), one THREAD per
+// (instance, stage, sensitivity pair) for the linearisation.  The warp routines are written against
+// TM_LANE / TM_NL / TM_SYNC so that the same source compiles as a 1-lane sequential program with g++ for the
+// CPU twin used by the CPU-only tests (tests/twin); that twin is test infrastructure, not a product path.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include TMPC_MODEL_HEADER
+
+#ifdef __CUDACC__
+#define TM_HD __host__ __device__ __forceinline__
+#define TM_HDN __host__ __device__ __noinline__
+#else
+#define TM_HD static inline
+#define TM_HDN static
+#endif
+
+#ifdef __CUDA_ARCH__
+#define TM_LANE ((int)(threadIdx.x & 31))
+#define TM_NL 32
+#define TM_SYNC() __syncwarp()
+__device__ __forceinline__ double tm_wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double tm_wmax(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int tm_wsumi(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// arg-min over the warp: returns the smallest value and its payload (ties: smallest payload)
+__device__ __forceinline__ void tm_wargmin(double& v, int& id) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, id, o);
+    if (ov < v || (ov == v && oi < id)) { v = ov; id = oi; }
+  }
+}
+__device__ __forceinline__ int tm_wany(int p) { return __any_sync(0xffffffffu, p); }
+#else
+#define TM_LANE 0
+#define TM_NL 1
+#define TM_SYNC() ((void)0)
+TM_HD double tm_wsum(double v) { return v; }
+TM_HD double tm_wmax(double v) { return v; }
+TM_HD int tm_wsumi(int v) { return v; }
+TM_HD void tm_wargmin(double&, int&) {}
+TM_HD int tm_wany(int p) { return p; }
+#endif
+
+#define NX TMPC_NX
+#define NU TMPC_NU
+#define NZ TMPC_NZ
+#define TM_NPAIR (NZ * (NZ + 1) / 2)
+#define TM_LSZ (NX + NX * NZ + TM_NPAIR)   /* per-stage linearisation record: xf | S row-major nx*nz | W packed i<=j */
+#define TM_INF 1e300
+
+// ---------------------------------------------------------------------------------------------------------------
+// problem constants and per-batch state (plain pointers; device memory in the product, malloc in the twin)
+// ---------------------------------------------------------------------------------------------------------------
+struct TmProb {
+  int N, nh, nxt, p, n_w, n_g;
+  int hessian_exact, max_iter, max_ls, filter_cap, maxact;
+  double tol, lam_tresh, beta, reg_tol, rho, al_gamma;
+  const double *wref, *H, *q, *ref_du, *C, *c;   // wref p*nz | H p*nz*nz (symmetric) | q p*nz | ref_du p*n_g | C nh*nz | c nh
+  const int *term_idx, *relax0;
+};
+
+struct TmState {
+  int64_t B;
+  int phase;              // index mod p of this step
+  const double* X0;       // B*nx
+  double *W, *LAM;        // B*n_w, B*n_g   current iterate (warm start before the step, solution after)
+  double *D, *LAMQ;       // QP step and QP multipliers
+  double* LIN;            // B*N*TM_LSZ
+  double* G;              // B*n_g constraint values at the last evaluated point
+  double* FILT;           // B*filter_cap*2
+  double* fval;           // B
+  int *nfilt, *iter, *status, *flags, *nAS, *nACtot, *nAC;
+  int* qpstat;            // B: result of the last QP (0 ok)
+  unsigned* asinit;       // B*aswords bitmask of initially active inequality rows
+  int aswords;
+  int *list_next, *cnt_next, *list_relin, *cnt_relin;
+  unsigned long long* counters;   // [0] iterations [2] qp solves [3] stage linearisations [4] ls dynamics evals
+};
+
+TM_HD int tm_gdyn(const TmProb& P, int k) { return NX + k * (NX + P.nh); }
+TM_HD int tm_gh(const TmProb& P, int k) { return NX + k * (NX + P.nh) + NX; }
+TM_HD int tm_gterm(const TmProb& P) { return NX + P.N * (NX + P.nh); }
+
+TM_HD void tm_pair_ij(int pr, int& i, int& j) {   // packed upper-triangular index -> (i<=j), row-major
+  int r = 0, rem = pr;
+  while (rem >= NZ - r) { rem -= NZ - r; ++r; }
+  i = r; j = r + rem;
+}
+TM_HD int tm_pair_idx(int i, int j) {             // requires i<=j
+  return i * NZ - i * (i - 1) / 2 + (j - i);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1: stage linearisation.  One call = one (stage, pair (i,j)) task: integrates x, s_i = dx/dz_i, s_j, t_ij = d2x/dz_i dz_j
+// through RK4 (or one map evaluation for a discrete model).  ORDER 0: value; 1: + s_i; 2: + s_j and t_ij.
+// ---------------------------------------------------------------------------------------------------------------
+template <int ORDER>
+TM_HD void tm_rhs(const double* X, const double* u, const double* Si, const double* Sj, const double* T, int i, int j,
+                  double* k, double* dki, double* dkj, double* ddk) {
+  if (ORDER == 0) { tmpc_ode(X, u, k); return; }
+  double J[NX * NZ];
+  double Hn[TMPC_NHESS > 0 ? TMPC_NHESS : 1];
+  if (ORDER == 1) tmpc_ode_jac(X, u, k, J); else tmpc_ode_d2(X, u, k, J, Hn);
+  double vi[NZ], vj[NZ];
+#pragma unroll
+  for (int a = 0; a < NX; ++a) { vi[a] = Si[a]; vj[a] = (ORDER == 2) ? Sj[a] : 0.0; }
+#pragma unroll
+  for (int b = 0; b < NU; ++b) { vi[NX + b] = (i == NX + b) ? 1.0 : 0.0; vj[NX + b] = (j == NX + b) ? 1.0 : 0.0; }
+#pragma unroll
+  for (int a = 0; a < NX; ++a) {
+    double s = 0.0;
+#pragma unroll
+    for (int b = 0; b < NZ; ++b) s += J[a * NZ + b] * vi[b];
+    dki[a] = s;
+  }
+  if (ORDER == 2) {
+#pragma unroll
+    for (int a = 0; a < NX; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) s += J[a * NZ + b] * vj[b];
+      dkj[a] = s;
+    }
+    tmpc_ode_bilin(Hn, vi, vj, ddk);
+#pragma unroll
+    for (int a = 0; a < NX; ++a) {
+      double s = ddk[a];
+#pragma unroll
+      for (int b = 0; b < NX; ++b) s += J[a * NZ + b] * T[b];
+      ddk[a] = s;
+    }
+  }
+}
+
+template <int ORDER>
+TM_HD void tm_integrate(const double* x0, const double* u, int i, int j, double* X, double* Si, double* Sj, double* T) {
+#pragma unroll
+  for (int a = 0; a < NX; ++a) { X[a] = x0[a]; Si[a] = (a == i) ? 1.0 : 0.0; Sj[a] = (a == j) ? 1.0 : 0.0; T[a] = 0.0; }
+#if TMPC_DISCRETE
+  {
+    double k[NX], di[NX], dj[NX], dd[NX];
+    tm_rhs<ORDER>(X, u, Si, Sj, T, i, j, k, di, dj, dd);
+#pragma unroll
+    for (int a = 0; a < NX; ++a) {
+      X[a] = k[a];
+      if (ORDER >= 1) Si[a] = di[a];
+      if (ORDER >= 2) { Sj[a] = dj[a]; T[a] = dd[a]; }
+    }
+  }
+#else
+  const double h = TMPC_RK_DT;
+  for (int s = 0; s < TMPC_RK_STEPS; ++s) {
+    double aX[NX], aI[NX], aJ[NX], aT[NX];      // accumulated increment (k1 + 2k2 + 2k3 + k4)
+    double k[NX], di[NX], dj[NX], dd[NX];       // current stage derivative
+    double Xs[NX], Is[NX], Js[NX], Ts[NX];      // stage argument
+#pragma unroll
+    for (int a = 0; a < NX; ++a) { Xs[a] = X[a]; Is[a] = Si[a]; Js[a] = Sj[a]; Ts[a] = T[a]; di[a] = dj[a] = dd[a] = 0.0; }
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      tm_rhs<ORDER>(Xs, u, Is, Js, Ts, i, j, k, di, dj, dd);
+      const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+      const double cn = (st == 2) ? 1.0 : 0.5;  // coefficient of the NEXT stage argument
+#pragma unroll
+      for (int a = 0; a < NX; ++a) {
+        if (st == 0) { aX[a] = k[a]; aI[a] = di[a]; aJ[a] = dj[a]; aT[a] = dd[a]; }
+        else { aX[a] += wgt * k[a]; aI[a] += wgt * di[a]; aJ[a] += wgt * dj[a]; aT[a] += wgt * dd[a]; }
+        if (st < 3) {
+          Xs[a] = X[a] + cn * h * k[a];
+          if (ORDER >= 1) Is[a] = Si[a] + cn * h * di[a];
+          if (ORDER >= 2) { Js[a] = Sj[a] + cn * h * dj[a]; Ts[a] = T[a] + cn * h * dd[a]; }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NX; ++a) {
+      X[a] += h / 6.0 * aX[a];
+      if (ORDER >= 1) Si[a] += h / 6.0 * aI[a];
+      if (ORDER >= 2) { Sj[a] += h / 6.0 * aJ[a]; T[a] += h / 6.0 * aT[a]; }
+    }
+  }
+#endif
+}
+
+// one linearisation task.  trial = 1: evaluate at (W + D, LAMQ), else at (W, LAM).
+// exact mode: task id pr in [0, NPAIR) is the pair (i,j); gauss-newton mode: pr in [0, NZ) is direction i.
+TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, int pr, int trial) {
+  const double* w = S.W + inst * P.n_w + (int64_t)k * NZ;
+  double x[NX], u[NU];
+#pragma unroll
+  for (int a = 0; a < NX; ++a) x[a] = w[a];
+#pragma unroll
+  for (int b = 0; b < NU; ++b) u[b] = w[NX + b];
+  if (trial && S.qpstat[inst] == 0) {
+    const double* d = S.D + inst * P.n_w + (int64_t)k * NZ;
+#pragma unroll
+    for (int a = 0; a < NX; ++a) x[a] += d[a];
+#pragma unroll
+    for (int b = 0; b < NU; ++b) u[b] += d[NX + b];
+  }
+  if (trial && S.qpstat[inst] != 0) return;   // failed QP: keep LIN at W for the final statistics
+  double* rec = S.LIN + (inst * P.N + k) * (int64_t)TM_LSZ;
+  double X[NX], Si[NX], Sj[NX], T[NX];
+  if (P.hessian_exact) {
+    int i, j;
+    tm_pair_ij(pr, i, j);
+    tm_integrate<2>(x, u, i, j, X, Si, Sj, T);
+    const double* lam = (trial ? S.LAMQ : S.LAM) + inst * P.n_g + tm_gdyn(P, k);
+    double wij = 0.0;
+#pragma unroll
+    for (int a = 0; a < NX; ++a) wij += lam[a] * T[a];
+    rec[NX + NX * NZ + pr] = wij;
+    if (i == j) {
+#pragma unroll
+      for (int a = 0; a < NX; ++a) rec[NX + a * NZ + i] = Si[a];
+    }
+    if (pr == 0) {
+#pragma unroll
+      for (int a = 0; a < NX; ++a) rec[a] = X[a];
+    }
+  } else {
+    tm_integrate<1>(x, u, pr, pr, X, Si, Sj, T);
+#pragma unroll
+    for (int a = 0; a < NX; ++a) rec[NX + a * NZ + pr] = Si[a];
+    if (pr == 0) {
+#pragma unroll
+      for (int a = 0; a < NX; ++a) rec[a] = X[a];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3: QP.  Riccati factorisation of the dynamics-constrained base problem (exact terminal penalty rho), then a
+// Goldfarb-Idnani dual active-set iteration in which every other constraint (terminal equality rows first, then the
+// violated inequality rows one at a time) lives in a small dense Schur complement S = N' G N, G = base inverse.
+// Exact active-set solution: inactive multipliers are exact zeros, as the reference relies on (sqp_method.py:421).
+// ---------------------------------------------------------------------------------------------------------------
+struct TmQpWs {
+  double *AB, *Q, *r, *b, *K, *Lc, *hv, *d, *y, *z, *rhs, *kk, *P0, *P1, *PAB, *F, *pv, *tr, *S, *Sc, *cA, *rv, *nu;
+  int *actk, *acti;
+  double* acts;
+};
+
+TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
+  size_t n = 0;
+  n += (size_t)N * NX * NZ;        // AB
+  n += (size_t)N * NZ * NZ;        // Q
+  n += (size_t)(N + 1) * NZ;       // r
+  n += (size_t)N * NX;             // b
+  n += (size_t)N * NU * NX;        // K
+  n += (size_t)N * NU * NU;        // Lc
+  n += (size_t)N * (nh > 0 ? nh : 1);   // hv
+  n += 4 * (size_t)(N + 1) * NZ;   // d y z rhs
+  n += (size_t)N * NU;             // kk
+  n += 2 * NX * NX + NX * NZ + NZ * NZ;   // P0 P1 PAB F
+  n += 4 * NX;                     // pv (two buffers of NX, e0, spare)
+  n += (nxt > 0 ? nxt : 1);        // tr
+  n += 2 * (size_t)M * M + 3 * (size_t)M + M;   // S Sc cA rv nu acts
+  n += M;                          // actk/acti packed as ints in one double-sized slot each (2 ints per double)
+  return n;
+}
+
+TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s) {
+  double* p = base;
+  s.AB = p; p += (size_t)N * NX * NZ;
+  s.Q = p; p += (size_t)N * NZ * NZ;
+  s.r = p; p += (size_t)(N + 1) * NZ;
+  s.b = p; p += (size_t)N * NX;
+  s.K = p; p += (size_t)N * NU * NX;
+  s.Lc = p; p += (size_t)N * NU * NU;
+  s.hv = p; p += (size_t)N * (nh > 0 ? nh : 1);
+  s.d = p; p += (size_t)(N + 1) * NZ;
+  s.y = p; p += (size_t)(N + 1) * NZ;
+  s.z = p; p += (size_t)(N + 1) * NZ;
+  s.rhs = p; p += (size_t)(N + 1) * NZ;
+  s.kk = p; p += (size_t)N * NU;
+  s.P0 = p; p += NX * NX;
+  s.P1 = p; p += NX * NX;
+  s.PAB = p; p += NX * NZ;
+  s.F = p; p += NZ * NZ;
+  s.pv = p; p += 4 * NX;
+  s.tr = p; p += (nxt > 0 ? nxt : 1);
+  s.S = p; p += (size_t)M * M;
+  s.Sc = p; p += (size_t)M * M;
+  s.cA = p; p += M;
+  s.rv = p; p += M;
+  s.nu = p; p += M;
+  s.acts = p; p += M;
+  s.actk = (int*)p; s.acti = s.actk + M; p += M;
+}
+
+// Cholesky of the NU x NU block Fuu (row-major, in registers of every lane): returns 0 if a pivot <= thr
+TM_HD int tm_chol_small(const double* Fuu, double* L, double thr) {
+#pragma unroll
+  for (int i = 0; i < NU * NU; ++i) L[i] = 0.0;
+  for (int c = 0; c < NU; ++c) {
+    double dg = Fuu[c * NU + c];
+    for (int l = 0; l < c; ++l) dg -= L[c * NU + l] * L[c * NU + l];
+    if (!(dg > thr)) return 0;
+    const double ld = sqrt(dg);
+    L[c * NU + c] = ld;
+    for (int rr = c + 1; rr < NU; ++rr) {
+      double v = Fuu[rr * NU + c];
+      for (int l = 0; l < c; ++l) v -= L[rr * NU + l] * L[c * NU + l];
+      L[rr * NU + c] = v / ld;
+    }
+  }
+  return 1;
+}
+// solve (L L') x = rhs in place
+TM_HD void tm_chol_small_solve(const double* L, double* x) {
+  for (int i = 0; i < NU; ++i) {
+    double v = x[i];
+    for (int l = 0; l < i; ++l) v -= L[i * NU + l] * x[l];
+    x[i] = v / L[i * NU + i];
+  }
+  for (int i = NU - 1; i >= 0; --i) {
+    double v = x[i];
+    for (int l = i + 1; l < NU; ++l) v -= L[l * NU + i] * x[l];
+    x[i] = v / L[i * NU + i];
+  }
+}
+
+// homogeneous base solve:  out = argmin 1/2 d'Qd + rhs'd  s.t. d_x0 = 0, d_x(k+1) = A d_x + B d_u   ( = -G rhs )
+TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, const double* rhs, double* out) {
+  const int N = P.N;
+  const int lane = TM_LANE;
+  double* pv0 = s.pv;
+  double* pv1 = s.pv + NX;
+  for (int a = lane; a < NX; a += TM_NL) pv0[a] = rhs[N * NZ + a];
+  TM_SYNC();
+  for (int k = N - 1; k >= 0; --k) {
+    const double* AB = s.AB + (size_t)k * NX * NZ;
+    const double* Kk = s.K + (size_t)k * NU * NX;
+    const double* L = s.Lc + (size_t)k * NU * NU;
+    const double* rk = rhs + k * NZ;
+    double fu[NU];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      double v = rk[NX + a];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + NX + a] * pv0[i];
+      fu[a] = v;
+    }
+    for (int j = lane; j < NX; j += TM_NL) {
+      double v = rk[j];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + j] * pv0[i];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) v += Kk[a * NX + j] * fu[a];
+      pv1[j] = v;
+    }
+    double ku[NU];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) ku[a] = -fu[a];
+    tm_chol_small_solve(L, ku);
+    for (int a = lane; a < NU; a += TM_NL) s.kk[k * NU + a] = ku[a];
+    TM_SYNC();
+    double* t = pv0; pv0 = pv1; pv1 = t;
+  }
+  for (int a = lane; a < NX; a += TM_NL) out[a] = 0.0;
+  TM_SYNC();
+  for (int k = 0; k < N; ++k) {
+    const double* AB = s.AB + (size_t)k * NX * NZ;
+    const double* Kk = s.K + (size_t)k * NU * NX;
+    const double* dx = out + k * NZ;
+    double du[NU];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      double v = s.kk[k * NU + a];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) v += Kk[a * NX + j] * dx[j];
+      du[a] = v;
+    }
+    for (int a = lane; a < NU; a += TM_NL) out[k * NZ + NX + a] = du[a];
+    for (int i = lane; i < NX; i += TM_NL) {
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) v += AB[i * NZ + j] * dx[j];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) v += AB[i * NZ + NX + a] * du[a];
+      out[(k + 1) * NZ + i] = v;
+    }
+    TM_SYNC();
+  }
+  for (int a = lane; a < NU; a += TM_NL) out[N * NZ + NX + a] = 0.0;
+  TM_SYNC();
+}
+
+// constraint row helpers.  row m of the working set: stage actk (== N for a terminal row), row acti, sign acts
+TM_HD double tm_row_dot(const TmProb& P, int k, int i, double sg, const double* v) {
+  if (k == P.N) return sg * v[P.N * NZ + P.term_idx[i]];
+  double t = 0.0;
+  const double* Ci = P.C + (size_t)i * NZ;
+  const double* vk = v + k * NZ;
+#pragma unroll
+  for (int b = 0; b < NZ; ++b) t += Ci[b] * vk[b];
+  return t;
+}
+// rhs += coef * n   (single lane)
+TM_HD void tm_row_axpy(const TmProb& P, int k, int i, double sg, double coef, double* rhs) {
+  if (k == P.N) { rhs[P.N * NZ + P.term_idx[i]] += coef * sg; return; }
+  const double* Ci = P.C + (size_t)i * NZ;
+#pragma unroll
+  for (int b = 0; b < NZ; ++b) rhs[k * NZ + b] += coef * Ci[b];
+}
+
+// dense Cholesky solve  S r = c  for the m x m working-set Schur complement (stride M); returns 0 on breakdown
+TM_HD int tm_schur_solve(TmQpWs& s, int m, int M, double* r) {
+  const int lane = TM_LANE;
+  double* Sc = s.Sc;
+  for (int e = lane; e < m * m; e += TM_NL) { int i = e / m, j = e % m; Sc[i * M + j] = s.S[i * M + j]; }
+  TM_SYNC();
+  int ok = 1;
+  for (int c = 0; c < m; ++c) {
+    double dg = Sc[c * M + c];
+    if (!(dg > 0.0)) { ok = 0; break; }
+    const double ld = sqrt(dg);
+    TM_SYNC();
+    for (int i = c + lane; i < m; i += TM_NL) Sc[i * M + c] = (i == c) ? ld : Sc[i * M + c] / ld;
+    TM_SYNC();
+    const int rem = m - c - 1;
+    for (int e = lane; e < rem * rem; e += TM_NL) {
+      int i = c + 1 + e / rem, j = c + 1 + e % rem;
+      if (j <= i) Sc[i * M + j] -= Sc[i * M + c] * Sc[j * M + c];
+    }
+    TM_SYNC();
+  }
+  if (!ok) return 0;
+  // forward / backward substitution, every lane redundantly on its own copy kept in shared r (lane 0 writes)
+  if (lane == 0) {
+    for (int i = 0; i < m; ++i) {
+      double v = s.cA[i];
+      for (int l = 0; l < i; ++l) v -= Sc[i * M + l] * r[l];
+      r[i] = v / Sc[i * M + i];
+    }
+    for (int i = m - 1; i >= 0; --i) {
+      double v = r[i];
+      for (int l = i + 1; l < m; ++l) v -= Sc[l * M + i] * r[l];
+      r[i] = v / Sc[i * M + i];
+    }
+  }
+  TM_SYNC();
+  return 1;
+}
+
+// returns: 0 ok, 2 infeasible / working-set overflow / numerical breakdown, 3 base factorisation not PD
+#define TM_ALW 8   /* words of the augmented-Lagrangian row mask: supports N*nh <= 256 */
+// al_mask: rows (k*nh+i) whose squared slack  gamma/2 (C_i d + h_i)^2  is added to the base problem.  The term and its
+// gradient vanish wherever the row is active at the QP solution, so the solution is unchanged iff every masked row ends
+// up in the working set; rows that do not are reported in al_bad (caller removes them and re-solves).  This makes the
+// base factorisation positive definite on the null space of (dynamics + warm-start active rows) -- the space on which
+// the reference tests and regularises its reduced Hessian (sqp_method.py:335-347) -- instead of dynamics only.
+TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& s, int use_exact,
+                       const unsigned* al_mask, unsigned* al_bad) {
+  const int N = P.N, nh = P.nh, nxt = P.nxt, M = P.maxact;
+  const int lane = TM_LANE;
+  const double* w = S.W + inst * P.n_w;
+  const double* lin = S.LIN + inst * P.N * (int64_t)TM_LSZ;
+  // ---- A. stage data ------------------------------------------------------------------------------------------
+  for (int e = lane; e < N * NX * NZ; e += TM_NL) { int k = e / (NX * NZ), o = e % (NX * NZ); s.AB[e] = lin[(size_t)k * TM_LSZ + NX + o]; }
+  for (int e = lane; e < N * NX; e += TM_NL) { int k = e / NX, a = e % NX; s.b[e] = lin[(size_t)k * TM_LSZ + a] - w[(k + 1) * NZ + a]; }
+  for (int e = lane; e < N * NZ * NZ; e += TM_NL) {
+    int k = e / (NZ * NZ), o = e % (NZ * NZ), i = o / NZ, j = o % NZ;
+    int ph = (S.phase + k) % P.p;
+    double v = P.H[(size_t)ph * NZ * NZ + o];
+    if (use_exact) v += lin[(size_t)k * TM_LSZ + NX + NX * NZ + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
+    s.Q[e] = v;
+  }
+  for (int e = lane; e < N * NZ; e += TM_NL) {
+    int k = e / NZ, i = e % NZ;
+    int ph = (S.phase + k) % P.p;
+    const double* Hk = P.H + (size_t)ph * NZ * NZ + (size_t)i * NZ;
+    const double* wr = P.wref + (size_t)ph * NZ;
+    double v = P.q[(size_t)ph * NZ + i];
+#pragma unroll
+    for (int j = 0; j < NZ; ++j) v += Hk[j] * (w[k * NZ + j] - wr[j]);
+    s.r[e] = v;
+  }
+  for (int a = lane; a < NZ; a += TM_NL) s.r[N * NZ + a] = 0.0;
+  for (int e = lane; e < N * nh; e += TM_NL) {
+    int k = e / nh, i = e % nh;
+    double v = P.c[i];
+#pragma unroll
+    for (int j = 0; j < NZ; ++j) v += P.C[(size_t)i * NZ + j] * w[k * NZ + j];
+    s.hv[e] = v;
+  }
+  double* e0 = s.pv + 2 * NX;
+  for (int a = lane; a < NX; a += TM_NL) e0[a] = S.X0[inst * NX + a] - w[a];
+  {
+    const double* xrN = P.wref + (size_t)((S.phase + N) % P.p) * NZ;
+    for (int t = lane; t < nxt; t += TM_NL) s.tr[t] = w[N * NZ + P.term_idx[t]] - xrN[P.term_idx[t]];
+  }
+  TM_SYNC();
+  if (al_mask) {
+    // gamma relative to the largest Hessian diagonal entry of the horizon
+    double qmax = 0.0;
+    for (int e = lane; e < N * NZ; e += TM_NL) { int k = e / NZ, i = e % NZ; qmax = fmax(qmax, fabs(s.Q[(size_t)k * NZ * NZ + i * NZ + i])); }
+    qmax = tm_wmax(qmax);
+    const double gam = P.al_gamma * fmax(qmax, 1e-300);
+    for (int k = lane; k < N; k += TM_NL) {
+      for (int i = 0; i < nh; ++i) {
+        const int e = k * nh + i;
+        if (!((al_mask[e >> 5] >> (e & 31)) & 1u)) continue;
+        const double* Ci = P.C + (size_t)i * NZ;
+        double cc = 0.0;
+#pragma unroll
+        for (int b = 0; b < NZ; ++b) cc += Ci[b] * Ci[b];
+        const double g = gam / cc;
+#pragma unroll
+        for (int a = 0; a < NZ; ++a) {
+#pragma unroll
+          for (int b = 0; b < NZ; ++b) s.Q[(size_t)k * NZ * NZ + a * NZ + b] += g * Ci[a] * Ci[b];
+          s.r[k * NZ + a] += g * s.hv[e] * Ci[a];
+        }
+      }
+    }
+    TM_SYNC();
+  }
+  // ---- B. Riccati factorisation + main solve (offsets b_k, e0, terminal penalty) -------------------------------
+  double* Pn = s.P0;   // P_{k+1}
+  double* Pk = s.P1;
+  double* pv0 = s.pv;
+  double* pv1 = s.pv + NX;
+  for (int e = lane; e < NX * NX; e += TM_NL) {
+    int i = e / NX, j = e % NX;
+    double v = 0.0;
+    for (int t = 0; t < nxt; ++t) if (P.term_idx[t] == i && i == j) v += P.rho;
+    Pn[e] = v;
+  }
+  for (int a = lane; a < NX; a += TM_NL) {
+    double v = 0.0;
+    for (int t = 0; t < nxt; ++t) if (P.term_idx[t] == a) v += P.rho * s.tr[t];
+    pv0[a] = v;
+  }
+  TM_SYNC();
+  int fail = 0;
+  for (int k = N - 1; k >= 0; --k) {
+    const double* AB = s.AB + (size_t)k * NX * NZ;
+    const double* Qk = s.Q + (size_t)k * NZ * NZ;
+    for (int e = lane; e < NX * NZ; e += TM_NL) {
+      int i = e / NZ, c = e % NZ;
+      double v = 0.0;
+#pragma unroll
+      for (int l = 0; l < NX; ++l) v += Pn[i * NX + l] * AB[l * NZ + c];
+      s.PAB[e] = v;
+    }
+    TM_SYNC();
+    for (int e = lane; e < NZ * NZ; e += TM_NL) {
+      int a = e / NZ, c = e % NZ;
+      double v = Qk[e];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + a] * s.PAB[i * NZ + c];
+      s.F[e] = v;
+    }
+    TM_SYNC();
+    double Fuu[NU * NU], L[NU * NU];
+#pragma unroll
+    for (int a = 0; a < NU; ++a)
+#pragma unroll
+      for (int c = 0; c < NU; ++c) Fuu[a * NU + c] = 0.5 * (s.F[(NX + a) * NZ + NX + c] + s.F[(NX + c) * NZ + NX + a]);
+    if (!tm_chol_small(Fuu, L, P.reg_tol)) { fail = 1; break; }
+    for (int e = lane; e < NU * NU; e += TM_NL) s.Lc[(size_t)k * NU * NU + e] = L[e];
+    // K = -Fuu^-1 Fux : lane j owns column j
+    for (int j = lane; j < NX; j += TM_NL) {
+      double col[NU];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) col[a] = -0.5 * (s.F[(NX + a) * NZ + j] + s.F[j * NZ + NX + a]);
+      tm_chol_small_solve(L, col);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) s.K[(size_t)k * NU * NX + a * NX + j] = col[a];
+    }
+    TM_SYNC();
+    const double* Kk = s.K + (size_t)k * NU * NX;
+    // P_k = Fxx + sym(Fux' K)
+    for (int e = lane; e < NX * NX; e += TM_NL) {
+      int i = e / NX, j = e % NX;
+      double v = 0.5 * (s.F[i * NZ + j] + s.F[j * NZ + i]);
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        const double fai = 0.5 * (s.F[(NX + a) * NZ + i] + s.F[i * NZ + NX + a]);
+        const double faj = 0.5 * (s.F[(NX + a) * NZ + j] + s.F[j * NZ + NX + a]);
+        v += 0.5 * (fai * Kk[a * NX + j] + faj * Kk[a * NX + i]);
+      }
+      Pk[e] = v;
+    }
+    // main right-hand side: v = p_{k+1} + P_{k+1} b_k
+    {
+      double vv[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double t = pv0[i];
+#pragma unroll
+        for (int l = 0; l < NX; ++l) t += Pn[i * NX + l] * s.b[k * NX + l];
+        vv[i] = t;
+      }
+      double fu[NU];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        double t = s.r[k * NZ + NX + a];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) t += AB[i * NZ + NX + a] * vv[i];
+        fu[a] = t;
+      }
+      for (int j = lane; j < NX; j += TM_NL) {
+        double t = s.r[k * NZ + j];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) t += AB[i * NZ + j] * vv[i];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) t += Kk[a * NX + j] * fu[a];
+        pv1[j] = t;
+      }
+      double ku[NU];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) ku[a] = -fu[a];
+      tm_chol_small_solve(L, ku);
+      for (int a = lane; a < NU; a += TM_NL) s.kk[k * NU + a] = ku[a];
+    }
+    TM_SYNC();
+    { double* t = Pn; Pn = Pk; Pk = t; }
+    { double* t = pv0; pv0 = pv1; pv1 = t; }
+  }
+  if (fail) return 3;
+  // forward sweep of the main solve
+  for (int a = lane; a < NX; a += TM_NL) s.d[a] = e0[a];
+  TM_SYNC();
+  for (int k = 0; k < N; ++k) {
+    const double* AB = s.AB + (size_t)k * NX * NZ;
+    const double* Kk = s.K + (size_t)k * NU * NX;
+    const double* dx = s.d + k * NZ;
+    double du[NU];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      double v = s.kk[k * NU + a];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) v += Kk[a * NX + j] * dx[j];
+      du[a] = v;
+    }
+    for (int a = lane; a < NU; a += TM_NL) s.d[k * NZ + NX + a] = du[a];
+    for (int i = lane; i < NX; i += TM_NL) {
+      double v = s.b[k * NX + i];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) v += AB[i * NZ + j] * dx[j];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) v += AB[i * NZ + NX + a] * du[a];
+      s.d[(k + 1) * NZ + i] = v;
+    }
+    TM_SYNC();
+  }
+  for (int a = lane; a < NU; a += TM_NL) s.d[N * NZ + NX + a] = 0.0;
+  TM_SYNC();
+  // ---- C. Goldfarb-Idnani on the Schur complement ------------------------------------------------------------
+  int m = 0, neq = 0, ret = 0;
+  const int maxit = 4 * (nxt + N * nh) + 8;
+  for (int it = 0; it < maxit; ++it) {
+    int qk, qi;
+    double qs = 1.0, sval;
+    if (neq < nxt) {
+      qk = N; qi = neq;
+      double v = s.d[N * NZ + P.term_idx[qi]] + s.tr[qi];
+      qs = (v > 0.0) ? -1.0 : 1.0;
+      sval = qs * v;
+    } else {
+      double best = TM_INF;
+      int bid = 0x7fffffff;
+      for (int e = lane; e < N * nh; e += TM_NL) {
+        int k = e / nh, i = e % nh;
+        if (k == 0 && P.relax0[i]) continue;
+        double v = s.hv[e];
+        const double* Ci = P.C + (size_t)i * NZ;
+#pragma unroll
+        for (int b = 0; b < NZ; ++b) v += Ci[b] * s.d[k * NZ + b];
+        v /= fmax(1.0, fabs(P.c[i]));
+        if (v < best) { best = v; bid = e; }
+      }
+      tm_wargmin(best, bid);
+      if (!(best < -1e-10)) break;            // primal feasible: optimal
+      // an active row can only show up here through round-off; treat as converged
+      int dup = 0;
+      for (int j2 = 0; j2 < m; ++j2) if (s.actk[j2] * nh + s.acti[j2] == bid && s.actk[j2] < N) dup = 1;
+      if (dup) break;
+      qk = bid / nh; qi = bid % nh;
+      sval = s.hv[bid] + tm_row_dot(P, qk, qi, 1.0, s.d);
+    }
+    if (m >= M) { ret = 2; break; }
+    // y = G n_q
+    for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.rhs[e] = 0.0;
+    TM_SYNC();
+    if (lane == 0) tm_row_axpy(P, qk, qi, qs, -1.0, s.rhs);
+    TM_SYNC();
+    tm_ricc_solve(P, s, s.rhs, s.y);
+    for (int j2 = lane; j2 < m; j2 += TM_NL) s.cA[j2] = tm_row_dot(P, s.actk[j2], s.acti[j2], s.acts[j2], s.y);
+    const double yq = tm_row_dot(P, qk, qi, qs, s.y);
+    TM_SYNC();
+    double nq = 0.0;
+    int added = 0;
+    for (int inner = 0; inner < M + 2; ++inner) {
+      const double* zz = s.y;
+      if (m > 0) {
+        if (!tm_schur_solve(s, m, M, s.rv)) { ret = 2; break; }
+        for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.rhs[e] = 0.0;
+        TM_SYNC();
+        if (lane == 0) for (int j2 = 0; j2 < m; ++j2) tm_row_axpy(P, s.actk[j2], s.acti[j2], s.acts[j2], s.rv[j2], s.rhs);
+        TM_SYNC();
+        tm_ricc_solve(P, s, s.rhs, s.z);
+        for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.z[e] += s.y[e];
+        TM_SYNC();
+        zz = s.z;
+      }
+      const double zn = tm_row_dot(P, qk, qi, qs, zz);
+      double t1 = TM_INF;
+      int jd = -1;
+      for (int j2 = 0; j2 < m; ++j2) {
+        if (s.actk[j2] == N) continue;                 // equality rows are never dropped
+        const double rj = s.rv[j2];
+        if (rj > 1e-14) { const double tj = s.nu[j2] / rj; if (tj < t1) { t1 = tj; jd = j2; } }
+      }
+      const int dependent = !(zn > 1e-11 * fmax(yq, 1e-300));
+      double t;
+      int do_add = 0;
+      if (dependent) {
+        if (jd < 0) { ret = 2; break; }
+        t = t1;
+      } else {
+        const double t2 = -sval / zn;
+        if (t2 <= t1) { t = t2; do_add = 1; } else t = t1;
+        for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.d[e] += t * zz[e];
+        sval += t * zn;
+      }
+      TM_SYNC();
+      for (int j2 = lane; j2 < m; j2 += TM_NL) s.nu[j2] -= t * s.rv[j2];
+      nq += t;
+      TM_SYNC();
+      if (do_add) {
+        for (int j2 = lane; j2 < m; j2 += TM_NL) { s.S[m * M + j2] = s.cA[j2]; s.S[j2 * M + m] = s.cA[j2]; }
+        if (lane == 0) { s.S[m * M + m] = yq; s.actk[m] = qk; s.acti[m] = qi; s.acts[m] = qs; s.nu[m] = nq; }
+        TM_SYNC();
+        ++m;
+        if (qk == N) ++neq;
+        added = 1;
+        break;
+      }
+      // drop working-set row jd: compact S, cA, nu, act*
+      TM_SYNC();
+      if (lane == 0) {
+        for (int a = jd; a < m - 1; ++a) {
+          s.actk[a] = s.actk[a + 1]; s.acti[a] = s.acti[a + 1]; s.acts[a] = s.acts[a + 1];
+          s.nu[a] = s.nu[a + 1]; s.cA[a] = s.cA[a + 1];
+        }
+        for (int a = 0; a < m; ++a)
+          for (int c = jd; c < m - 1; ++c) s.S[a * M + c] = s.S[a * M + c + 1];
+        for (int a = jd; a < m - 1; ++a)
+          for (int c = 0; c < m - 1; ++c) s.S[a * M + c] = s.S[(a + 1) * M + c];
+      }
+      --m;
+      TM_SYNC();
+    }
+    if (ret) break;
+    if (!added) { ret = 2; break; }
+    if (it == maxit - 1) ret = 2;
+  }
+  if (ret) return ret;
+  if (al_mask) {
+    int nbad = 0;
+    for (int wd = 0; wd < TM_ALW; ++wd) al_bad[wd] = 0u;
+    for (int e = 0; e < N * nh && e < 32 * TM_ALW; ++e) {
+      if (!((al_mask[e >> 5] >> (e & 31)) & 1u)) continue;
+      int found = 0;
+      for (int j2 = 0; j2 < m; ++j2) if (s.actk[j2] < N && s.actk[j2] * nh + s.acti[j2] == e) found = 1;
+      if (!found) { al_bad[e >> 5] |= (1u << (e & 31)); ++nbad; }
+    }
+    if (nbad) return 5;
+  }
+  // ---- D. outputs: step and multipliers (CasADi sign: H d + g + J' lam = 0) ------------------------------------
+  double* dout = S.D + inst * P.n_w;
+  double* lq = S.LAMQ + inst * P.n_g;
+  for (int e = lane; e < P.n_w; e += TM_NL) dout[e] = s.d[e];
+  for (int e = lane; e < P.n_g; e += TM_NL) lq[e] = 0.0;
+  TM_SYNC();
+  if (lane == 0) {
+    for (int j2 = 0; j2 < m; ++j2) {
+      if (s.actk[j2] == N) lq[tm_gterm(P) + s.acti[j2]] = -s.acts[j2] * s.nu[j2];
+      else lq[tm_gh(P, s.actk[j2]) + s.acti[j2]] = -s.nu[j2];
+    }
+  }
+  TM_SYNC();
+  // dynamics multipliers by the stationarity recursion (pv0/pv1 reused as lam_{k}, lam_{k-1})
+  pv0 = s.pv; pv1 = s.pv + NX;
+  for (int a = lane; a < NX; a += TM_NL) {
+    double v = 0.0;
+    for (int t = 0; t < nxt; ++t) if (P.term_idx[t] == a) v += lq[tm_gterm(P) + t];
+    pv0[a] = v;
+  }
+  TM_SYNC();
+  for (int k = N - 1; k >= 0; --k) {
+    const double* AB = s.AB + (size_t)k * NX * NZ;
+    const double* Qk = s.Q + (size_t)k * NZ * NZ;
+    for (int a = lane; a < NX; a += TM_NL) lq[tm_gdyn(P, k) + a] = pv0[a];
+    for (int j = lane; j < NX; j += TM_NL) {
+      double v = s.r[k * NZ + j];
+#pragma unroll
+      for (int c = 0; c < NZ; ++c) v += 0.5 * (Qk[j * NZ + c] + Qk[c * NZ + j]) * s.d[k * NZ + c];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + j] * pv0[i];
+      for (int i = 0; i < nh; ++i) v += P.C[(size_t)i * NZ + j] * lq[tm_gh(P, k) + i];
+      pv1[j] = v;
+    }
+    TM_SYNC();
+    { double* t = pv0; pv0 = pv1; pv1 = t; }
+  }
+  for (int a = lane; a < NX; a += TM_NL) lq[a] = -pv0[a];
+  TM_SYNC();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// objective and infeasibility of a point w_t = W + alpha*D.  xf_from_lin: take F(x_k,u_k) from LIN (valid for the
+// point LIN was evaluated at), else integrate (lane <-> stage).  Writes g (n_g) when gout != nullptr.
+// ---------------------------------------------------------------------------------------------------------------
+TM_HD void tm_eval_point(const TmProb& P, const TmState& S, int64_t inst, double alpha, int xf_from_lin,
+                         double* gout, double& f_out, double& viol_out) {
+  const int N = P.N, nh = P.nh;
+  const int lane = TM_LANE;
+  const double* w = S.W + inst * P.n_w;
+  const double* d = S.D + inst * P.n_w;
+  const double* lin = S.LIN + inst * P.N * (int64_t)TM_LSZ;
+  double f = 0.0, viol = 0.0;
+  for (int k = lane; k < N; k += TM_NL) {
+    double z[NZ], xn[NX], xf[NX];
+#pragma unroll
+    for (int b = 0; b < NZ; ++b) z[b] = w[k * NZ + b] + (alpha != 0.0 ? alpha * d[k * NZ + b] : 0.0);
+#pragma unroll
+    for (int a = 0; a < NX; ++a) xn[a] = w[(k + 1) * NZ + a] + (alpha != 0.0 ? alpha * d[(k + 1) * NZ + a] : 0.0);
+    if (xf_from_lin) {
+#pragma unroll
+      for (int a = 0; a < NX; ++a) xf[a] = lin[(size_t)k * TM_LSZ + a];
+    } else {
+      double t1[NX], t2[NX], t3[NX];
+      tm_integrate<0>(z, z + NX, 0, 0, xf, t1, t2, t3);
+    }
+    const int ph = (S.phase + k) % P.p;
+    const double* Hk = P.H + (size_t)ph * NZ * NZ;
+    const double* wr = P.wref + (size_t)ph * NZ;
+    const double* qk = P.q + (size_t)ph * NZ;
+    double dz[NZ];
+#pragma unroll
+    for (int b = 0; b < NZ; ++b) dz[b] = z[b] - wr[b];
+    double fk = 0.0;
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) {
+      double t = 0.0;
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) t += Hk[a * NZ + b] * dz[b];
+      fk += dz[a] * (0.5 * t + qk[a]);
+    }
+    f += fk;
+#pragma unroll
+    for (int a = 0; a < NX; ++a) {
+      const double rdy = xf[a] - xn[a];
+      viol = fmax(viol, fabs(rdy));
+      if (gout) gout[tm_gdyn(P, k) + a] = rdy;
+    }
+    for (int i = 0; i < nh; ++i) {
+      double v = P.c[i];
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) v += P.C[(size_t)i * NZ + b] * z[b];
+      if (gout) gout[tm_gh(P, k) + i] = v;
+      if (!(k == 0 && P.relax0[i]) && v < 0.0) viol = fmax(viol, -v);
+    }
+    if (k == 0) {
+#pragma unroll
+      for (int a = 0; a < NX; ++a) {
+        const double r0 = z[a] - S.X0[inst * NX + a];
+        viol = fmax(viol, fabs(r0));
+        if (gout) gout[a] = r0;
+      }
+    }
+    if (k == N - 1) {
+      const double* xrN = P.wref + (size_t)((S.phase + N) % P.p) * NZ;
+      for (int t = 0; t < P.nxt; ++t) {
+        const double rt = xn[P.term_idx[t]] - xrN[P.term_idx[t]];
+        viol = fmax(viol, fabs(rt));
+        if (gout) gout[tm_gterm(P) + t] = rt;
+      }
+    }
+  }
+  f_out = tm_wsum(f);
+  viol_out = tm_wmax(viol);
+}
+
+// |grad_w L|_inf at (W, LAM) using the linearisation stored in LIN (must be valid at W)      sqp_method.py:246
+TM_HD double tm_dual_infeas(const TmProb& P, const TmState& S, int64_t inst) {
+  const int N = P.N, nh = P.nh;
+  const int lane = TM_LANE;
+  const double* w = S.W + inst * P.n_w;
+  const double* lam = S.LAM + inst * P.n_g;
+  const double* lin = S.LIN + inst * P.N * (int64_t)TM_LSZ;
+  double mx = 0.0;
+  for (int k = lane; k < N; k += TM_NL) {
+    const int ph = (S.phase + k) % P.p;
+    const double* Hk = P.H + (size_t)ph * NZ * NZ;
+    const double* wr = P.wref + (size_t)ph * NZ;
+    const double* qk = P.q + (size_t)ph * NZ;
+    const double* AB = lin + (size_t)k * TM_LSZ + NX;
+    const double* ld = lam + tm_gdyn(P, k);
+    const double* lh = lam + tm_gh(P, k);
+    double dz[NZ];
+#pragma unroll
+    for (int b = 0; b < NZ; ++b) dz[b] = w[k * NZ + b] - wr[b];
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) {
+      double v = qk[a];
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) v += Hk[a * NZ + b] * dz[b];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + a] * ld[i];
+      for (int i = 0; i < nh; ++i) v += P.C[(size_t)i * NZ + a] * lh[i];
+      if (a < NX) v += (k == 0) ? lam[a] : -lam[tm_gdyn(P, k - 1) + a];
+      mx = fmax(mx, fabs(v));
+    }
+    if (k == N - 1) {
+#pragma unroll
+      for (int a = 0; a < NX; ++a) {
+        double v = -ld[a];
+        for (int t = 0; t < P.nxt; ++t) if (P.term_idx[t] == a) v += lam[tm_gterm(P) + t];
+        mx = fmax(mx, fabs(v));
+      }
+    }
+  }
+  return tm_wmax(mx);
+}
+
+TM_HD int tm_is_ineq_active(const TmProb& P, const double* lam, int e) {   // e = k*nh + i
+  return lam[tm_gh(P, e / P.nh) + e % P.nh] != 0.0;
+}
+
+// k = 0 bookkeeping (sqp_method.py:248-261): filter <- [(f0, infeas0)], as_idx_init.  LIN valid at (W, LAM).
+TM_HD void tm_init(const TmProb& P, const TmState& S, int64_t inst) {
+  double f, v;
+  tm_eval_point(P, S, inst, 0.0, 1, nullptr, f, v);
+  const int lane = TM_LANE;
+  if (lane == 0) {
+    S.FILT[inst * P.filter_cap * 2 + 0] = f;
+    S.FILT[inst * P.filter_cap * 2 + 1] = v;
+    S.nfilt[inst] = 1;
+    S.iter[inst] = 0;
+    S.status[inst] = -1;
+    S.flags[inst] = 0;
+    const double* lam = S.LAM + inst * P.n_g;
+    for (int wd = 0; wd < S.aswords; ++wd) {
+      unsigned bits = 0;
+      for (int bt = 0; bt < 32; ++bt) {
+        int e = wd * 32 + bt;
+        if (e < P.N * P.nh && tm_is_ineq_active(P, lam, e)) bits |= (1u << bt);
+      }
+      S.asinit[inst * S.aswords + wd] = bits;
+    }
+  }
+  TM_SYNC();
+}
+
+// finalise an instance: stats of __postprocessing (sqp_method.py:203-219) and __detect_AC (pmpc.py:840-856)
+TM_HD void tm_finalize(const TmProb& P, const TmState& S, int64_t inst, int status) {
+  double f, v;
+  tm_eval_point(P, S, inst, 0.0, 1, S.G + inst * P.n_g, f, v);
+  if (TM_LANE == 0) {
+    const double* lam = S.LAM + inst * P.n_g;
+    int nAS = 0, nACt = 0, nAC0 = 0;
+    for (int e = 0; e < P.N * P.nh; ++e) {
+      const int a = tm_is_ineq_active(P, lam, e);
+      const int a0 = (S.asinit[inst * S.aswords + e / 32] >> (e % 32)) & 1u;
+      nAS += a;
+      nACt += (a != a0);
+    }
+    const double* lref = P.ref_du + (size_t)S.phase * P.n_g;
+    for (int i = 0; i < P.nh; ++i) nAC0 += ((lam[tm_gh(P, 0) + i] != 0.0) != (lref[tm_gh(P, 0) + i] != 0.0));
+    S.fval[inst] = f;
+    S.nAS[inst] = nAS;
+    S.nACtot[inst] = nACt;
+    S.nAC[inst] = nAC0;
+    S.status[inst] = status;
+  }
+  TM_SYNC();
+}
+
+// convergence test at the accepted point (LIN valid at W, LAM):  sqp_method.py:276-283
+TM_HD void tm_conv(const TmProb& P, const TmState& S, int64_t inst) {
+  const double dual = tm_dual_infeas(P, S, inst);
+  const int nf = S.nfilt[inst];
+  const double viol = S.FILT[(inst * P.filter_cap + nf - 1) * 2 + 1];
+  const int it = S.iter[inst];
+  int done = -1;
+  if (!(dual == dual) || !(viol == viol)) done = 4;
+  else if (viol < P.tol && dual < P.tol) done = 0;
+  else if (it >= P.max_iter || nf >= P.filter_cap) done = 1;
+  if (done >= 0) {
+    tm_finalize(P, S, inst, done);
+  } else if (TM_LANE == 0) {
+#ifdef __CUDA_ARCH__
+    int pos = atomicAdd(S.cnt_next, 1);
+#else
+    int pos = (*S.cnt_next)++;
+#endif
+    S.list_next[pos] = (int)inst;
+  }
+  TM_SYNC();
+}
+
+// after the QP and the trial linearisation at (W + D, LAMQ): filter line search, update, convergence
+TM_HD void tm_post(const TmProb& P, const TmState& S, int64_t inst) {
+  const int lane = TM_LANE;
+  const int qp_status = S.qpstat[inst];
+  if (qp_status != 0) { tm_finalize(P, S, inst, qp_status); return; }
+  double alpha = 1.0, f, v;
+  tm_eval_point(P, S, inst, alpha, 1, nullptr, f, v);
+  const int nf = S.nfilt[inst];
+  const double* F = S.FILT + inst * P.filter_cap * 2;
+  int relin = 0;
+  unsigned long long ndyn = 0;
+  for (int ls = 0; ls < P.max_ls; ++ls) {                       // sqp_method.py:304-320
+    int cnt = 0;
+    for (int e = lane; e < nf; e += TM_NL) cnt += (f > F[2 * e] && v > F[2 * e + 1]) ? 1 : 0;
+    cnt = tm_wsumi(cnt);
+    if (cnt > 1) {
+      alpha *= P.beta;
+      tm_eval_point(P, S, inst, alpha, 0, nullptr, f, v);
+      relin = 1;
+      ndyn += (unsigned long long)P.N;
+    } else break;
+  }
+  if (!(f == f) || !(v == v)) { tm_finalize(P, S, inst, 4); return; }
+  double* w = S.W + inst * P.n_w;
+  const double* d = S.D + inst * P.n_w;
+  double* lam = S.LAM + inst * P.n_g;
+  const double* lq = S.LAMQ + inst * P.n_g;
+  for (int e = lane; e < P.n_w; e += TM_NL) w[e] += alpha * d[e];        // :174
+  for (int e = lane; e < P.n_g; e += TM_NL) lam[e] = lq[e];              // :175 full dual step
+  if (lane == 0) {
+    S.FILT[(inst * P.filter_cap + nf) * 2 + 0] = f;                       // :323
+    S.FILT[(inst * P.filter_cap + nf) * 2 + 1] = v;
+    S.nfilt[inst] = nf + 1;
+    S.iter[inst] += 1;
+    if (relin) S.flags[inst] |= 2;
+#ifdef __CUDA_ARCH__
+    atomicAdd(S.counters + 0, 1ull);
+    if (ndyn) atomicAdd(S.counters + 4, ndyn);
+#else
+    S.counters[0] += 1; S.counters[4] += ndyn;
+#endif
+  }
+  TM_SYNC();
+  if (relin) {
+    if (lane == 0) {
+#ifdef __CUDA_ARCH__
+      int pos = atomicAdd(S.cnt_relin, 1);
+#else
+      int pos = (*S.cnt_relin)++;
+#endif
+      S.list_relin[pos] = (int)inst;
+    }
+    TM_SYNC();
+    return;
+  }
+  tm_conv(P, S, inst);
+}
+
+// warm-start shift (pmpc.py:867-906): (W, LAM) -> (Ws, Ls); one warp per instance
+TM_HD void tm_shift(const TmProb& P, const double* w, const double* lam, double* ws, double* ls) {
+  const int N = P.N, nh = P.nh;
+  const int lane = TM_LANE;
+  for (int e = lane; e < P.n_w; e += TM_NL) {
+    int k = e / NZ, o = e % NZ;
+    double v;
+    if (k >= N) v = w[N * NZ + o];                                   // x_N <- x_N
+    else if (o < NX) v = w[(k + 1) * NZ + o];                        // x_i <- x_{i+1}  (x_{N-1} <- x_N)
+    else v = (k < N - 1) ? w[(k + 1) * NZ + o] : w[(N - 1) * NZ + o];  // u_{N-1} <- u_{N-2}^{shifted} = u_{N-1}
+    ws[e] = v;
+  }
+  for (int e = lane; e < P.n_g; e += TM_NL) {
+    double v;
+    if (e < NX) v = lam[tm_gdyn(P, 0) + e];                          // init <- dyn_0
+    else if (e >= tm_gterm(P)) v = lam[e];                           // term kept
+    else {
+      int k = (e - NX) / (NX + nh), o = (e - NX) % (NX + nh);
+      int ksrc = (k < N - 1) ? k + 1 : N - 1;                        // last stage duplicated
+      v = lam[NX + ksrc * (NX + nh) + o];
+    }
+    ls[e] = v;
+  }
+  TM_SYNC();
+}
+
+// __prefilter_lam_g (sqp_method.py:223-238): zero every multiplier below lam_tresh, equality rows included
+TM_HD void tm_prefilter(const TmProb& P, const TmState& S, int64_t inst) {
+  double* lam = S.LAM + inst * P.n_g;
+  for (int e = TM_LANE; e < P.n_g; e += TM_NL) if (fabs(lam[e]) < P.lam_tresh) lam[e] = 0.0;
+  TM_SYNC();
+}
+
+// QP with the configured Hessian.  Exact mode: (1) augmented-Lagrangian convexification on the rows that are active
+// in the current multipliers (the reference's reduced space); rows that turn out inactive are dropped and the QP is
+// re-solved; (2) if the base factorisation is still not positive definite: Gauss-Newton Hessian, flagged
+// (the reference would eigen-clip its reduced Hessian there, sqp_method.py:345-376).
+TM_HD void tm_qp(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& ws) {
+  unsigned mask[TM_ALW], bad[TM_ALW];
+  int nmask = 0;
+  const double* lam = S.LAM + inst * P.n_g;
+  for (int wd = 0; wd < TM_ALW; ++wd) mask[wd] = 0u;
+  if (P.hessian_exact && P.al_gamma > 0.0) {
+    for (int e = 0; e < P.N * P.nh && e < 32 * TM_ALW; ++e) {
+      const int k = e / P.nh, i = e % P.nh;
+      if (k == 0 && P.relax0[i]) continue;
+      if (lam[tm_gh(P, k) + i] != 0.0) { mask[e >> 5] |= (1u << (e & 31)); ++nmask; }
+    }
+  }
+  int ret = 0, fb = 0;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    ret = tm_qp_solve(P, S, inst, ws, P.hessian_exact, nmask ? mask : nullptr, bad);
+    if (ret != 5) break;
+    nmask = 0;
+    for (int wd = 0; wd < TM_ALW; ++wd) { mask[wd] &= ~bad[wd]; nmask += (mask[wd] != 0u); }
+    if (attempt == 3) ret = 3;
+  }
+  if (ret == 5) ret = 3;
+  if (ret == 3 && P.hessian_exact) { ret = tm_qp_solve(P, S, inst, ws, 0, nullptr, bad); fb = 1; }
+  if (TM_LANE == 0) {
+    S.qpstat[inst] = ret;
+    if (fb) S.flags[inst] |= 1;
+  }
+  TM_SYNC();
+}
