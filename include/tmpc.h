@@ -55,6 +55,7 @@ typedef struct {
   double ls_step_factor;   /* sqp_method.py:58 (0.8) */
   double reg_tol;          /* sqp_method.py:54 (1e-8): pivot threshold of the reduced-Hessian PD test */
   double term_penalty;     /* rho of the exact terminal penalty used inside the Riccati base factorisation */
+  double al_gamma;         /* relative weight of the exact augmented-Lagrangian convexification on warm-start active rows (0 = off) */
 } tmpc_opts;
 
 void tmpc_default_opts(tmpc_opts* o);
@@ -88,11 +89,11 @@ int tmpc_step_host(tmpc_handle* h, const double* X0_host, int64_t B, double* U0_
 int tmpc_plant_step(tmpc_handle* h, const double* X_dev, const double* U_dev, int64_t B, double* Xn_dev,
                     void* cuda_stream);
 
-/* per-step log tensors of the last tmpc_step, device pointers owned by the library, valid until the next call:
- * f (B) objective, nAS (B) active inequality rows, nACtot (B) active-set changes vs the initial guess,
- * nAC (B) stage-0 active-set changes vs the reference multipliers   (pmpc.py:815-856, sqp_method.py:203-219) */
-int tmpc_get_log(tmpc_handle* h, const double** f_dev, const int32_t** nAS_dev, const int32_t** nACtot_dev,
-                 const int32_t** nAC_dev);
+/* per-step log of the last tmpc_step, copied into caller buffers of B elements each (any may be NULL); the buffers are
+ * host memory if dst_is_host != 0, else device memory on the handle's device:
+ * f objective, nAS active inequality rows, nACtot active-set changes vs the initial guess,
+ * nAC stage-0 active-set changes vs the reference multipliers   (pmpc.py:815-856, sqp_method.py:203-219) */
+int tmpc_get_log(tmpc_handle* h, double* f, int32_t* nAS, int32_t* nACtot, int32_t* nAC, int dst_is_host);
 /* counters of the last tmpc_step: [0] SQP iterations summed over the batch, [1] kernel launches, [2] QP solves,
  * [3] stage linearisations (instance*stage), [4] plain dynamics evaluations (instance*stage) in the line search */
 int tmpc_get_counters(const tmpc_handle* h, int64_t out[8]);

@@ -1,0 +1,77 @@
+"""Generate the committed fixtures under tests/golden/ (run in the build container; needs oracle/ built).
+
+  problem_<cfg>.npz   the tuned MpcProblem (tables the controller is constructed from)
+  golden_<cfg>.npz    seeded x0 batch + the ORACLE's answers (oracle/reference_port.py, QP = the reference tree's
+                      qpOASES_e from oracle/_ref): u0, w, lam_g, iter, status, nAS at tol 1e-6 and tol 1e-9
+
+The reference itself cannot run here (CasADi absent), so these are outputs of the restatement, not of the reference:
+"parity unpinned" in the sense of SURVEY.md section 8(c).  Independent pins: LQ gain G (dense KKT).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import reference_port as rp            # noqa: E402
+from tunempc_b200 import configs                   # noqa: E402
+from tunempc_b200.problem import build_tables      # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def sample_x0(name, pb, B, seed=0):
+    """synthetic initial states of SURVEY.md section 8(d) (same generator as bench.py)"""
+    rng = np.random.default_rng(seed)
+    xs = pb.wref[0, :pb.nx]
+    if name == "lq":
+        return xs + rng.uniform(-1, 1, (B, pb.nx))
+    if name == "cstr":
+        alpha = rng.uniform(-0.1, 1.0, B)                       # examples/cstr/main.py:124
+        X0 = np.tile(xs, (B, 1))
+        X0[:, 0] += alpha * (1.0 - xs[0])                       # dx_diehl direction, examples/cstr/main.py:126-131
+        X0[:, 1:] += 1e-2 * np.abs(xs[1:]) * rng.uniform(-1, 1, (B, pb.nx - 1))
+        return X0
+    raise KeyError(name)
+
+
+def main():
+    rp.build()
+    for name, B in (("lq", 64), ("cstr", 48)):
+        st = rp.StageLib(name)
+        pb, info = configs.make_problem(name, st.F)
+        pb.save(os.path.join(HERE, "problem_%s.npz" % name))
+        X0 = sample_x0(name, pb, B)
+        out = {"X0": X0}
+        for tag, tol in (("t6", 1e-6), ("t9", 1e-9)):
+            ctrl = rp.Pmpc(pb, qp="qpoases", sqp_options={"tol": tol})
+            U, W, LAM, IT, ST, NAS = [], [], [], [], [], []
+            for b in range(B):
+                ctrl.reset()
+                u = ctrl.step(X0[b])
+                U.append(u); W.append(ctrl.w_sol); LAM.append(ctrl.lam_g)
+                IT.append(ctrl.log["iter"][-1]); ST.append(ctrl.log["status"][-1]); NAS.append(ctrl.log["nAS"][-1])
+            out.update({"u0_" + tag: np.array(U), "w_" + tag: np.array(W), "lam_" + tag: np.array(LAM),
+                        "iter_" + tag: np.array(IT), "status_" + tag: np.array(ST), "nAS_" + tag: np.array(NAS)})
+            print(name, tag, "iter hist", np.bincount(np.array(IT)), "status", np.bincount(np.array(ST)))
+        # closed loop of 5 steps on the first 8 instances (plant = model), oracle
+        ctrl = rp.Pmpc(pb, qp="qpoases")
+        Xcl = []
+        Ucl = []
+        for b in range(8):
+            ctrl.reset()
+            x = X0[b].copy()
+            xs_, us_ = [x.copy()], []
+            for _ in range(5):
+                u = ctrl.step(x)
+                x = st.F(x[None, :], u[None, :])[0]
+                xs_.append(x.copy()); us_.append(u.copy())
+            Xcl.append(xs_); Ucl.append(us_)
+        out["cl_X"] = np.array(Xcl)
+        out["cl_U"] = np.array(Ucl)
+        np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % name), **out)
+
+
+if __name__ == "__main__":
+    main()

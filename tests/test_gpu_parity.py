@@ -1,0 +1,155 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI (tunempc_b200.pmpc.Pmpc -> libtmpc_<model>.so),
+against the oracle's golden outputs, a live oracle, and size-independent properties at large batch."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, load_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _relerr(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0))
+
+
+@pytest.fixture(scope="module")
+def torch_mod(built):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _ctrl(name, **kw):
+    from tunempc_b200.pmpc import Pmpc
+    pb = load_problem(name)
+    for k, v in kw.items():
+        setattr(pb, k, v)
+    return Pmpc(pb, device=0), pb
+
+
+def test_lq_golden(torch_mod):
+    torch = torch_mod
+    ctrl, pb = _ctrl("lq")
+    gold = load_golden("lq")
+    U = ctrl.step(torch.tensor(gold["X0"], device="cuda:0"))
+    assert (ctrl.status.cpu().numpy() == 0).all()
+    assert (ctrl.log["iter"][-1].cpu().numpy() == 1).all()                      # LQ: one iteration is exact
+    assert _relerr(U.cpu().numpy(), gold["u0_t6"]) < 1e-10
+    assert _relerr(ctrl.w_sol.cpu().numpy(), gold["w_t6"]) < 1e-9
+    assert _relerr(ctrl.lam_g.cpu().numpy(), gold["lam_t6"]) < 1e-8
+    G = np.array([-0.08241103740895, -0.188345092908991, 0.225692606094775])    # SURVEY.md 8(c) known answer
+    assert np.allclose(U.cpu().numpy()[:, 0], gold["X0"] @ G, atol=1e-9)
+
+
+@pytest.mark.parametrize("tag,tol", [("t6", 1e-6), ("t9", 1e-9)])
+def test_cstr_golden(torch_mod, tag, tol):
+    torch = torch_mod
+    ctrl, pb = _ctrl("cstr", tol=tol)
+    gold = load_golden("cstr")
+    U = ctrl.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
+    st = ctrl.status.cpu().numpy()
+    assert (st == 0).all(), np.bincount(st)
+    assert _relerr(U, gold["u0_" + tag]) < 1e-6                                  # north_star: 1e-6 relative on u0
+    w = ctrl.w_sol.cpu().numpy()
+    assert _relerr(w, gold["w_" + tag]) < (1e-5 if tag == "t6" else 1e-6)        # predicted trajectory
+    lam = ctrl.lam_g.cpu().numpy()
+    for b in range(lam.shape[0]):                                                # identical active sets
+        assert set(np.nonzero(lam[b])[0]) == set(np.nonzero(gold["lam_" + tag][b])[0]), b
+    assert np.array_equal(ctrl.log["nAS"][-1].cpu().numpy(), gold["nAS_" + tag])
+    fl = ctrl.log["flags"][-1].cpu().numpy()
+    clean = (fl & 1) == 0
+    assert clean.any()
+    assert np.array_equal(ctrl.log["iter"][-1].cpu().numpy()[clean], gold["iter_" + tag][clean])
+    # g_sol: constraint values at the solution
+    g = ctrl.g_sol.cpu().numpy()
+    for k in range(pb.N):
+        assert np.abs(g[:, pb.g_dyn(k)]).max() < 10 * tol and g[:, pb.g_h(k)].min() > -10 * tol
+    assert np.abs(g[:, pb.g_init()]).max() < 10 * tol and np.abs(g[:, pb.g_term()]).max() < 10 * tol
+
+
+def test_cstr_live_oracle_and_host_path(torch_mod):
+    torch = torch_mod
+    from oracle import reference_port as rp
+    ctrl, pb = _ctrl("cstr")
+    rng = np.random.default_rng(77)
+    xs = pb.wref[0, :4]
+    X0 = np.tile(xs, (6, 1))
+    X0[:, 0] += rng.uniform(-0.1, 1.0, 6) * (1.0 - xs[0])
+    U_host = ctrl.step(X0)                                                       # numpy in -> tmpc_step_host
+    w_host = ctrl.w_sol.copy()
+    ctrl.reset()
+    U_dev = ctrl.step(torch.tensor(X0, device="cuda:0")).cpu().numpy()           # device tensors -> tmpc_step
+    assert np.array_equal(U_host, U_dev) and np.array_equal(w_host, ctrl.w_sol.cpu().numpy())
+    oc = rp.Pmpc(pb)
+    for b in range(6):
+        oc.reset()
+        uo = oc.step(X0[b])
+        assert _relerr(U_dev[b], uo) < 1e-6
+        assert set(np.nonzero(ctrl.lam_g.cpu().numpy()[b])[0]) == set(np.nonzero(oc.lam_g)[0])
+    # reference single-instance semantics: (nx,) in -> (nu,) out; reset-then-step idempotent (P5)
+    ctrl.reset()
+    u1 = ctrl.step(X0[0])
+    ctrl.reset()
+    u2 = ctrl.step(X0[0].reshape(4, 1))
+    assert u1.shape == (2,) and u2.shape == (2, 1) and np.array_equal(u1, u2[:, 0]) and np.array_equal(u1, U_dev[0])
+
+
+def test_cstr_reference_point(torch_mod):
+    torch = torch_mod
+    ctrl, pb = _ctrl("cstr")
+    X0 = torch.tensor(np.tile(pb.wref[0, :4], (3, 1)), device="cuda:0")
+    U = ctrl.step(X0).cpu().numpy()                                              # P1: step(x_ref) = u_ref
+    assert np.allclose(U, pb.wref[0, 4:], rtol=1e-9)
+    assert (ctrl.log["iter"][-1].cpu().numpy() == 1).all()                       # always >= 1 QP (sqp_method.py:145-146)
+
+
+def test_cstr_closed_loop_and_shift(torch_mod):
+    torch = torch_mod
+    ctrl, pb = _ctrl("cstr")
+    gold = load_golden("cstr")
+    X = torch.tensor(gold["cl_X"][:, 0], device="cuda:0")
+    for s in range(5):
+        U = ctrl.step(X)
+        assert _relerr(U.cpu().numpy(), gold["cl_U"][:, s]) < 1e-6, s
+        X = ctrl.plant_step(X, U)                                                # closed_loop_tools.py:102
+        assert _relerr(X.cpu().numpy(), gold["cl_X"][:, s + 1]) < 1e-6, s
+    assert ctrl.index == 5
+
+
+def test_gauss_newton_same_solution(torch_mod):
+    torch = torch_mod
+    a, pb = _ctrl("cstr", tol=1e-9)
+    b, _ = _ctrl("cstr", tol=1e-9, hessian_approximation="gauss_newton")
+    gold = load_golden("cstr")
+    X0 = torch.tensor(gold["X0"][:16], device="cuda:0")
+    Ua, Ub = a.step(X0).cpu().numpy(), b.step(X0).cpu().numpy()
+    ok = (a.status.cpu().numpy() == 0) & (b.status.cpu().numpy() == 0)
+    assert ok.sum() >= 12
+    assert _relerr(Ua[ok], Ub[ok]) < 1e-6                                        # P3: Hessian-mode independence
+
+
+def test_large_batch_properties(torch_mod):
+    """size-independent properties at 2^16 instances: every instance converges, the result of an instance does not
+    depend on its neighbours (bitwise), sharding the batch changes nothing (bitwise), KKT conditions hold."""
+    torch = torch_mod
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import sample_x0
+    ctrl, pb = _ctrl("cstr")
+    B = 1 << 16
+    X0 = torch.tensor(sample_x0(pb, B, 5), device="cuda:0")
+    U = ctrl.step(X0)
+    st = ctrl.status.cpu().numpy()
+    assert (st == 0).mean() >= 0.99, np.bincount(st)
+    w, lam, g = ctrl.w_sol, ctrl.lam_g, ctrl.g_sol
+    ok = torch.tensor(st == 0, device="cuda:0")
+    for k in range(pb.N):
+        assert g[ok][:, pb.g_dyn(k)].abs().max().item() < 1e-5
+        assert g[ok][:, pb.g_h(k)].min().item() > -1e-5
+        lh = lam[ok][:, pb.g_h(k)]
+        assert lh.max().item() <= 0.0                                            # multiplier sign
+        assert (lh * g[ok][:, pb.g_h(k)]).abs().max().item() < 1e-4              # complementarity
+    c2, _ = _ctrl("cstr")
+    idx = torch.arange(1000, 1000 + 512, device="cuda:0")
+    U2 = c2.step(X0[idx].contiguous())
+    assert torch.equal(U2, U[idx]) and torch.equal(c2.w_sol, w[idx])             # neighbours / sharding invariance

@@ -1,0 +1,80 @@
+"""CPU tests of the CUDA source compiled as a 1-lane host program (tests/twin) against the oracle / golden fixtures.
+Checks the algorithm the kernels implement (pair-wise sensitivity integration, Riccati + dual active-set QP, filter line
+search, convergence, shift) without a GPU; the same comparisons run against the real kernels in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, load_problem
+
+
+@pytest.fixture(scope="module")
+def env(built):
+    from oracle import reference_port as rp
+    from tunempc_b200.problem import build_tables
+    from twin.twin import Twin
+    return rp, build_tables, Twin
+
+
+def _relerr(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0))
+
+
+def test_twin_stage_eval_matches_oracle(env):
+    rp, build_tables, Twin = env
+    for name in ("lq", "cstr"):
+        pb = load_problem(name)
+        tw = Twin(pb, build_tables(pb))
+        rng = np.random.default_rng(1)
+        z = pb.wref[0] * (1 + 0.05 * rng.standard_normal((6, pb.nz))) + 0.1 * rng.standard_normal((6, pb.nz))
+        a = rp.StageLib(name).F(z[:, :pb.nx], z[:, pb.nx:], 2)
+        b = tw.stage_eval(z[:, :pb.nx], z[:, pb.nx:], 2)
+        for x, y in zip(a, b):
+            assert np.max(np.abs(x - y)) <= 1e-12 * max(1.0, np.max(np.abs(x)))
+
+
+def test_twin_lq_golden(env):
+    rp, build_tables, Twin = env
+    pb, gold = load_problem("lq"), load_golden("lq")
+    tw = Twin(pb, build_tables(pb))
+    tw.reset(64)
+    o = tw.step(gold["X0"])
+    assert (o["status"] == 0).all() and (o["iter"] == 1).all()
+    assert _relerr(o["u0"], gold["u0_t6"]) < 1e-10
+    assert _relerr(o["w"], gold["w_t6"]) < 1e-9
+    assert _relerr(o["lam"], gold["lam_t6"]) < 1e-8
+
+
+def test_twin_cstr_golden(env):
+    rp, build_tables, Twin = env
+    pb, gold = load_problem("cstr"), load_golden("cstr")
+    n = 48
+    tw = Twin(pb, build_tables(pb), rho=1e6, al_gamma=1e3)
+    tw.reset(n)
+    o = tw.step(gold["X0"][:n])
+    assert (o["status"] == 0).all()
+    assert _relerr(o["u0"], gold["u0_t6"][:n]) < 1e-6                 # north_star tolerance: 1e-6 relative on u0
+    assert _relerr(o["w"], gold["w_t6"][:n]) < 1e-5                   # both sides stop at KKT residual 1e-6
+    for b in range(n):                                                # identical active sets
+        assert set(np.nonzero(o["lam"][b])[0]) == set(np.nonzero(gold["lam_t6"][b])[0])
+    assert np.array_equal(o["nAS"], gold["nAS_t6"][:n])
+    clean = (o["flags"] & 1) == 0                                         # no convexification: same iteration path
+    assert clean.any() and np.array_equal(o["iter"][clean], gold["iter_t6"][:n][clean])
+
+
+def test_twin_shift_and_closed_loop(env):
+    rp, build_tables, Twin = env
+    pb, gold = load_problem("cstr"), load_golden("cstr")
+    tw = Twin(pb, build_tables(pb), rho=1e6, al_gamma=1e3)
+    st = rp.StageLib("cstr")
+    n = 2
+    tw.reset(n)
+    x = gold["X0"][:n].copy()
+    for s in range(3):
+        o = tw.step(x)
+        assert _relerr(o["u0"], gold["cl_U"][:n, s]) < 1e-6
+        x = st.F(x, o["u0"])
+        assert _relerr(x, gold["cl_X"][:n, s + 1]) < 1e-6
+    # shift: compare with the oracle's own shift of the same solution
+    oc = rp.Pmpc(pb)
+    ws, ls = oc._shift(o["w"][0], o["lam"][0])
+    assert np.array_equal(tw.W[0], ws) and np.array_equal(tw.LAM[0], ls)

@@ -159,7 +159,8 @@ void tmpc_default_opts(tmpc_opts* o) {
   o->lam_tresh = 1e-8;
   o->ls_step_factor = 0.8;
   o->reg_tol = 1e-8;
-  o->term_penalty = 1.0;
+  o->term_penalty = 1e6;
+  o->al_gamma = 1e3;
 }
 
 const char* tmpc_model_info(int32_t* nx, int32_t* nu, int32_t* rk_steps, double* dt) {
@@ -205,7 +206,7 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
   P.maxact = 32;
   if (P.maxact < P.nxt + 4) P.maxact = P.nxt + 4;
   P.tol = h->opts.tol; P.lam_tresh = h->opts.lam_tresh; P.beta = h->opts.ls_step_factor;
-  P.reg_tol = h->opts.reg_tol; P.rho = h->opts.term_penalty;
+  P.reg_tol = h->opts.reg_tol; P.rho = h->opts.term_penalty; P.al_gamma = h->opts.al_gamma;
   h->qp_smem = QP_WARPS * tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact) * sizeof(double);
   if (h->qp_smem > 227 * 1024) {
     fprintf(stderr, "tmpc_create: QP workspace %zu B exceeds shared memory\n", h->qp_smem);
@@ -237,6 +238,7 @@ void tmpc_destroy(tmpc_handle* h) {
   delete h;
 }
 
+}  // extern C (templates need C++ linkage)
 template <typename T>
 static int upload(tmpc_handle* h, std::vector<void*>& owner, const T* src, size_t n, const T** dst) {
   T* d = nullptr;
@@ -247,6 +249,7 @@ static int upload(tmpc_handle* h, std::vector<void*>& owner, const T* src, size_
   return 0;
 }
 
+extern "C" {
 int tmpc_set_tables(tmpc_handle* h, const double* wref, const double* H, const double* q, const double* ref_du,
                     const double* C, const double* c, const int32_t* term_idx, const int32_t* relax0) {
   if (!h) return 1;
@@ -271,6 +274,7 @@ int tmpc_set_tables(tmpc_handle* h, const double* wref, const double* H, const d
   return 0;
 }
 
+}  // extern C
 template <typename T>
 static int dalloc(tmpc_handle* h, T** p, size_t n) {
   CK(cudaMalloc(p, (n ? n : 1) * sizeof(T)));
@@ -300,6 +304,7 @@ static int ensure_capacity(tmpc_handle* h, int64_t B) {
   return 0;
 }
 
+extern "C" {
 int tmpc_reset(tmpc_handle* h, int64_t B) {
   if (!h) return 1;
   if (!h->tables_set) { h->err = "tmpc_reset: tables not set"; return 1; }
@@ -462,13 +467,15 @@ int tmpc_plant_step(tmpc_handle* h, const double* X_dev, const double* U_dev, in
   return 0;
 }
 
-int tmpc_get_log(tmpc_handle* h, const double** f_dev, const int32_t** nAS_dev, const int32_t** nACtot_dev,
-                 const int32_t** nAC_dev) {
+int tmpc_get_log(tmpc_handle* h, double* f, int32_t* nAS, int32_t* nACtot, int32_t* nAC, int dst_is_host) {
   if (!h) return 1;
-  if (f_dev) *f_dev = h->S.fval;
-  if (nAS_dev) *nAS_dev = h->S.nAS;
-  if (nACtot_dev) *nACtot_dev = h->S.nACtot;
-  if (nAC_dev) *nAC_dev = h->S.nAC;
+  cudaSetDevice(h->device);
+  const cudaMemcpyKind kd = dst_is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  const size_t b = (size_t)h->S.B;
+  if (f) CK(cudaMemcpy(f, h->S.fval, b * sizeof(double), kd));
+  if (nAS) CK(cudaMemcpy(nAS, h->S.nAS, b * sizeof(int), kd));
+  if (nACtot) CK(cudaMemcpy(nACtot, h->S.nACtot, b * sizeof(int), kd));
+  if (nAC) CK(cudaMemcpy(nAC, h->S.nAC, b * sizeof(int), kd));
   return 0;
 }
 
