@@ -100,7 +100,7 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
     if (++guard > P.max_iter + 2) return 9;
   }
   for (long long i = 0; i < B; ++i) tm_shift(P, W + i * P.n_w, LAM + i * P.n_g, Wsh + i * P.n_w, Lsh + i * P.n_g);
-  if (counters_out) { counters_out[0] = (long long)counters[0]; counters_out[2] = nqp; counters_out[3] = nlin; counters_out[4] = (long long)counters[4]; }
+  if (counters_out) { counters_out[0] = (long long)counters[0]; counters_out[2] = nqp; counters_out[3] = nlin; counters_out[4] = (long long)counters[4]; counters_out[5] = (long long)counters[5]; counters_out[6] = (long long)counters[6]; counters_out[7] = (long long)counters[7]; }
   return 0;
 }
 

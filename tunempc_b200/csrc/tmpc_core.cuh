@@ -26,7 +26,8 @@
 #define TM_HDN static
 #endif
 
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(TM_THREAD_MODE)
+#define TM_WARP_MODE 1
 #define TM_LANE ((int)(threadIdx.x & 31))
 #define TM_NL 32
 #define TM_SYNC() __syncwarp()
@@ -64,6 +65,23 @@ TM_HD double tm_wmax(double v) { return v; }
 TM_HD int tm_wsumi(int v) { return v; }
 TM_HD void tm_wargmin(double&, int&) {}
 TM_HD int tm_wany(int p) { return p; }
+#endif
+
+// workspace accessor: plain pointer (shared memory, warp-per-instance; host twin) or a lane-interleaved view of global
+// memory (thread-per-instance mode: element e of lane l lives at base[e*TM_WS_STRIDE + l], so a warp touching the same
+// element of its 32 instances issues one coalesced 256-byte transaction)
+#ifdef TM_WS_STRIDE
+struct TmP {
+  double* p;
+  TM_HD double& operator[](int i) const { return p[(size_t)i * TM_WS_STRIDE]; }
+  TM_HD double& operator[](size_t i) const { return p[i * TM_WS_STRIDE]; }
+  TM_HD TmP operator+(size_t o) const { TmP r; r.p = p + o * TM_WS_STRIDE; return r; }
+  TM_HD TmP operator+(int o) const { TmP r; r.p = p + (size_t)o * TM_WS_STRIDE; return r; }
+};
+TM_HD TmP tm_mkp(double* base, size_t off) { TmP r; r.p = base + off * TM_WS_STRIDE; return r; }
+#else
+typedef double* TmP;
+TM_HD TmP tm_mkp(double* base, size_t off) { return base + off; }
 #endif
 
 #define NX TMPC_NX
@@ -260,9 +278,8 @@ TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, i
 // Exact active-set solution: inactive multipliers are exact zeros, as the reference relies on (sqp_method.py:421).
 // ---------------------------------------------------------------------------------------------------------------
 struct TmQpWs {
-  double *AB, *Q, *r, *b, *K, *Lc, *hv, *d, *y, *z, *rhs, *kk, *P0, *P1, *PAB, *F, *pv, *tr, *S, *Sc, *cA, *rv, *nu;
-  int *actk, *acti;
-  double* acts;
+  TmP AB, Q, r, b, K, Lc, hv, d, y, z, rhs, kk, P0, P1, PAB, F, pv, tr, S, Sc, cA, rv, nu;
+  TmP actk, acti, acts;   // working-set rows: stage (N = terminal), row index, sign (small integers stored as doubles)
 };
 
 TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
@@ -279,38 +296,40 @@ TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
   n += 2 * NX * NX + NX * NZ + NZ * NZ;   // P0 P1 PAB F
   n += 4 * NX;                     // pv (two buffers of NX, e0, spare)
   n += (nxt > 0 ? nxt : 1);        // tr
-  n += 2 * (size_t)M * M + 3 * (size_t)M + M;   // S Sc cA rv nu acts
-  n += M;                          // actk/acti packed as ints in one double-sized slot each (2 ints per double)
+  n += 2 * (size_t)M * M + 6 * (size_t)M;   // S Sc | cA rv nu acts actk acti
   return n;
 }
 
 TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s) {
-  double* p = base;
-  s.AB = p; p += (size_t)N * NX * NZ;
-  s.Q = p; p += (size_t)N * NZ * NZ;
-  s.r = p; p += (size_t)(N + 1) * NZ;
-  s.b = p; p += (size_t)N * NX;
-  s.K = p; p += (size_t)N * NU * NX;
-  s.Lc = p; p += (size_t)N * NU * NU;
-  s.hv = p; p += (size_t)N * (nh > 0 ? nh : 1);
-  s.d = p; p += (size_t)(N + 1) * NZ;
-  s.y = p; p += (size_t)(N + 1) * NZ;
-  s.z = p; p += (size_t)(N + 1) * NZ;
-  s.rhs = p; p += (size_t)(N + 1) * NZ;
-  s.kk = p; p += (size_t)N * NU;
-  s.P0 = p; p += NX * NX;
-  s.P1 = p; p += NX * NX;
-  s.PAB = p; p += NX * NZ;
-  s.F = p; p += NZ * NZ;
-  s.pv = p; p += 4 * NX;
-  s.tr = p; p += (nxt > 0 ? nxt : 1);
-  s.S = p; p += (size_t)M * M;
-  s.Sc = p; p += (size_t)M * M;
-  s.cA = p; p += M;
-  s.rv = p; p += M;
-  s.nu = p; p += M;
-  s.acts = p; p += M;
-  s.actk = (int*)p; s.acti = s.actk + M; p += M;
+  size_t o = 0;
+#define TM_CARVE(member, n) s.member = tm_mkp(base, o); o += (size_t)(n)
+  TM_CARVE(AB, (size_t)N * NX * NZ);
+  TM_CARVE(Q, (size_t)N * NZ * NZ);
+  TM_CARVE(r, (size_t)(N + 1) * NZ);
+  TM_CARVE(b, (size_t)N * NX);
+  TM_CARVE(K, (size_t)N * NU * NX);
+  TM_CARVE(Lc, (size_t)N * NU * NU);
+  TM_CARVE(hv, (size_t)N * (nh > 0 ? nh : 1));
+  TM_CARVE(d, (size_t)(N + 1) * NZ);
+  TM_CARVE(y, (size_t)(N + 1) * NZ);
+  TM_CARVE(z, (size_t)(N + 1) * NZ);
+  TM_CARVE(rhs, (size_t)(N + 1) * NZ);
+  TM_CARVE(kk, (size_t)N * NU);
+  TM_CARVE(P0, NX * NX);
+  TM_CARVE(P1, NX * NX);
+  TM_CARVE(PAB, NX * NZ);
+  TM_CARVE(F, NZ * NZ);
+  TM_CARVE(pv, 4 * NX);
+  TM_CARVE(tr, (nxt > 0 ? nxt : 1));
+  TM_CARVE(S, (size_t)M * M);
+  TM_CARVE(Sc, (size_t)M * M);
+  TM_CARVE(cA, M);
+  TM_CARVE(rv, M);
+  TM_CARVE(nu, M);
+  TM_CARVE(acts, M);
+  TM_CARVE(actk, M);
+  TM_CARVE(acti, M);
+#undef TM_CARVE
 }
 
 // Cholesky of the NU x NU block Fuu (row-major, in registers of every lane): returns 0 if a pivot <= thr
@@ -332,7 +351,8 @@ TM_HD int tm_chol_small(const double* Fuu, double* L, double thr) {
   return 1;
 }
 // solve (L L') x = rhs in place
-TM_HD void tm_chol_small_solve(const double* L, double* x) {
+template <class PL>
+TM_HD void tm_chol_small_solve(PL L, double* x) {
   for (int i = 0; i < NU; ++i) {
     double v = x[i];
     for (int l = 0; l < i; ++l) v -= L[i * NU + l] * x[l];
@@ -346,18 +366,18 @@ TM_HD void tm_chol_small_solve(const double* L, double* x) {
 }
 
 // homogeneous base solve:  out = argmin 1/2 d'Qd + rhs'd  s.t. d_x0 = 0, d_x(k+1) = A d_x + B d_u   ( = -G rhs )
-TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, const double* rhs, double* out) {
+TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, TmP rhs, TmP out) {
   const int N = P.N;
   const int lane = TM_LANE;
-  double* pv0 = s.pv;
-  double* pv1 = s.pv + NX;
+  TmP pv0 = s.pv;
+  TmP pv1 = s.pv + NX;
   for (int a = lane; a < NX; a += TM_NL) pv0[a] = rhs[N * NZ + a];
   TM_SYNC();
   for (int k = N - 1; k >= 0; --k) {
-    const double* AB = s.AB + (size_t)k * NX * NZ;
-    const double* Kk = s.K + (size_t)k * NU * NX;
-    const double* L = s.Lc + (size_t)k * NU * NU;
-    const double* rk = rhs + k * NZ;
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NU * NX;
+    const TmP L = s.Lc + (size_t)k * NU * NU;
+    const TmP rk = rhs + k * NZ;
     double fu[NU];
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
@@ -380,14 +400,14 @@ TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, const double* rhs, double* 
     tm_chol_small_solve(L, ku);
     for (int a = lane; a < NU; a += TM_NL) s.kk[k * NU + a] = ku[a];
     TM_SYNC();
-    double* t = pv0; pv0 = pv1; pv1 = t;
+    TmP t = pv0; pv0 = pv1; pv1 = t;
   }
   for (int a = lane; a < NX; a += TM_NL) out[a] = 0.0;
   TM_SYNC();
   for (int k = 0; k < N; ++k) {
-    const double* AB = s.AB + (size_t)k * NX * NZ;
-    const double* Kk = s.K + (size_t)k * NU * NX;
-    const double* dx = out + k * NZ;
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NU * NX;
+    const TmP dx = out + k * NZ;
     double du[NU];
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
@@ -412,17 +432,17 @@ TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, const double* rhs, double* 
 }
 
 // constraint row helpers.  row m of the working set: stage actk (== N for a terminal row), row acti, sign acts
-TM_HD double tm_row_dot(const TmProb& P, int k, int i, double sg, const double* v) {
+TM_HD double tm_row_dot(const TmProb& P, int k, int i, double sg, TmP v) {
   if (k == P.N) return sg * v[P.N * NZ + P.term_idx[i]];
   double t = 0.0;
   const double* Ci = P.C + (size_t)i * NZ;
-  const double* vk = v + k * NZ;
+  const TmP vk = v + k * NZ;
 #pragma unroll
   for (int b = 0; b < NZ; ++b) t += Ci[b] * vk[b];
   return t;
 }
 // rhs += coef * n   (single lane)
-TM_HD void tm_row_axpy(const TmProb& P, int k, int i, double sg, double coef, double* rhs) {
+TM_HD void tm_row_axpy(const TmProb& P, int k, int i, double sg, double coef, TmP rhs) {
   if (k == P.N) { rhs[P.N * NZ + P.term_idx[i]] += coef * sg; return; }
   const double* Ci = P.C + (size_t)i * NZ;
 #pragma unroll
@@ -430,9 +450,9 @@ TM_HD void tm_row_axpy(const TmProb& P, int k, int i, double sg, double coef, do
 }
 
 // dense Cholesky solve  S r = c  for the m x m working-set Schur complement (stride M); returns 0 on breakdown
-TM_HD int tm_schur_solve(TmQpWs& s, int m, int M, double* r) {
+TM_HD int tm_schur_solve(TmQpWs& s, int m, int M, TmP r) {
   const int lane = TM_LANE;
-  double* Sc = s.Sc;
+  TmP Sc = s.Sc;
   for (int e = lane; e < m * m; e += TM_NL) { int i = e / m, j = e % m; Sc[i * M + j] = s.S[i * M + j]; }
   TM_SYNC();
   int ok = 1;
@@ -509,7 +529,7 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     for (int j = 0; j < NZ; ++j) v += P.C[(size_t)i * NZ + j] * w[k * NZ + j];
     s.hv[e] = v;
   }
-  double* e0 = s.pv + 2 * NX;
+  TmP e0 = s.pv + 2 * NX;
   for (int a = lane; a < NX; a += TM_NL) e0[a] = S.X0[inst * NX + a] - w[a];
   {
     const double* xrN = P.wref + (size_t)((S.phase + N) % P.p) * NZ;
@@ -542,10 +562,10 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     TM_SYNC();
   }
   // ---- B. Riccati factorisation + main solve (offsets b_k, e0, terminal penalty) -------------------------------
-  double* Pn = s.P0;   // P_{k+1}
-  double* Pk = s.P1;
-  double* pv0 = s.pv;
-  double* pv1 = s.pv + NX;
+  TmP Pn = s.P0;   // P_{k+1}
+  TmP Pk = s.P1;
+  TmP pv0 = s.pv;
+  TmP pv1 = s.pv + NX;
   for (int e = lane; e < NX * NX; e += TM_NL) {
     int i = e / NX, j = e % NX;
     double v = 0.0;
@@ -560,8 +580,8 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   TM_SYNC();
   int fail = 0;
   for (int k = N - 1; k >= 0; --k) {
-    const double* AB = s.AB + (size_t)k * NX * NZ;
-    const double* Qk = s.Q + (size_t)k * NZ * NZ;
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Qk = s.Q + (size_t)k * NZ * NZ;
     for (int e = lane; e < NX * NZ; e += TM_NL) {
       int i = e / NZ, c = e % NZ;
       double v = 0.0;
@@ -595,7 +615,7 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
       for (int a = 0; a < NU; ++a) s.K[(size_t)k * NU * NX + a * NX + j] = col[a];
     }
     TM_SYNC();
-    const double* Kk = s.K + (size_t)k * NU * NX;
+    const TmP Kk = s.K + (size_t)k * NU * NX;
     // P_k = Fxx + sym(Fux' K)
     for (int e = lane; e < NX * NX; e += TM_NL) {
       int i = e / NX, j = e % NX;
@@ -641,17 +661,17 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
       for (int a = lane; a < NU; a += TM_NL) s.kk[k * NU + a] = ku[a];
     }
     TM_SYNC();
-    { double* t = Pn; Pn = Pk; Pk = t; }
-    { double* t = pv0; pv0 = pv1; pv1 = t; }
+    { TmP t = Pn; Pn = Pk; Pk = t; }
+    { TmP t = pv0; pv0 = pv1; pv1 = t; }
   }
   if (fail) return 3;
   // forward sweep of the main solve
   for (int a = lane; a < NX; a += TM_NL) s.d[a] = e0[a];
   TM_SYNC();
   for (int k = 0; k < N; ++k) {
-    const double* AB = s.AB + (size_t)k * NX * NZ;
-    const double* Kk = s.K + (size_t)k * NU * NX;
-    const double* dx = s.d + k * NZ;
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NU * NX;
+    const TmP dx = s.d + k * NZ;
     double du[NU];
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
@@ -675,6 +695,7 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   TM_SYNC();
   // ---- C. Goldfarb-Idnani on the Schur complement ------------------------------------------------------------
   int m = 0, neq = 0, ret = 0;
+  int n_gi = 0, n_ricc = 0;
   const int maxit = 4 * (nxt + N * nh) + 8;
   for (int it = 0; it < maxit; ++it) {
     int qk, qi;
@@ -713,20 +734,22 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     if (lane == 0) tm_row_axpy(P, qk, qi, qs, -1.0, s.rhs);
     TM_SYNC();
     tm_ricc_solve(P, s, s.rhs, s.y);
-    for (int j2 = lane; j2 < m; j2 += TM_NL) s.cA[j2] = tm_row_dot(P, s.actk[j2], s.acti[j2], s.acts[j2], s.y);
+    ++n_gi; ++n_ricc;
+    for (int j2 = lane; j2 < m; j2 += TM_NL) s.cA[j2] = tm_row_dot(P, (int)s.actk[j2], (int)s.acti[j2], s.acts[j2], s.y);
     const double yq = tm_row_dot(P, qk, qi, qs, s.y);
     TM_SYNC();
     double nq = 0.0;
     int added = 0;
     for (int inner = 0; inner < M + 2; ++inner) {
-      const double* zz = s.y;
+      TmP zz = s.y;
       if (m > 0) {
         if (!tm_schur_solve(s, m, M, s.rv)) { ret = 2; break; }
         for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.rhs[e] = 0.0;
         TM_SYNC();
-        if (lane == 0) for (int j2 = 0; j2 < m; ++j2) tm_row_axpy(P, s.actk[j2], s.acti[j2], s.acts[j2], s.rv[j2], s.rhs);
+        if (lane == 0) for (int j2 = 0; j2 < m; ++j2) tm_row_axpy(P, (int)s.actk[j2], (int)s.acti[j2], s.acts[j2], s.rv[j2], s.rhs);
         TM_SYNC();
         tm_ricc_solve(P, s, s.rhs, s.z);
+        ++n_ricc;
         for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.z[e] += s.y[e];
         TM_SYNC();
         zz = s.z;
@@ -783,6 +806,13 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     if (!added) { ret = 2; break; }
     if (it == maxit - 1) ret = 2;
   }
+  if (lane == 0) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(S.counters + 5, 1ull); atomicAdd(S.counters + 6, (unsigned long long)n_gi); atomicAdd(S.counters + 7, (unsigned long long)n_ricc);
+#else
+    S.counters[5] += 1; S.counters[6] += n_gi; S.counters[7] += n_ricc;
+#endif
+  }
   if (ret) return ret;
   if (al_mask) {
     int nbad = 0;
@@ -803,8 +833,8 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   TM_SYNC();
   if (lane == 0) {
     for (int j2 = 0; j2 < m; ++j2) {
-      if (s.actk[j2] == N) lq[tm_gterm(P) + s.acti[j2]] = -s.acts[j2] * s.nu[j2];
-      else lq[tm_gh(P, s.actk[j2]) + s.acti[j2]] = -s.nu[j2];
+      if (s.actk[j2] == N) lq[tm_gterm(P) + (int)s.acti[j2]] = -s.acts[j2] * s.nu[j2];
+      else lq[tm_gh(P, (int)s.actk[j2]) + (int)s.acti[j2]] = -s.nu[j2];
     }
   }
   TM_SYNC();
@@ -817,8 +847,8 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   }
   TM_SYNC();
   for (int k = N - 1; k >= 0; --k) {
-    const double* AB = s.AB + (size_t)k * NX * NZ;
-    const double* Qk = s.Q + (size_t)k * NZ * NZ;
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Qk = s.Q + (size_t)k * NZ * NZ;
     for (int a = lane; a < NX; a += TM_NL) lq[tm_gdyn(P, k) + a] = pv0[a];
     for (int j = lane; j < NX; j += TM_NL) {
       double v = s.r[k * NZ + j];
@@ -830,7 +860,7 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
       pv1[j] = v;
     }
     TM_SYNC();
-    { double* t = pv0; pv0 = pv1; pv1 = t; }
+    { TmP t = pv0; pv0 = pv1; pv1 = t; }
   }
   for (int a = lane; a < NX; a += TM_NL) lq[a] = -pv0[a];
   TM_SYNC();
