@@ -63,13 +63,15 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
   S.status = status; S.iter = iter; S.flags = flags; S.fval = fval; S.nAS = nAS; S.nACtot = nACtot; S.nAC = nAC;
   std::vector<double> D((size_t)B * P.n_w), LQ((size_t)B * P.n_g), LIN((size_t)B * P.N * TM_LSZ),
       FILT((size_t)B * P.filter_cap * 2);
-  std::vector<int> nfilt(B), qpstat(B, 0), la(B), lb(B), lrel(B);
+  std::vector<int> nfilt(B), qpstat(B, 0), qpmode(B, 0), la(B), lb(B), lrel(B), lretry(B);
+  std::vector<unsigned> almask((size_t)B * TM_ALW);
+  int cnt_retry = 0;
   S.aswords = (P.N * P.nh + 31) / 32; if (S.aswords < 1) S.aswords = 1;
   std::vector<unsigned> asinit((size_t)B * S.aswords);
   unsigned long long counters[8] = {0};
   int cnts[2] = {0, 0};
   S.D = D.data(); S.LAMQ = LQ.data(); S.LIN = LIN.data(); S.FILT = FILT.data(); S.nfilt = nfilt.data();
-  S.qpstat = qpstat.data(); S.asinit = asinit.data(); S.counters = counters;
+  S.qpstat = qpstat.data(); S.qpmode = qpmode.data(); S.almask = almask.data(); S.list_retry = lretry.data(); S.cnt_retry = &cnt_retry; S.asinit = asinit.data(); S.counters = counters;
   S.cnt_next = &cnts[0]; S.cnt_relin = &cnts[1]; S.list_relin = lrel.data();
   const int per = P.hessian_exact ? TM_NPAIR : NZ;
   std::vector<double> wsbuf(tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact));
@@ -87,7 +89,13 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
   while (nact > 0) {
     S.list_next = nxt->data();
     cnts[0] = cnts[1] = 0;
+    cnt_retry = 0;
     for (long long s = 0; s < nact; ++s) tm_qp(P, S, (*cur)[s], ws);
+    for (int pass = 0; pass < 5 && cnt_retry > 0; ++pass) {      // re-solves (mask shrink / Gauss-Newton fallback)
+      std::vector<int> todo(lretry.begin(), lretry.begin() + cnt_retry);
+      cnt_retry = 0;
+      for (int v : todo) tm_qp(P, S, v, ws);
+    }
     for (long long s = 0; s < nact; ++s) for (int k = 0; k < P.N; ++k) for (int pr = 0; pr < per; ++pr) tm_lin_task(P, S, (*cur)[s], k, pr, 1);
     for (long long s = 0; s < nact; ++s) tm_post(P, S, (*cur)[s]);
     nqp += nact; nlin += nact * P.N;

@@ -21,6 +21,11 @@
 #include "tmpc.h"
 #include "tmpc_core.cuh"
 
+// thread-per-instance QP kernel (tmpc_qp_thread.cu)
+cudaError_t tm_launch_qp_thread(const TmProb& P, const TmState& S, const int* list, int cnt, const int* cnt_dev,
+                                double* wsbase, size_t ws_per_inst, int nblocks, int* work_counter, cudaStream_t st);
+int tm_qp_thread_block();
+
 #define QP_WARPS 4          /* warps (instances) per CTA in the warp-per-instance kernels */
 #define LIN_THREADS 128
 
@@ -35,7 +40,8 @@ struct tmpc_handle {
   bool tables_set = false;
   std::string err;
   std::vector<void*> tab_allocs, ws_allocs;
-  int *list_a = nullptr, *list_b = nullptr, *cnts = nullptr;   // cnts[0] next, cnts[1] relin
+  int *list_a = nullptr, *list_b = nullptr, *cnts = nullptr;   // cnts[0] next, cnts[1] relin, cnts[2..3] retry ping-pong
+  int *retry_a = nullptr, *retry_b = nullptr;
   double *Wsh = nullptr, *Lsh = nullptr;                       // shift targets
   double* X0buf = nullptr;                                     // device staging for tmpc_step_host
   int64_t counters_host[8] = {0};
@@ -43,6 +49,11 @@ struct tmpc_handle {
   cudaEvent_t ev[8];
   bool ev_ok = false;
   size_t qp_smem = 0;
+  int qp_mode = 1;             // 1: thread per instance (global interleaved workspace), 0: warp per instance (shared memory)
+  int qp_blocks = 0;           // resident CTAs of the thread-per-instance kernel
+  double* qp_ws = nullptr;     // its workspace
+  size_t qp_ws_per_inst = 0;
+  int* qp_counter = nullptr;
 };
 
 static int fail(tmpc_handle* h, const char* what, cudaError_t e) {
@@ -79,8 +90,9 @@ __global__ void k_init(TmProb P, TmState S) {
   tm_init(P, S, inst);
 }
 
-__global__ void __launch_bounds__(QP_WARPS * 32) k_qp(TmProb P, TmState S, const int* list, int cnt) {
+__global__ void __launch_bounds__(QP_WARPS * 32) k_qp(TmProb P, TmState S, const int* list, int cnt, const int* cnt_dev) {
   extern __shared__ double smem[];
+  if (cnt_dev) cnt = *cnt_dev;
   const int wid = threadIdx.x / 32;
   const int64_t slot = (int64_t)blockIdx.x * QP_WARPS + wid;
   if (slot >= cnt) return;
@@ -218,6 +230,27 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
     delete h;
     return 4;
   }
+  {
+    const char* m = getenv("TMPC_QP_MODE");
+    if (m && m[0] == 'w') h->qp_mode = 0;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    int tps = 512;
+    const char* t = getenv("TMPC_QP_THREADS_PER_SM");
+    if (t) tps = atoi(t);
+    if (tps < 32) tps = 32;
+    h->qp_blocks = prop.multiProcessorCount * (tps / tm_qp_thread_block() > 0 ? tps / tm_qp_thread_block() : 1);
+    h->qp_ws_per_inst = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact);
+    if (h->qp_mode == 1) {
+      const size_t nthreads = (size_t)h->qp_blocks * tm_qp_thread_block();
+      if (cudaMalloc(&h->qp_ws, nthreads * h->qp_ws_per_inst * sizeof(double)) != cudaSuccess ||
+          cudaMalloc(&h->qp_counter, sizeof(int)) != cudaSuccess) {
+        fprintf(stderr, "tmpc_create: cannot allocate the QP workspace\n");
+        delete h;
+        return 5;
+      }
+    }
+  }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
   h->ev_ok = true;
   *out = h;
@@ -234,6 +267,8 @@ void tmpc_destroy(tmpc_handle* h) {
   cudaSetDevice(h->device);
   free_list(h->tab_allocs);
   free_list(h->ws_allocs);
+  if (h->qp_ws) cudaFree(h->qp_ws);
+  if (h->qp_counter) cudaFree(h->qp_counter);
   if (h->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
   delete h;
 }
@@ -295,9 +330,10 @@ static int ensure_capacity(tmpc_handle* h, int64_t B) {
       dalloc(h, &S.LAMQ, b * P.n_g) || dalloc(h, &S.LIN, b * P.N * TM_LSZ) || dalloc(h, &S.G, b * P.n_g) ||
       dalloc(h, &S.FILT, b * P.filter_cap * 2) || dalloc(h, &S.fval, b) || dalloc(h, &S.nfilt, b) ||
       dalloc(h, &S.iter, b) || dalloc(h, &S.status, b) || dalloc(h, &S.flags, b) || dalloc(h, &S.nAS, b) ||
-      dalloc(h, &S.nACtot, b) || dalloc(h, &S.nAC, b) || dalloc(h, &S.qpstat, b) ||
+      dalloc(h, &S.nACtot, b) || dalloc(h, &S.nAC, b) || dalloc(h, &S.qpstat, b) || dalloc(h, &S.qpmode, b) || dalloc(h, &S.almask, b * TM_ALW) ||
+      dalloc(h, &h->retry_a, b) || dalloc(h, &h->retry_b, b) ||
       dalloc(h, &S.asinit, b * S.aswords) || dalloc(h, &h->list_a, b) || dalloc(h, &h->list_b, b) ||
-      dalloc(h, &S.list_relin, b) || dalloc(h, &h->cnts, 4) || dalloc(h, &S.counters, 8) ||
+      dalloc(h, &S.list_relin, b) || dalloc(h, &h->cnts, 8) || dalloc(h, &S.counters, 8) ||
       dalloc(h, &h->Wsh, b * P.n_w) || dalloc(h, &h->Lsh, b * P.n_g) || dalloc(h, &h->X0buf, b * NX))
     return 1;
   h->cap = B;
@@ -374,16 +410,28 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   while (nact > 0) {
     const unsigned wb = (unsigned)((nact + QP_WARPS - 1) / QP_WARPS);
     S.list_next = (cur == h->list_a) ? h->list_b : h->list_a;
-    CK(cudaMemsetAsync(h->cnts, 0, 2 * sizeof(int), st));
+    CK(cudaMemsetAsync(h->cnts, 0, 4 * sizeof(int), st));
     CK(cudaEventRecord(h->ev[0], st));
-    k_qp<<<wb, QP_WARPS * 32, h->qp_smem, st>>>(P, S, cur, (int)nact);
+    for (int pass = 0; pass < 5; ++pass) {
+      // pass 0: the active list (host-known count); passes 1..4: re-solves queued by the previous pass (device count)
+      const int* plist = pass == 0 ? cur : ((pass & 1) ? h->retry_a : h->retry_b);
+      const int* pcnt = pass == 0 ? nullptr : h->cnts + 2 + ((pass - 1) & 1);
+      S.list_retry = (pass & 1) ? h->retry_b : h->retry_a;
+      S.cnt_retry = h->cnts + 2 + (pass & 1);
+      if (pass >= 2) CK(cudaMemsetAsync(S.cnt_retry, 0, sizeof(int), st));
+      if (h->qp_mode == 1)
+        CK(tm_launch_qp_thread(P, S, plist, (int)nact, pcnt, h->qp_ws, h->qp_ws_per_inst, h->qp_blocks, h->qp_counter, st));
+      else
+        k_qp<<<wb, QP_WARPS * 32, h->qp_smem, st>>>(P, S, plist, (int)nact, pcnt);
+      ++launches;
+    }
     CK(cudaEventRecord(h->ev[1], st));
     k_lin<<<lin_grid(nact), LIN_THREADS, 0, st>>>(P, S, cur, nullptr, (int)nact, 1, per);
     CK(cudaEventRecord(h->ev[2], st));
     k_post<<<wb, QP_WARPS * 32, 0, st>>>(P, S, cur, (int)nact);
     CK(cudaEventRecord(h->ev[3], st));
     CK(cudaGetLastError());
-    launches += 3; n_qp += nact; n_lin += nact * P.N;
+    launches += 2; n_qp += nact; n_lin += nact * P.N;
     CK(cudaMemcpyAsync(hc, h->cnts, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); ms_qp += ms;

@@ -20,8 +20,10 @@
 
 #ifdef __CUDACC__
 #define TM_HD __host__ __device__ __forceinline__
-#define TM_HDN __host__ __device__ __noinline__
+#define TM_HDN static __host__ __device__ __noinline__
+#define TM_HDM __host__ __device__ __forceinline__
 #else
+#define TM_HDM inline
 #define TM_HD static inline
 #define TM_HDN static
 #endif
@@ -73,10 +75,10 @@ TM_HD int tm_wany(int p) { return p; }
 #ifdef TM_WS_STRIDE
 struct TmP {
   double* p;
-  TM_HD double& operator[](int i) const { return p[(size_t)i * TM_WS_STRIDE]; }
-  TM_HD double& operator[](size_t i) const { return p[i * TM_WS_STRIDE]; }
-  TM_HD TmP operator+(size_t o) const { TmP r; r.p = p + o * TM_WS_STRIDE; return r; }
-  TM_HD TmP operator+(int o) const { TmP r; r.p = p + (size_t)o * TM_WS_STRIDE; return r; }
+  TM_HDM double& operator[](int i) const { return p[(size_t)i * TM_WS_STRIDE]; }
+  TM_HDM double& operator[](size_t i) const { return p[i * TM_WS_STRIDE]; }
+  TM_HDM TmP operator+(size_t o) const { TmP r; r.p = p + o * TM_WS_STRIDE; return r; }
+  TM_HDM TmP operator+(int o) const { TmP r; r.p = p + (size_t)o * TM_WS_STRIDE; return r; }
 };
 TM_HD TmP tm_mkp(double* base, size_t off) { TmP r; r.p = base + off * TM_WS_STRIDE; return r; }
 #else
@@ -90,6 +92,7 @@ TM_HD TmP tm_mkp(double* base, size_t off) { return base + off; }
 #define TM_NPAIR (NZ * (NZ + 1) / 2)
 #define TM_LSZ (NX + NX * NZ + TM_NPAIR)   /* per-stage linearisation record: xf | S row-major nx*nz | W packed i<=j */
 #define TM_INF 1e300
+#define TM_ALW 8   /* words of the augmented-Lagrangian row mask: supports N*nh <= 256 */
 
 // ---------------------------------------------------------------------------------------------------------------
 // problem constants and per-batch state (plain pointers; device memory in the product, malloc in the twin)
@@ -114,6 +117,9 @@ struct TmState {
   double* fval;           // B
   int *nfilt, *iter, *status, *flags, *nAS, *nACtot, *nAC;
   int* qpstat;            // B: result of the last QP (0 ok)
+  int* qpmode;            // B: 0 fresh, 1..3 retry with the stored row mask, 100 Gauss-Newton fallback
+  unsigned* almask;       // B*TM_ALW: augmented-Lagrangian row mask carried between retries
+  int *list_retry, *cnt_retry;   // instances whose QP must be re-solved (filled by tm_qp)
   unsigned* asinit;       // B*aswords bitmask of initially active inequality rows
   int aswords;
   int *list_next, *cnt_next, *list_relin, *cnt_relin;
@@ -278,11 +284,15 @@ TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, i
 // Exact active-set solution: inactive multipliers are exact zeros, as the reference relies on (sqp_method.py:421).
 // ---------------------------------------------------------------------------------------------------------------
 struct TmQpWs {
-  TmP AB, Q, r, b, K, Lc, hv, d, y, z, rhs, kk, P0, P1, PAB, F, pv, tr, S, Sc, cA, rv, nu;
-  TmP actk, acti, acts;   // working-set rows: stage (N = terminal), row index, sign (small integers stored as doubles)
+  TmP AB, Q, r, b, K, Lc, hv, d, y, rhs, kk, P0, P1, PAB, F, pv, tr;
+  TmP sl;                 // E = N*nh + nxt: current value of every constraint row (slack / terminal residual)
+  TmP Mc;                 // M x E: column j = N G n_j of the dual Hessian for working-set member j (+ one candidate)
+  TmP Lf;                 // M x M: Cholesky factor of the working-set Schur complement S = N_A G N_A'
+  TmP cA, rv, nu, acts, acte, sc;   // per member: L^-1 S_Aq, S^-1 S_Aq, multiplier, sign, row id; scalars
 };
 
 TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
+  const size_t E = (size_t)N * nh + nxt;
   size_t n = 0;
   n += (size_t)N * NX * NZ;        // AB
   n += (size_t)N * NZ * NZ;        // Q
@@ -291,16 +301,20 @@ TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
   n += (size_t)N * NU * NX;        // K
   n += (size_t)N * NU * NU;        // Lc
   n += (size_t)N * (nh > 0 ? nh : 1);   // hv
-  n += 4 * (size_t)(N + 1) * NZ;   // d y z rhs
+  n += 3 * (size_t)(N + 1) * NZ;   // d y rhs
   n += (size_t)N * NU;             // kk
   n += 2 * NX * NX + NX * NZ + NZ * NZ;   // P0 P1 PAB F
   n += 4 * NX;                     // pv (two buffers of NX, e0, spare)
   n += (nxt > 0 ? nxt : 1);        // tr
-  n += 2 * (size_t)M * M + 6 * (size_t)M;   // S Sc | cA rv nu acts actk acti
+  n += (E > 0 ? E : 1);            // sl
+  n += (size_t)(M + 1) * (E > 0 ? E : 1);   // Mc (+1 candidate column)
+  n += (size_t)M * M;              // Lf
+  n += 5 * (size_t)M + 8;          // cA rv nu acts acte sc
   return n;
 }
 
 TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s) {
+  const size_t E = (size_t)N * nh + nxt;
   size_t o = 0;
 #define TM_CARVE(member, n) s.member = tm_mkp(base, o); o += (size_t)(n)
   TM_CARVE(AB, (size_t)N * NX * NZ);
@@ -312,7 +326,6 @@ TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s)
   TM_CARVE(hv, (size_t)N * (nh > 0 ? nh : 1));
   TM_CARVE(d, (size_t)(N + 1) * NZ);
   TM_CARVE(y, (size_t)(N + 1) * NZ);
-  TM_CARVE(z, (size_t)(N + 1) * NZ);
   TM_CARVE(rhs, (size_t)(N + 1) * NZ);
   TM_CARVE(kk, (size_t)N * NU);
   TM_CARVE(P0, NX * NX);
@@ -321,14 +334,15 @@ TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s)
   TM_CARVE(F, NZ * NZ);
   TM_CARVE(pv, 4 * NX);
   TM_CARVE(tr, (nxt > 0 ? nxt : 1));
-  TM_CARVE(S, (size_t)M * M);
-  TM_CARVE(Sc, (size_t)M * M);
+  TM_CARVE(sl, (E > 0 ? E : 1));
+  TM_CARVE(Mc, (size_t)(M + 1) * (E > 0 ? E : 1));
+  TM_CARVE(Lf, (size_t)M * M);
   TM_CARVE(cA, M);
   TM_CARVE(rv, M);
   TM_CARVE(nu, M);
   TM_CARVE(acts, M);
-  TM_CARVE(actk, M);
-  TM_CARVE(acti, M);
+  TM_CARVE(acte, M);
+  TM_CARVE(sc, 8);
 #undef TM_CARVE
 }
 
@@ -366,30 +380,35 @@ TM_HD void tm_chol_small_solve(PL L, double* x) {
 }
 
 // homogeneous base solve:  out = argmin 1/2 d'Qd + rhs'd  s.t. d_x0 = 0, d_x(k+1) = A d_x + B d_u   ( = -G rhs )
-TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, TmP rhs, TmP out) {
+// kfrom: last stage with a non-zero right-hand side (N = the x_N block): the backward sweep starts there.
+TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, TmP rhs, TmP out, int kfrom) {
   const int N = P.N;
   const int lane = TM_LANE;
   TmP pv0 = s.pv;
   TmP pv1 = s.pv + NX;
-  for (int a = lane; a < NX; a += TM_NL) pv0[a] = rhs[N * NZ + a];
+  for (int a = lane; a < NX; a += TM_NL) pv0[a] = (kfrom >= N) ? rhs[N * NZ + a] : 0.0;
   TM_SYNC();
-  for (int k = N - 1; k >= 0; --k) {
+  const int kb = (kfrom >= N) ? N - 1 : kfrom;
+  for (int k = kb; k >= 0; --k) {
     const TmP AB = s.AB + (size_t)k * NX * NZ;
     const TmP Kk = s.K + (size_t)k * NU * NX;
     const TmP L = s.Lc + (size_t)k * NU * NU;
     const TmP rk = rhs + k * NZ;
+    double pvr[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) pvr[i] = pv0[i];
     double fu[NU];
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
       double v = rk[NX + a];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) v += AB[i * NZ + NX + a] * pv0[i];
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + NX + a] * pvr[i];
       fu[a] = v;
     }
     for (int j = lane; j < NX; j += TM_NL) {
       double v = rk[j];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) v += AB[i * NZ + j] * pv0[i];
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + j] * pvr[i];
 #pragma unroll
       for (int a = 0; a < NU; ++a) v += Kk[a * NX + j] * fu[a];
       pv1[j] = v;
@@ -408,19 +427,22 @@ TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, TmP rhs, TmP out) {
     const TmP AB = s.AB + (size_t)k * NX * NZ;
     const TmP Kk = s.K + (size_t)k * NU * NX;
     const TmP dx = out + k * NZ;
+    double dxr[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) dxr[j] = dx[j];
     double du[NU];
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
-      double v = s.kk[k * NU + a];
+      double v = (k <= kb) ? s.kk[k * NU + a] : 0.0;
 #pragma unroll
-      for (int j = 0; j < NX; ++j) v += Kk[a * NX + j] * dx[j];
+      for (int j = 0; j < NX; ++j) v += Kk[a * NX + j] * dxr[j];
       du[a] = v;
     }
     for (int a = lane; a < NU; a += TM_NL) out[k * NZ + NX + a] = du[a];
     for (int i = lane; i < NX; i += TM_NL) {
       double v = 0.0;
 #pragma unroll
-      for (int j = 0; j < NX; ++j) v += AB[i * NZ + j] * dx[j];
+      for (int j = 0; j < NX; ++j) v += AB[i * NZ + j] * dxr[j];
 #pragma unroll
       for (int a = 0; a < NU; ++a) v += AB[i * NZ + NX + a] * du[a];
       out[(k + 1) * NZ + i] = v;
@@ -431,9 +453,11 @@ TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, TmP rhs, TmP out) {
   TM_SYNC();
 }
 
-// constraint row helpers.  row m of the working set: stage actk (== N for a terminal row), row acti, sign acts
-TM_HD double tm_row_dot(const TmProb& P, int k, int i, double sg, TmP v) {
-  if (k == P.N) return sg * v[P.N * NZ + P.term_idx[i]];
+// constraint rows by unified id e: e < N*nh is inequality row (k = e / nh, i = e % nh), e >= N*nh terminal row
+TM_HD double tm_erow_dot(const TmProb& P, int e, TmP v) {
+  const int NI = P.N * P.nh;
+  if (e >= NI) return v[P.N * NZ + P.term_idx[e - NI]];
+  const int k = e / P.nh, i = e % P.nh;
   double t = 0.0;
   const double* Ci = P.C + (size_t)i * NZ;
   const TmP vk = v + k * NZ;
@@ -441,55 +465,36 @@ TM_HD double tm_row_dot(const TmProb& P, int k, int i, double sg, TmP v) {
   for (int b = 0; b < NZ; ++b) t += Ci[b] * vk[b];
   return t;
 }
-// rhs += coef * n   (single lane)
-TM_HD void tm_row_axpy(const TmProb& P, int k, int i, double sg, double coef, TmP rhs) {
-  if (k == P.N) { rhs[P.N * NZ + P.term_idx[i]] += coef * sg; return; }
+// rhs += coef * n_e   (single lane)
+TM_HD void tm_erow_axpy(const TmProb& P, int e, double coef, TmP rhs) {
+  const int NI = P.N * P.nh;
+  if (e >= NI) { rhs[P.N * NZ + P.term_idx[e - NI]] += coef; return; }
+  const int k = e / P.nh, i = e % P.nh;
   const double* Ci = P.C + (size_t)i * NZ;
 #pragma unroll
   for (int b = 0; b < NZ; ++b) rhs[k * NZ + b] += coef * Ci[b];
 }
 
-// dense Cholesky solve  S r = c  for the m x m working-set Schur complement (stride M); returns 0 on breakdown
-TM_HD int tm_schur_solve(TmQpWs& s, int m, int M, TmP r) {
-  const int lane = TM_LANE;
-  TmP Sc = s.Sc;
-  for (int e = lane; e < m * m; e += TM_NL) { int i = e / m, j = e % m; Sc[i * M + j] = s.S[i * M + j]; }
-  TM_SYNC();
-  int ok = 1;
+// rebuild the Cholesky factor Lf of S_ij = acts_i * Mc[j][acte_i] (i, j < m) after a deletion (single lane)
+TM_HD int tm_schur_refactor(TmQpWs& s, int m, int M, int E) {
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j <= i; ++j) s.Lf[i * M + j] = s.acts[i] * s.Mc[(size_t)j * E + (int)s.acte[i]];
   for (int c = 0; c < m; ++c) {
-    double dg = Sc[c * M + c];
-    if (!(dg > 0.0)) { ok = 0; break; }
+    double dg = s.Lf[c * M + c];
+    for (int l = 0; l < c; ++l) dg -= s.Lf[c * M + l] * s.Lf[c * M + l];
+    if (!(dg > 0.0)) return 0;
     const double ld = sqrt(dg);
-    TM_SYNC();
-    for (int i = c + lane; i < m; i += TM_NL) Sc[i * M + c] = (i == c) ? ld : Sc[i * M + c] / ld;
-    TM_SYNC();
-    const int rem = m - c - 1;
-    for (int e = lane; e < rem * rem; e += TM_NL) {
-      int i = c + 1 + e / rem, j = c + 1 + e % rem;
-      if (j <= i) Sc[i * M + j] -= Sc[i * M + c] * Sc[j * M + c];
-    }
-    TM_SYNC();
-  }
-  if (!ok) return 0;
-  // forward / backward substitution, every lane redundantly on its own copy kept in shared r (lane 0 writes)
-  if (lane == 0) {
-    for (int i = 0; i < m; ++i) {
-      double v = s.cA[i];
-      for (int l = 0; l < i; ++l) v -= Sc[i * M + l] * r[l];
-      r[i] = v / Sc[i * M + i];
-    }
-    for (int i = m - 1; i >= 0; --i) {
-      double v = r[i];
-      for (int l = i + 1; l < m; ++l) v -= Sc[l * M + i] * r[l];
-      r[i] = v / Sc[i * M + i];
+    s.Lf[c * M + c] = ld;
+    for (int i = c + 1; i < m; ++i) {
+      double v = s.Lf[i * M + c];
+      for (int l = 0; l < c; ++l) v -= s.Lf[i * M + l] * s.Lf[c * M + l];
+      s.Lf[i * M + c] = v / ld;
     }
   }
-  TM_SYNC();
   return 1;
 }
 
 // returns: 0 ok, 2 infeasible / working-set overflow / numerical breakdown, 3 base factorisation not PD
-#define TM_ALW 8   /* words of the augmented-Lagrangian row mask: supports N*nh <= 256 */
 // al_mask: rows (k*nh+i) whose squared slack  gamma/2 (C_i d + h_i)^2  is added to the base problem.  The term and its
 // gradient vanish wherever the row is active at the QP solution, so the solution is unchanged iff every masked row ends
 // up in the working set; rows that do not are reported in al_bad (caller removes them and re-solves).  This makes the
@@ -693,72 +698,78 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   }
   for (int a = lane; a < NU; a += TM_NL) s.d[N * NZ + NX + a] = 0.0;
   TM_SYNC();
-  // ---- C. Goldfarb-Idnani on the Schur complement ------------------------------------------------------------
+  // ---- C. Goldfarb-Idnani dual active set, carried in the dual space ----------------------------------------------
+  // The primal iterate is never updated inside the loop: d = d_base + sum_j nu_j G n_j is recovered by ONE solve at
+  // the end.  Per added constraint: one (partial) Riccati solve y = G n_q, its dual-Hessian column Mc_q[e] = n_e'y for
+  // every row e, an O(m^2) Cholesky append, and an O(E m) update of all row values sl[e].
+  const int NI = N * nh, E = NI + nxt;
+  for (int e = lane; e < E; e += TM_NL) s.sl[e] = (e < NI ? s.hv[e] : s.tr[e - NI]) + tm_erow_dot(P, e, s.d);
+  TM_SYNC();
   int m = 0, neq = 0, ret = 0;
   int n_gi = 0, n_ricc = 0;
-  const int maxit = 4 * (nxt + N * nh) + 8;
+  const int maxit = 4 * E + 8;
   for (int it = 0; it < maxit; ++it) {
-    int qk, qi;
+    int qe;
     double qs = 1.0, sval;
     if (neq < nxt) {
-      qk = N; qi = neq;
-      double v = s.d[N * NZ + P.term_idx[qi]] + s.tr[qi];
+      qe = NI + neq;
+      const double v = s.sl[qe];
       qs = (v > 0.0) ? -1.0 : 1.0;
       sval = qs * v;
     } else {
       double best = TM_INF;
       int bid = 0x7fffffff;
-      for (int e = lane; e < N * nh; e += TM_NL) {
-        int k = e / nh, i = e % nh;
+      for (int e = lane; e < NI; e += TM_NL) {
+        const int k = e / nh, i = e % nh;
         if (k == 0 && P.relax0[i]) continue;
-        double v = s.hv[e];
-        const double* Ci = P.C + (size_t)i * NZ;
-#pragma unroll
-        for (int b = 0; b < NZ; ++b) v += Ci[b] * s.d[k * NZ + b];
-        v /= fmax(1.0, fabs(P.c[i]));
+        const double v = s.sl[e] / fmax(1.0, fabs(P.c[i]));
         if (v < best) { best = v; bid = e; }
       }
       tm_wargmin(best, bid);
       if (!(best < -1e-10)) break;            // primal feasible: optimal
-      // an active row can only show up here through round-off; treat as converged
-      int dup = 0;
-      for (int j2 = 0; j2 < m; ++j2) if (s.actk[j2] * nh + s.acti[j2] == bid && s.actk[j2] < N) dup = 1;
+      int dup = 0;                            // a working-set row can only show up here through round-off
+      for (int j2 = 0; j2 < m; ++j2) if ((int)s.acte[j2] == bid) dup = 1;
       if (dup) break;
-      qk = bid / nh; qi = bid % nh;
-      sval = s.hv[bid] + tm_row_dot(P, qk, qi, 1.0, s.d);
+      qe = bid;
+      sval = s.sl[qe];
     }
     if (m >= M) { ret = 2; break; }
-    // y = G n_q
     for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.rhs[e] = 0.0;
     TM_SYNC();
-    if (lane == 0) tm_row_axpy(P, qk, qi, qs, -1.0, s.rhs);
+    if (lane == 0) tm_erow_axpy(P, qe, -qs, s.rhs);
     TM_SYNC();
-    tm_ricc_solve(P, s, s.rhs, s.y);
+    tm_ricc_solve(P, s, s.rhs, s.y, qe < NI ? qe / nh : N);
     ++n_gi; ++n_ricc;
-    for (int j2 = lane; j2 < m; j2 += TM_NL) s.cA[j2] = tm_row_dot(P, (int)s.actk[j2], (int)s.acti[j2], s.acts[j2], s.y);
-    const double yq = tm_row_dot(P, qk, qi, qs, s.y);
+    TmP mq = s.Mc + (size_t)m * E;            // candidate column, becomes member m when added
+    for (int e = lane; e < E; e += TM_NL) mq[e] = tm_erow_dot(P, e, s.y);
     TM_SYNC();
+    const double yq = qs * mq[qe];
     double nq = 0.0;
     int added = 0;
     for (int inner = 0; inner < M + 2; ++inner) {
-      TmP zz = s.y;
-      if (m > 0) {
-        if (!tm_schur_solve(s, m, M, s.rv)) { ret = 2; break; }
-        for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.rhs[e] = 0.0;
-        TM_SYNC();
-        if (lane == 0) for (int j2 = 0; j2 < m; ++j2) tm_row_axpy(P, (int)s.actk[j2], (int)s.acti[j2], s.acts[j2], s.rv[j2], s.rhs);
-        TM_SYNC();
-        tm_ricc_solve(P, s, s.rhs, s.z);
-        ++n_ricc;
-        for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.z[e] += s.y[e];
-        TM_SYNC();
-        zz = s.z;
+      // l = L^-1 S_Aq (kept in cA), zn = yq - l'l, r = L^-T l (rv)
+      if (lane == 0) {
+        double ll = 0.0;
+        for (int i = 0; i < m; ++i) {
+          double v = s.acts[i] * mq[(int)s.acte[i]];
+          for (int l = 0; l < i; ++l) v -= s.Lf[i * M + l] * s.cA[l];
+          v /= s.Lf[i * M + i];
+          s.cA[i] = v;
+          ll += v * v;
+        }
+        for (int i = m - 1; i >= 0; --i) {
+          double v = s.cA[i];
+          for (int l = i + 1; l < m; ++l) v -= s.Lf[l * M + i] * s.rv[l];
+          s.rv[i] = v / s.Lf[i * M + i];
+        }
+        s.sc[0] = ll;
       }
-      const double zn = tm_row_dot(P, qk, qi, qs, zz);
+      TM_SYNC();
+      const double zn = yq - s.sc[0];
       double t1 = TM_INF;
       int jd = -1;
       for (int j2 = 0; j2 < m; ++j2) {
-        if (s.actk[j2] == N) continue;                 // equality rows are never dropped
+        if ((int)s.acte[j2] >= NI) continue;           // equality rows are never dropped
         const double rj = s.rv[j2];
         if (rj > 1e-14) { const double tj = s.nu[j2] / rj; if (tj < t1) { t1 = tj; jd = j2; } }
       }
@@ -771,7 +782,11 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
       } else {
         const double t2 = -sval / zn;
         if (t2 <= t1) { t = t2; do_add = 1; } else t = t1;
-        for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.d[e] += t * zz[e];
+        for (int e = lane; e < E; e += TM_NL) {
+          double acc = mq[e];
+          for (int j2 = 0; j2 < m; ++j2) acc -= s.rv[j2] * s.Mc[(size_t)j2 * E + e];
+          s.sl[e] += t * acc;
+        }
         sval += t * zn;
       }
       TM_SYNC();
@@ -779,32 +794,50 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
       nq += t;
       TM_SYNC();
       if (do_add) {
-        for (int j2 = lane; j2 < m; j2 += TM_NL) { s.S[m * M + j2] = s.cA[j2]; s.S[j2 * M + m] = s.cA[j2]; }
-        if (lane == 0) { s.S[m * M + m] = yq; s.actk[m] = qk; s.acti[m] = qi; s.acts[m] = qs; s.nu[m] = nq; }
+        if (lane == 0) {
+          for (int l = 0; l < m; ++l) s.Lf[m * M + l] = s.cA[l];
+          s.Lf[m * M + m] = sqrt(zn);
+          s.acte[m] = (double)qe; s.acts[m] = qs; s.nu[m] = nq;
+        }
         TM_SYNC();
         ++m;
-        if (qk == N) ++neq;
+        if (qe >= NI) ++neq;
         added = 1;
         break;
       }
-      // drop working-set row jd: compact S, cA, nu, act*
-      TM_SYNC();
+      // drop member jd: shift members jd+1..m-1 and the candidate column down by one slot, rebuild the factor
+      for (int a = jd; a < m; ++a) {
+        for (int e = lane; e < E; e += TM_NL) s.Mc[(size_t)a * E + e] = s.Mc[(size_t)(a + 1) * E + e];
+        TM_SYNC();
+      }
       if (lane == 0) {
-        for (int a = jd; a < m - 1; ++a) {
-          s.actk[a] = s.actk[a + 1]; s.acti[a] = s.acti[a + 1]; s.acts[a] = s.acts[a + 1];
-          s.nu[a] = s.nu[a + 1]; s.cA[a] = s.cA[a + 1];
-        }
-        for (int a = 0; a < m; ++a)
-          for (int c = jd; c < m - 1; ++c) s.S[a * M + c] = s.S[a * M + c + 1];
-        for (int a = jd; a < m - 1; ++a)
-          for (int c = 0; c < m - 1; ++c) s.S[a * M + c] = s.S[(a + 1) * M + c];
+        for (int a = jd; a < m - 1; ++a) { s.acte[a] = s.acte[a + 1]; s.acts[a] = s.acts[a + 1]; s.nu[a] = s.nu[a + 1]; }
       }
       --m;
       TM_SYNC();
+      mq = s.Mc + (size_t)m * E;
+      if (lane == 0) s.sc[1] = (double)tm_schur_refactor(s, m, M, E);
+      TM_SYNC();
+      if (s.sc[1] == 0.0) { ret = 2; break; }
     }
     if (ret) break;
     if (!added) { ret = 2; break; }
     if (it == maxit - 1) ret = 2;
+  }
+  if (!ret) {
+    // primal recovery: d = d_base + G N_A' nu  (one full solve)
+    for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.rhs[e] = 0.0;
+    TM_SYNC();
+    int kfrom = -1;
+    if (lane == 0) for (int j2 = 0; j2 < m; ++j2) tm_erow_axpy(P, (int)s.acte[j2], -s.acts[j2] * s.nu[j2], s.rhs);
+    for (int j2 = 0; j2 < m; ++j2) { const int e = (int)s.acte[j2]; const int k = e < NI ? e / nh : N; if (k > kfrom) kfrom = k; }
+    TM_SYNC();
+    if (m > 0) {
+      tm_ricc_solve(P, s, s.rhs, s.y, kfrom);
+      ++n_ricc;
+      for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.d[e] += s.y[e];
+      TM_SYNC();
+    }
   }
   if (lane == 0) {
 #ifdef __CUDA_ARCH__
@@ -817,10 +850,10 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   if (al_mask) {
     int nbad = 0;
     for (int wd = 0; wd < TM_ALW; ++wd) al_bad[wd] = 0u;
-    for (int e = 0; e < N * nh && e < 32 * TM_ALW; ++e) {
+    for (int e = 0; e < NI && e < 32 * TM_ALW; ++e) {
       if (!((al_mask[e >> 5] >> (e & 31)) & 1u)) continue;
       int found = 0;
-      for (int j2 = 0; j2 < m; ++j2) if (s.actk[j2] < N && s.actk[j2] * nh + s.acti[j2] == e) found = 1;
+      for (int j2 = 0; j2 < m; ++j2) if ((int)s.acte[j2] == e) found = 1;
       if (!found) { al_bad[e >> 5] |= (1u << (e & 31)); ++nbad; }
     }
     if (nbad) return 5;
@@ -833,8 +866,9 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   TM_SYNC();
   if (lane == 0) {
     for (int j2 = 0; j2 < m; ++j2) {
-      if (s.actk[j2] == N) lq[tm_gterm(P) + (int)s.acti[j2]] = -s.acts[j2] * s.nu[j2];
-      else lq[tm_gh(P, (int)s.actk[j2]) + (int)s.acti[j2]] = -s.nu[j2];
+      const int e = (int)s.acte[j2];
+      if (e >= NI) lq[tm_gterm(P) + (e - NI)] = -s.acts[j2] * s.nu[j2];
+      else lq[tm_gh(P, e / nh) + e % nh] = -s.nu[j2];
     }
   }
   TM_SYNC();
@@ -1000,6 +1034,8 @@ TM_HD void tm_init(const TmProb& P, const TmState& S, int64_t inst) {
     S.iter[inst] = 0;
     S.status[inst] = -1;
     S.flags[inst] = 0;
+    S.qpmode[inst] = 0;
+    S.qpstat[inst] = 0;
     const double* lam = S.LAM + inst * P.n_g;
     for (int wd = 0; wd < S.aswords; ++wd) {
       unsigned bits = 0;
@@ -1151,35 +1187,49 @@ TM_HD void tm_prefilter(const TmProb& P, const TmState& S, int64_t inst) {
   TM_SYNC();
 }
 
-// QP with the configured Hessian.  Exact mode: (1) augmented-Lagrangian convexification on the rows that are active
-// in the current multipliers (the reference's reduced space); rows that turn out inactive are dropped and the QP is
-// re-solved; (2) if the base factorisation is still not positive definite: Gauss-Newton Hessian, flagged
-// (the reference would eigen-clip its reduced Hessian there, sqp_method.py:345-376).
+// One QP attempt with the configured Hessian.  Exact mode: (1) augmented-Lagrangian convexification on the rows that
+// are active in the current multipliers (the reference's reduced space); if some of those rows turn out inactive they
+// are removed from the mask and the instance is queued for a re-solve; (2) if the base factorisation is still not
+// positive definite: re-solve with the Gauss-Newton Hessian, flagged (the reference would eigen-clip its reduced
+// Hessian there, sqp_method.py:345-376).  Re-solves run in a later launch over the compacted retry list, so that the
+// lanes of a warp stay in step (thread-per-instance kernel).
 TM_HD void tm_qp(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& ws) {
   unsigned mask[TM_ALW], bad[TM_ALW];
   int nmask = 0;
-  const double* lam = S.LAM + inst * P.n_g;
+  const int mode = S.qpmode[inst];
+  const int use_exact = P.hessian_exact && mode < 100;
   for (int wd = 0; wd < TM_ALW; ++wd) mask[wd] = 0u;
-  if (P.hessian_exact && P.al_gamma > 0.0) {
-    for (int e = 0; e < P.N * P.nh && e < 32 * TM_ALW; ++e) {
-      const int k = e / P.nh, i = e % P.nh;
-      if (k == 0 && P.relax0[i]) continue;
-      if (lam[tm_gh(P, k) + i] != 0.0) { mask[e >> 5] |= (1u << (e & 31)); ++nmask; }
+  if (use_exact && P.al_gamma > 0.0) {
+    if (mode == 0) {
+      const double* lam = S.LAM + inst * P.n_g;
+      for (int e = 0; e < P.N * P.nh && e < 32 * TM_ALW; ++e) {
+        const int k = e / P.nh, i = e % P.nh;
+        if (k == 0 && P.relax0[i]) continue;
+        if (lam[tm_gh(P, k) + i] != 0.0) { mask[e >> 5] |= (1u << (e & 31)); ++nmask; }
+      }
+    } else {
+      for (int wd = 0; wd < TM_ALW; ++wd) { mask[wd] = S.almask[inst * TM_ALW + wd]; nmask += (mask[wd] != 0u); }
     }
   }
-  int ret = 0, fb = 0;
-  for (int attempt = 0; attempt < 4; ++attempt) {
-    ret = tm_qp_solve(P, S, inst, ws, P.hessian_exact, nmask ? mask : nullptr, bad);
-    if (ret != 5) break;
-    nmask = 0;
-    for (int wd = 0; wd < TM_ALW; ++wd) { mask[wd] &= ~bad[wd]; nmask += (mask[wd] != 0u); }
-    if (attempt == 3) ret = 3;
-  }
-  if (ret == 5) ret = 3;
-  if (ret == 3 && P.hessian_exact) { ret = tm_qp_solve(P, S, inst, ws, 0, nullptr, bad); fb = 1; }
+  int ret = tm_qp_solve(P, S, inst, ws, use_exact, nmask ? mask : nullptr, bad);
+  int next_mode = 0;
+  if (ret == 5) next_mode = (mode + 1 >= 4) ? 100 : mode + 1;
+  else if (ret == 3 && use_exact) next_mode = 100;
   if (TM_LANE == 0) {
-    S.qpstat[inst] = ret;
-    if (fb) S.flags[inst] |= 1;
+    if (next_mode) {
+      for (int wd = 0; wd < TM_ALW; ++wd) S.almask[inst * TM_ALW + wd] = (ret == 5) ? (mask[wd] & ~bad[wd]) : 0u;
+      S.qpmode[inst] = next_mode;
+      if (next_mode == 100) S.flags[inst] |= 1;
+#ifdef __CUDA_ARCH__
+      const int pos = atomicAdd(S.cnt_retry, 1);
+#else
+      const int pos = (*S.cnt_retry)++;
+#endif
+      S.list_retry[pos] = (int)inst;
+    } else {
+      S.qpmode[inst] = 0;
+      S.qpstat[inst] = ret;
+    }
   }
   TM_SYNC();
 }
