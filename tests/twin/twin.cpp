@@ -73,7 +73,7 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
   S.D = D.data(); S.LAMQ = LQ.data(); S.LIN = LIN.data(); S.FILT = FILT.data(); S.nfilt = nfilt.data();
   S.qpstat = qpstat.data(); S.qpmode = qpmode.data(); S.almask = almask.data(); S.list_retry = lretry.data(); S.cnt_retry = &cnt_retry; S.asinit = asinit.data(); S.counters = counters;
   S.cnt_next = &cnts[0]; S.cnt_relin = &cnts[1]; S.list_relin = lrel.data();
-  const int per = P.hessian_exact ? TM_NPAIR : NZ;
+  const int per = tm_lin_tasks_per_stage(P.hessian_exact);
   std::vector<double> wsbuf(tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact));
   TmQpWs ws;
   tm_qpws_carve(wsbuf.data(), P.N, P.nh, P.nxt, P.maxact, ws);

@@ -26,7 +26,7 @@ cudaError_t tm_launch_qp_thread(const TmProb& P, const TmState& S, const int* li
                                 double* wsbase, size_t ws_per_inst, int nblocks, int* work_counter, cudaStream_t st);
 int tm_qp_thread_block();
 
-#define QP_WARPS 4          /* warps (instances) per CTA in the warp-per-instance kernels */
+#define QP_WARPS 2          /* warps (instances) per CTA in the warp-per-instance kernels */
 #define LIN_THREADS 128
 
 struct tmpc_handle {
@@ -49,7 +49,10 @@ struct tmpc_handle {
   cudaEvent_t ev[8];
   bool ev_ok = false;
   size_t qp_smem = 0;
-  int qp_mode = 1;             // 1: thread per instance (global interleaved workspace), 0: warp per instance (shared memory)
+  int qp_mode = 2;             // 2: hybrid (thread per instance for big launches, warp per instance for the tail), 1: thread, 0: warp
+  int qp_thread_min = 16384;   // hybrid: launches with fewer candidate instances use the low-latency warp kernel
+  bool trace = false;
+  bool uniform_ws = false;     // warm start identical for every instance (right after tmpc_reset)
   int qp_blocks = 0;           // resident CTAs of the thread-per-instance kernel
   double* qp_ws = nullptr;     // its workspace
   size_t qp_ws_per_inst = 0;
@@ -233,6 +236,10 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
   {
     const char* m = getenv("TMPC_QP_MODE");
     if (m && m[0] == 'w') h->qp_mode = 0;
+    if (m && m[0] == 't') h->qp_mode = 1;
+    h->trace = getenv("TMPC_TRACE") != nullptr;
+    const char* tm = getenv("TMPC_QP_THREAD_MIN");
+    if (tm) h->qp_thread_min = atoi(tm);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     int tps = 512;
@@ -241,7 +248,7 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
     if (tps < 32) tps = 32;
     h->qp_blocks = prop.multiProcessorCount * (tps / tm_qp_thread_block() > 0 ? tps / tm_qp_thread_block() : 1);
     h->qp_ws_per_inst = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact);
-    if (h->qp_mode == 1) {
+    if (h->qp_mode >= 1) {
       const size_t nthreads = (size_t)h->qp_blocks * tm_qp_thread_block();
       if (cudaMalloc(&h->qp_ws, nthreads * h->qp_ws_per_inst * sizeof(double)) != cudaSuccess ||
           cudaMalloc(&h->qp_counter, sizeof(int)) != cudaSuccess) {
@@ -348,6 +355,7 @@ int tmpc_reset(tmpc_handle* h, int64_t B) {
   if (ensure_capacity(h, B)) return 1;
   h->index = 0;
   h->S.B = B;
+  h->uniform_ws = true;
   TmProb& P = h->P;
   // w0 <- reference window at phase 0, lam0 <- ref_du[0]   (pmpc.py:930-942)
   std::vector<double> w0(P.n_w);
@@ -385,7 +393,7 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   S.list_next = h->list_a;
   S.cnt_next = h->cnts;
   S.cnt_relin = h->cnts + 1;
-  const int per = P.hessian_exact ? TM_NPAIR : NZ;
+  const int per = tm_lin_tasks_per_stage(P.hessian_exact);
   int64_t launches = 0, n_qp = 0, n_lin = 0;
   float ms_lin = 0, ms_qp = 0, ms_post = 0, ms;
   const unsigned wblocks = (unsigned)((B + QP_WARPS - 1) / QP_WARPS);
@@ -395,7 +403,16 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   CK(cudaEventRecord(h->ev[6], st));
   k_prefilter<<<wblocks, QP_WARPS * 32, 0, st>>>(P, S);
   CK(cudaEventRecord(h->ev[0], st));
-  k_lin<<<lin_grid(B), LIN_THREADS, 0, st>>>(P, S, nullptr, nullptr, (int)B, 0, per);
+  if (h->uniform_ws && B > 1) {
+    // right after reset every instance starts from the same (w0, lam0): linearise one and replicate the record
+    k_lin<<<lin_grid(1), LIN_THREADS, 0, st>>>(P, S, nullptr, nullptr, 1, 0, per);
+    const int64_t nrec = (int64_t)P.N * TM_LSZ;
+    k_bcast<<<(unsigned)(((B - 1) * nrec + 255) / 256), 256, 0, st>>>(S.LIN + nrec, S.LIN, B - 1, (int)nrec);
+    ++launches; n_lin -= (B - 1) * P.N;
+  } else {
+    k_lin<<<lin_grid(B), LIN_THREADS, 0, st>>>(P, S, nullptr, nullptr, (int)B, 0, per);
+  }
+  h->uniform_ws = false;
   CK(cudaEventRecord(h->ev[1], st));
   k_init<<<wblocks, QP_WARPS * 32, 0, st>>>(P, S);
   CK(cudaGetLastError());
@@ -419,7 +436,8 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
       S.list_retry = (pass & 1) ? h->retry_b : h->retry_a;
       S.cnt_retry = h->cnts + 2 + (pass & 1);
       if (pass >= 2) CK(cudaMemsetAsync(S.cnt_retry, 0, sizeof(int), st));
-      if (h->qp_mode == 1)
+      const bool use_thread = h->qp_mode == 1 || (h->qp_mode == 2 && nact >= (pass == 0 ? h->qp_thread_min : 8 * (int64_t)h->qp_thread_min));
+      if (use_thread)
         CK(tm_launch_qp_thread(P, S, plist, (int)nact, pcnt, h->qp_ws, h->qp_ws_per_inst, h->qp_blocks, h->qp_counter, st));
       else
         k_qp<<<wb, QP_WARPS * 32, h->qp_smem, st>>>(P, S, plist, (int)nact, pcnt);
@@ -434,9 +452,14 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
     launches += 2; n_qp += nact; n_lin += nact * P.N;
     CK(cudaMemcpyAsync(hc, h->cnts, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); ms_qp += ms;
-    CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); ms_lin += ms;
-    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); ms_post += ms;
+    {
+      float a, b2, c2;
+      CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1])); ms_qp += a;
+      CK(cudaEventElapsedTime(&b2, h->ev[1], h->ev[2])); ms_lin += b2;
+      CK(cudaEventElapsedTime(&c2, h->ev[2], h->ev[3])); ms_post += c2;
+      if (h->trace) fprintf(stderr, "[tmpc] it %3d nact %8lld  qp %9.3f ms  lin %9.3f ms  post %8.3f ms  next %d relin %d\n",
+                            iter_guard, (long long)nact, a, b2, c2, hc[0], hc[1]);
+    }
     if (hc[1] > 0) {   // damped steps: re-linearise at the accepted point, then test convergence
       CK(cudaEventRecord(h->ev[0], st));
       k_lin<<<lin_grid(hc[1]), LIN_THREADS, 0, st>>>(P, S, S.list_relin, nullptr, hc[1], 0, per);

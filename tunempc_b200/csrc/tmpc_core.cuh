@@ -230,49 +230,264 @@ TM_HD void tm_integrate(const double* x0, const double* u, int i, int j, double*
 #endif
 }
 
-// one linearisation task.  trial = 1: evaluate at (W + D, LAMQ), else at (W, LAM).
-// exact mode: task id pr in [0, NPAIR) is the pair (i,j); gauss-newton mode: pr in [0, NZ) is direction i.
-TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, int pr, int trial) {
+// ---- grouped linearisation: one task integrates x, up to TMPC_LIN_D first-order directions and up to TMPC_LIN_PP
+// second-order pairs among them, so the ODE, its Jacobian and its second derivatives are evaluated once per group
+// (TMPC_LIN_NG groups cover all NZ(NZ+1)/2 pairs; tables generated by modelgen.lin_groups).
+#define TM_LD TMPC_LIN_D
+#define TM_LP TMPC_LIN_PP
+TM_HD constexpr int tm_g_nd(int g) { constexpr int t[] = TMPC_LIN_GND; return t[g]; }
+TM_HD constexpr int tm_g_np(int g) { constexpr int t[] = TMPC_LIN_GNP; return t[g]; }
+TM_HD constexpr int tm_g_dir(int g, int a) { constexpr int t[] = TMPC_LIN_GD; return t[g * TM_LD + a]; }
+TM_HD constexpr int tm_g_own(int g, int a) { constexpr int t[] = TMPC_LIN_GOWN; return t[g * TM_LD + a]; }
+TM_HD constexpr int tm_g_pa(int g, int p) { constexpr int t[] = TMPC_LIN_GPA; return t[g * TM_LP + p]; }
+TM_HD constexpr int tm_g_pb(int g, int p) { constexpr int t[] = TMPC_LIN_GPB; return t[g * TM_LP + p]; }
+TM_HD constexpr int tm_g_pi(int g, int p) { constexpr int t[] = TMPC_LIN_GPI; return t[g * TM_LP + p]; }
+
+// derivative of the group state at stage argument (Xs, Ss, Ts).  ND directions with global ids dir[a]
+template <int ND, int NP, class DirF, class PaF, class PbF>
+TM_HD void tm_rhs_group(const double* Xs, const double* u, const double (*Ss)[NX], const double (*Ts)[NX], DirF dir, PaF pa,
+                        PbF pb, double* k, double (*dS)[NX], double (*dT)[NX]) {
+  double J[NX * NZ];
+  double Hn[TMPC_NHESS > 0 ? TMPC_NHESS : 1];
+  if (NP > 0) tmpc_ode_d2(Xs, u, k, J, Hn); else tmpc_ode_jac(Xs, u, k, J);
+  double v[ND > 0 ? ND : 1][NZ];
+#pragma unroll
+  for (int a = 0; a < ND; ++a) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) v[a][i] = Ss[a][i];
+#pragma unroll
+    for (int b = 0; b < NU; ++b) v[a][NX + b] = (dir(a) == NX + b) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double t = 0.0;
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) t += J[i * NZ + b] * v[a][b];
+      dS[a][i] = t;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    double dd[NX];
+    tmpc_ode_bilin(Hn, v[pa(p)], v[pb(p)], dd);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double t = dd[i];
+#pragma unroll
+      for (int b = 0; b < NX; ++b) t += J[i * NZ + b] * Ts[p][b];
+      dT[p][i] = t;
+    }
+  }
+}
+
+template <int ND, int NP, class DirF, class PaF, class PbF>
+TM_HD void tm_integrate_group(const double* x0, const double* u, DirF dir, PaF pa, PbF pb, double* X, double (*S)[NX],
+                              double (*T)[NX]) {
+#pragma unroll
+  for (int i = 0; i < NX; ++i) X[i] = x0[i];
+#pragma unroll
+  for (int a = 0; a < ND; ++a)
+#pragma unroll
+    for (int i = 0; i < NX; ++i) S[a][i] = (dir(a) == i) ? 1.0 : 0.0;
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+#pragma unroll
+    for (int i = 0; i < NX; ++i) T[p][i] = 0.0;
+#if TMPC_DISCRETE
+  {
+    double k[NX], dS[ND > 0 ? ND : 1][NX], dT[NP > 0 ? NP : 1][NX];
+    tm_rhs_group<ND, NP>(X, u, S, T, dir, pa, pb, k, dS, dT);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      X[i] = k[i];
+#pragma unroll
+      for (int a = 0; a < ND; ++a) S[a][i] = dS[a][i];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) T[p][i] = dT[p][i];
+    }
+  }
+#else
+  const double h = TMPC_RK_DT;
+  for (int s = 0; s < TMPC_RK_STEPS; ++s) {
+    double aX[NX], aS[ND > 0 ? ND : 1][NX], aT[NP > 0 ? NP : 1][NX];
+    double k[NX], dS[ND > 0 ? ND : 1][NX], dT[NP > 0 ? NP : 1][NX];
+    double Xs[NX], Ss[ND > 0 ? ND : 1][NX], Ts[NP > 0 ? NP : 1][NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      Xs[i] = X[i];
+#pragma unroll
+      for (int a = 0; a < ND; ++a) Ss[a][i] = S[a][i];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) Ts[p][i] = T[p][i];
+    }
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      tm_rhs_group<ND, NP>(Xs, u, Ss, Ts, dir, pa, pb, k, dS, dT);
+      const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+      const double cn = (st == 2) ? 1.0 : 0.5;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        aX[i] = (st == 0) ? k[i] : aX[i] + wgt * k[i];
+        if (st < 3) Xs[i] = X[i] + cn * h * k[i];
+#pragma unroll
+        for (int a = 0; a < ND; ++a) {
+          aS[a][i] = (st == 0) ? dS[a][i] : aS[a][i] + wgt * dS[a][i];
+          if (st < 3) Ss[a][i] = S[a][i] + cn * h * dS[a][i];
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          aT[p][i] = (st == 0) ? dT[p][i] : aT[p][i] + wgt * dT[p][i];
+          if (st < 3) Ts[p][i] = T[p][i] + cn * h * dT[p][i];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      X[i] += h / 6.0 * aX[i];
+#pragma unroll
+      for (int a = 0; a < ND; ++a) S[a][i] += h / 6.0 * aS[a][i];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) T[p][i] += h / 6.0 * aT[p][i];
+    }
+  }
+#endif
+}
+
+// exact-Hessian group G: writes its owned S columns, its W entries and (group 0) xf
+template <int G>
+TM_HD void tm_lin_group_exact(const double* x, const double* u, const double* lam, double* rec) {
+  constexpr int ND = tm_g_nd(G), NP = tm_g_np(G);
+  double X[NX], S[ND][NX], T[NP][NX];
+  tm_integrate_group<ND, NP>(x, u, [](int a) { return tm_g_dir(G, a); }, [](int p) { return tm_g_pa(G, p); },
+                             [](int p) { return tm_g_pb(G, p); }, X, S, T);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    double wij = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) wij += lam[i] * T[p][i];
+    rec[NX + NX * NZ + tm_g_pi(G, p)] = wij;
+  }
+#pragma unroll
+  for (int a = 0; a < ND; ++a)
+    if (tm_g_own(G, a)) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) rec[NX + i * NZ + tm_g_dir(G, a)] = S[a][i];
+    }
+  if (G == 0) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) rec[i] = X[i];
+  }
+}
+
+// Gauss-Newton group g: directions 3g .. 3g+2 (first order only)
+#define TM_GN_NG ((NZ + 2) / 3)
+template <int G>
+TM_HD void tm_lin_group_gn(const double* x, const double* u, double* rec) {
+  constexpr int ND = (NZ - 3 * G) < 3 ? (NZ - 3 * G) : 3;
+  double X[NX], S[ND][NX], T[1][NX];
+  tm_integrate_group<ND, 0>(x, u, [](int a) { return 3 * G + a; }, [](int) { return 0; }, [](int) { return 0; }, X, S, T);
+#pragma unroll
+  for (int a = 0; a < ND; ++a)
+#pragma unroll
+    for (int i = 0; i < NX; ++i) rec[NX + i * NZ + 3 * G + a] = S[a][i];
+  if (G == 0) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) rec[i] = X[i];
+  }
+}
+
+#ifdef TMPC_LIN_GROUPED
+TM_HD int tm_lin_tasks_per_stage(int hessian_exact) { return hessian_exact ? TMPC_LIN_NG : TM_GN_NG; }
+#else
+TM_HD int tm_lin_tasks_per_stage(int hessian_exact) { return hessian_exact ? TM_NPAIR : TM_GN_NG; }
+#endif
+
+// one linearisation task.  trial = 1: evaluate at (W + D, LAMQ), else at (W, LAM).  g = group id.
+TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, int g, int trial) {
   const double* w = S.W + inst * P.n_w + (int64_t)k * NZ;
   double x[NX], u[NU];
 #pragma unroll
   for (int a = 0; a < NX; ++a) x[a] = w[a];
 #pragma unroll
   for (int b = 0; b < NU; ++b) u[b] = w[NX + b];
-  if (trial && S.qpstat[inst] == 0) {
+  if (trial && S.qpstat[inst] != 0) return;   // failed QP: keep LIN at W for the final statistics
+  if (trial) {
     const double* d = S.D + inst * P.n_w + (int64_t)k * NZ;
 #pragma unroll
     for (int a = 0; a < NX; ++a) x[a] += d[a];
 #pragma unroll
     for (int b = 0; b < NU; ++b) u[b] += d[NX + b];
   }
-  if (trial && S.qpstat[inst] != 0) return;   // failed QP: keep LIN at W for the final statistics
   double* rec = S.LIN + (inst * P.N + k) * (int64_t)TM_LSZ;
-  double X[NX], Si[NX], Sj[NX], T[NX];
   if (P.hessian_exact) {
-    int i, j;
-    tm_pair_ij(pr, i, j);
-    tm_integrate<2>(x, u, i, j, X, Si, Sj, T);
-    const double* lam = (trial ? S.LAMQ : S.LAM) + inst * P.n_g + tm_gdyn(P, k);
-    double wij = 0.0;
+    const double* lamp = (trial ? S.LAMQ : S.LAM) + inst * P.n_g + tm_gdyn(P, k);
+    double lam[NX];
 #pragma unroll
-    for (int a = 0; a < NX; ++a) wij += lam[a] * T[a];
-    rec[NX + NX * NZ + pr] = wij;
-    if (i == j) {
-#pragma unroll
-      for (int a = 0; a < NX; ++a) rec[NX + a * NZ + i] = Si[a];
+    for (int a = 0; a < NX; ++a) lam[a] = lamp[a];
+    // one (i,j) pair per thread: 164 registers, no spills, FP64 pipe 82 % busy.  The grouped variant
+    // (tm_lin_group_exact: 3 directions + 3-4 pairs per thread, half the flops) needs 255 registers, spills, and ran
+    // 3.5x slower on B200 (profiles/r01b_summary.md) -- kept for models with a cheaper right-hand side.
+#ifdef TMPC_LIN_GROUPED
+    switch (g) {
+      case 0: tm_lin_group_exact<0>(x, u, lam, rec); break;
+#if TMPC_LIN_NG > 1
+      case 1: tm_lin_group_exact<1>(x, u, lam, rec); break;
+#endif
+#if TMPC_LIN_NG > 2
+      case 2: tm_lin_group_exact<2>(x, u, lam, rec); break;
+#endif
+#if TMPC_LIN_NG > 3
+      case 3: tm_lin_group_exact<3>(x, u, lam, rec); break;
+#endif
+#if TMPC_LIN_NG > 4
+      case 4: tm_lin_group_exact<4>(x, u, lam, rec); break;
+#endif
+#if TMPC_LIN_NG > 5
+      case 5: tm_lin_group_exact<5>(x, u, lam, rec); break;
+#endif
+#if TMPC_LIN_NG > 6
+      case 6: tm_lin_group_exact<6>(x, u, lam, rec); break;
+#endif
+#if TMPC_LIN_NG > 7
+      case 7: tm_lin_group_exact<7>(x, u, lam, rec); break;
+#endif
+      default: break;
     }
-    if (pr == 0) {
+#else
+    {
+      int i, j;
+      tm_pair_ij(g, i, j);
+      double X[NX], Si[NX], Sj[NX], T[NX];
+      tm_integrate<2>(x, u, i, j, X, Si, Sj, T);
+      double wij = 0.0;
 #pragma unroll
-      for (int a = 0; a < NX; ++a) rec[a] = X[a];
+      for (int a = 0; a < NX; ++a) wij += lam[a] * T[a];
+      rec[NX + NX * NZ + g] = wij;
+      if (i == j) {
+#pragma unroll
+        for (int a = 0; a < NX; ++a) rec[NX + a * NZ + i] = Si[a];
+      }
+      if (g == 0) {
+#pragma unroll
+        for (int a = 0; a < NX; ++a) rec[a] = X[a];
+      }
     }
+#endif
   } else {
-    tm_integrate<1>(x, u, pr, pr, X, Si, Sj, T);
-#pragma unroll
-    for (int a = 0; a < NX; ++a) rec[NX + a * NZ + pr] = Si[a];
-    if (pr == 0) {
-#pragma unroll
-      for (int a = 0; a < NX; ++a) rec[a] = X[a];
+    switch (g) {
+      case 0: tm_lin_group_gn<0>(x, u, rec); break;
+#if (TMPC_NZ > 3)
+      case 1: tm_lin_group_gn<1>(x, u, rec); break;
+#endif
+#if (TMPC_NZ > 6)
+      case 2: tm_lin_group_gn<2>(x, u, rec); break;
+#endif
+#if (TMPC_NZ > 9)
+      case 3: tm_lin_group_gn<3>(x, u, rec); break;
+#endif
+#if (TMPC_NZ > 12)
+#error "more than 4 Gauss-Newton groups: extend the dispatch in tm_lin_task"
+#endif
+      default: break;
     }
   }
 }

@@ -84,6 +84,32 @@ def _emit_block(lines, assigns, outputs):
     return int(nops)
 
 
+def lin_groups(nz, d=3):
+    """Cover all direction pairs (i<=j) of nz directions by groups of <= d directions (a pair covering design, found
+    exhaustively) and assign every pair to exactly one group, balanced.  One CUDA thread integrates one group: the ODE,
+    its Jacobian and second derivatives are evaluated once per group instead of once per pair."""
+    import itertools
+    d = min(d, nz)
+    pairs = [(i, j) for i in range(nz) for j in range(i + 1, nz)]
+    triples = list(itertools.combinations(range(nz), d))
+    groups = None
+    for ng in range(1, len(pairs) + 2):
+        for gs in itertools.combinations(triples, ng):
+            cov = set(p for g in gs for p in itertools.combinations(g, 2))
+            if len(cov) == len(pairs) and set(x for g in gs for x in g) == set(range(nz)):
+                groups = list(gs)
+                break
+        if groups:
+            break
+    allp = [(i, j) for i in range(nz) for j in range(i, nz)]
+    load = [[] for _ in groups]
+    opts = lambda p: [g for g, t in enumerate(groups) if p[0] in t and p[1] in t]
+    for p in sorted(allp, key=lambda p: len(opts(p))):
+        g = min(opts(p), key=lambda g: len(load[g]))
+        load[g].append(p)
+    return groups, load
+
+
 def generate_header(model: OdeModel, out_path: str) -> dict:
     nx, nu = model.nx, model.nu
     nz = nx + nu
@@ -125,6 +151,31 @@ def generate_header(model: OdeModel, out_path: str) -> dict:
     L.append("#define TMPC_HESS_B {%s}" % ",".join(str(h[1]) for h in hess) if hess else "#define TMPC_HESS_B {0}")
     L.append("#define TMPC_HESS_C {%s}" % ",".join(str(h[2]) for h in hess) if hess else "#define TMPC_HESS_C {0}")
 
+    # linearisation task groups (see lin_groups)
+    groups, load = lin_groups(nz)
+    D = max(len(g) for g in groups)
+    PP = max(len(l) for l in load)
+    owner = {}
+    for gi, g in enumerate(groups):
+        for a in g:
+            owner.setdefault(a, gi)
+    gd, gown, gpa, gpb, gpi = [], [], [], [], []
+    pidx = lambda i, j: i * nz - i * (i - 1) // 2 + (j - i)
+    for gi, g in enumerate(groups):
+        gd += list(g) + [-1] * (D - len(g))
+        gown += [1 if owner[a] == gi else 0 for a in g] + [0] * (D - len(g))
+        for (i, j) in load[gi]:
+            gpa.append(g.index(i)); gpb.append(g.index(j)); gpi.append(pidx(i, j))
+        pad = PP - len(load[gi])
+        gpa += [0] * pad; gpb += [0] * pad; gpi += [-1] * pad
+    L.append("#define TMPC_LIN_NG %d\n#define TMPC_LIN_D %d\n#define TMPC_LIN_PP %d" % (len(groups), D, PP))
+    L.append("#define TMPC_LIN_GND {%s}" % ",".join(str(len(g)) for g in groups))
+    L.append("#define TMPC_LIN_GNP {%s}" % ",".join(str(len(l)) for l in load))
+    L.append("#define TMPC_LIN_GD {%s}" % ",".join(map(str, gd)))
+    L.append("#define TMPC_LIN_GOWN {%s}" % ",".join(map(str, gown)))
+    L.append("#define TMPC_LIN_GPA {%s}" % ",".join(map(str, gpa)))
+    L.append("#define TMPC_LIN_GPB {%s}" % ",".join(map(str, gpb)))
+    L.append("#define TMPC_LIN_GPI {%s}" % ",".join(map(str, gpi)))
     # ode
     L.append("TMPC_HD void tmpc_ode(const double* x, const double* u, double* f) {")
     L.append("  (void)x; (void)u;")
