@@ -20,6 +20,7 @@
 #include <vector>
 #include "tmpc.h"
 #include "tmpc_core.cuh"
+#include "tmpc_lin2.cuh"
 
 // thread-per-instance QP kernel (tmpc_qp_thread.cu)
 cudaError_t tm_launch_qp_thread(const TmProb& P, const TmState& S, const int* list, int cnt, const int* cnt_dev,
@@ -52,6 +53,7 @@ struct tmpc_handle {
   int qp_mode = 2;             // 2: hybrid (thread per instance for big launches, warp per instance for the tail), 1: thread, 0: warp
   int qp_thread_min = 16384;   // hybrid: launches with fewer candidate instances use the low-latency warp kernel
   bool trace = false;
+  int lin_mode = 2;             // 2: warp-specialised k_lin2 (RK4 models), 1: thread per (instance, stage, pair) k_lin
   bool uniform_ws = false;     // warm start identical for every instance (right after tmpc_reset)
   int qp_blocks = 0;           // resident CTAs of the thread-per-instance kernel
   double* qp_ws = nullptr;     // its workspace
@@ -150,6 +152,23 @@ __global__ void k_plant(const double* X, const double* U, int64_t B, double* Xn)
   for (int a = 0; a < NX; ++a) Xn[b * NX + a] = xf[a];
 }
 
+// linearise `cnt` instances (list == nullptr: identity) at the iterate (trial = 0) or at the trial point (trial = 1)
+static cudaError_t launch_lin(tmpc_handle* h, const int* list, int64_t cnt, int trial, cudaStream_t st) {
+  const TmProb& P = h->P;
+  const TmState& S = h->S;
+#if !TMPC_DISCRETE
+  if (h->lin_mode == 2) {
+    const unsigned grid = (unsigned)((cnt * P.N + 31) / 32);
+    if (P.hessian_exact) k_lin2<true><<<grid, L2_THREADS, tm_lin2_smem_bytes(), st>>>(P, S, list, nullptr, (int)cnt, trial);
+    else k_lin2<false><<<grid, L2_THREADS, tm_lin2_smem_bytes(), st>>>(P, S, list, nullptr, (int)cnt, trial);
+    return cudaGetLastError();
+  }
+#endif
+  const int per = tm_lin_tasks_per_stage(P.hessian_exact);
+  k_lin<<<(unsigned)((cnt * P.N * per + LIN_THREADS - 1) / LIN_THREADS), LIN_THREADS, 0, st>>>(P, S, list, nullptr, (int)cnt, trial, per);
+  return cudaGetLastError();
+}
+
 // dependent-chain-free DFMA loop: 8 independent accumulators per thread
 __global__ void k_fp64_peak(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -238,6 +257,16 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
     if (m && m[0] == 'w') h->qp_mode = 0;
     if (m && m[0] == 't') h->qp_mode = 1;
     h->trace = getenv("TMPC_TRACE") != nullptr;
+    const char* lm = getenv("TMPC_LIN_MODE");
+    if (lm) h->lin_mode = atoi(lm);
+#if TMPC_DISCRETE
+    h->lin_mode = 1;
+#else
+    if (tm_lin2_smem_bytes() > 48 * 1024) {
+      cudaFuncSetAttribute(k_lin2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm_lin2_smem_bytes());
+      cudaFuncSetAttribute(k_lin2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm_lin2_smem_bytes());
+    }
+#endif
     const char* tm = getenv("TMPC_QP_THREAD_MIN");
     if (tm) h->qp_thread_min = atoi(tm);
     cudaDeviceProp prop;
@@ -393,11 +422,9 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   S.list_next = h->list_a;
   S.cnt_next = h->cnts;
   S.cnt_relin = h->cnts + 1;
-  const int per = tm_lin_tasks_per_stage(P.hessian_exact);
   int64_t launches = 0, n_qp = 0, n_lin = 0;
   float ms_lin = 0, ms_qp = 0, ms_post = 0, ms;
   const unsigned wblocks = (unsigned)((B + QP_WARPS - 1) / QP_WARPS);
-  auto lin_grid = [&](int64_t cnt) { return (unsigned)((cnt * P.N * per + LIN_THREADS - 1) / LIN_THREADS); };
 
   CK(cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long), st));
   CK(cudaEventRecord(h->ev[6], st));
@@ -405,12 +432,12 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   CK(cudaEventRecord(h->ev[0], st));
   if (h->uniform_ws && B > 1) {
     // right after reset every instance starts from the same (w0, lam0): linearise one and replicate the record
-    k_lin<<<lin_grid(1), LIN_THREADS, 0, st>>>(P, S, nullptr, nullptr, 1, 0, per);
+    CK(launch_lin(h, nullptr, 1, 0, st));
     const int64_t nrec = (int64_t)P.N * TM_LSZ;
     k_bcast<<<(unsigned)(((B - 1) * nrec + 255) / 256), 256, 0, st>>>(S.LIN + nrec, S.LIN, B - 1, (int)nrec);
     ++launches; n_lin -= (B - 1) * P.N;
   } else {
-    k_lin<<<lin_grid(B), LIN_THREADS, 0, st>>>(P, S, nullptr, nullptr, (int)B, 0, per);
+    CK(launch_lin(h, nullptr, B, 0, st));
   }
   h->uniform_ws = false;
   CK(cudaEventRecord(h->ev[1], st));
@@ -444,7 +471,7 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
       ++launches;
     }
     CK(cudaEventRecord(h->ev[1], st));
-    k_lin<<<lin_grid(nact), LIN_THREADS, 0, st>>>(P, S, cur, nullptr, (int)nact, 1, per);
+    CK(launch_lin(h, cur, nact, 1, st));
     CK(cudaEventRecord(h->ev[2], st));
     k_post<<<wb, QP_WARPS * 32, 0, st>>>(P, S, cur, (int)nact);
     CK(cudaEventRecord(h->ev[3], st));
@@ -462,7 +489,7 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
     }
     if (hc[1] > 0) {   // damped steps: re-linearise at the accepted point, then test convergence
       CK(cudaEventRecord(h->ev[0], st));
-      k_lin<<<lin_grid(hc[1]), LIN_THREADS, 0, st>>>(P, S, S.list_relin, nullptr, hc[1], 0, per);
+      CK(launch_lin(h, S.list_relin, hc[1], 0, st));
       CK(cudaEventRecord(h->ev[1], st));
       k_conv<<<(unsigned)((hc[1] + QP_WARPS - 1) / QP_WARPS), QP_WARPS * 32, 0, st>>>(P, S, S.list_relin, S.cnt_relin);
       CK(cudaEventRecord(h->ev[2], st));

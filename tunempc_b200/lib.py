@@ -44,7 +44,7 @@ def build_model_lib(name, force=False, verbose=False):
     """nvcc-compile libtmpc_<name>.so in-tree for sm_100a (cross-compiles without a GPU)."""
     out = lib_path(name)
     srcs = [os.path.join(_PKG, "csrc", "tmpc.cu"), os.path.join(_PKG, "csrc", "tmpc_qp_thread.cu"),
-            os.path.join(_PKG, "csrc", "tmpc_core.cuh"),
+            os.path.join(_PKG, "csrc", "tmpc_core.cuh"), os.path.join(_PKG, "csrc", "tmpc_lin2.cuh"),
             os.path.join(_PKG, "csrc", "gen", "model_%s.h" % name), os.path.join(_ROOT, "include", "tmpc.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
         return out

@@ -110,6 +110,46 @@ def lin_groups(nz, d=3):
     return groups, load
 
 
+def lin2_roles(nz, npart=3):
+    """Role tables of the warp-specialised linearisation kernel (csrc/tmpc_lin2.cuh).  Every consumer warp runs the
+    SAME code on a 'star' of direction pairs: a centre direction d and up to `npart` partners j (j == d is the diagonal
+    pair), so that one operand column of every pair is shared.  The first nz roles own (integrate and publish) the
+    first-order column of their centre; further roles only read it.  Returns [(centre, owns, [partners])]."""
+    import random
+    rng = random.Random(0)
+    lower = -(-(nz * (nz + 1) // 2) // npart)
+    best = None
+    for attempt in range(400):
+        pairs = set((i, j) for i in range(nz) for j in range(i + 1, nz))
+        roles = [[d, 1, [d]] for d in range(nz)]
+        order = list(range(nz))
+        if attempt:
+            rng.shuffle(order)
+        for d in order:                          # owners pick partners among their free incident pairs
+            inc = sorted(e for e in pairs if d in e)
+            if attempt:
+                rng.shuffle(inc)
+            for e in inc[: npart - 1]:
+                roles[d][2].append(e[0] if e[1] == d else e[1])
+                pairs.discard(e)
+        while pairs:                             # the rest is grouped into stars (most frequent endpoint first)
+            cnt = {}
+            for (i, j) in pairs:
+                cnt[i] = cnt.get(i, 0) + 1
+                cnt[j] = cnt.get(j, 0) + 1
+            d = max(sorted(cnt), key=lambda k: cnt[k])
+            mine = sorted(e for e in pairs if d in e)[:npart]
+            roles.append([d, 0, [e[0] if e[1] == d else e[1] for e in mine]])
+            for e in mine:
+                pairs.discard(e)
+        if best is None or len(roles) < len(best):
+            best = roles
+        if len(best) <= max(lower, nz):
+            break
+    roles = best
+    return [(r[0], r[1], list(r[2])) for r in roles]
+
+
 def generate_header(model: OdeModel, out_path: str) -> dict:
     nx, nu = model.nx, model.nu
     nz = nx + nu
@@ -176,6 +216,18 @@ def generate_header(model: OdeModel, out_path: str) -> dict:
     L.append("#define TMPC_LIN_GPA {%s}" % ",".join(map(str, gpa)))
     L.append("#define TMPC_LIN_GPB {%s}" % ",".join(map(str, gpb)))
     L.append("#define TMPC_LIN_GPI {%s}" % ",".join(map(str, gpi)))
+    # warp-specialised kernel: consumer roles and the structural sparsity of J
+    roles = lin2_roles(nz, int(os.environ.get("TMPC_L2_NPART", "3")))
+    np2 = max(len(r[2]) for r in roles)
+    part = []
+    for _, _, js in roles:
+        part += list(js) + [-1] * (np2 - len(js))
+    L.append("#define TMPC_L2_NCW %d\n#define TMPC_L2_NP %d" % (len(roles), np2))
+    L.append("#define TMPC_L2_CEN {%s}" % ",".join(str(r[0]) for r in roles))
+    L.append("#define TMPC_L2_OWN {%s}" % ",".join(str(r[1]) for r in roles))
+    L.append("#define TMPC_L2_PART {%s}" % ",".join(map(str, part)))
+    L.append("#define TMPC_JNZ {%s}" % ",".join("0" if sp.simplify(J[a][b]) == 0 else "1"
+                                                  for a in range(nx) for b in range(nz)))
     # ode
     L.append("TMPC_HD void tmpc_ode(const double* x, const double* u, double* f) {")
     L.append("  (void)x; (void)u;")
@@ -206,6 +258,26 @@ def generate_header(model: OdeModel, out_path: str) -> dict:
                 terms.append("H[%d]*v[%d]*w[%d]" % (i, b, c))
             else:
                 terms.append("H[%d]*(v[%d]*w[%d]+v[%d]*w[%d])" % (i, b, c, c, b))
+        L.append("  out[%d] = %s;" % (a, " + ".join(terms) if terms else "0.0"))
+    L.append("}")
+    # the same bilinear form in two steps, for several w sharing one v:  G = d2f . v  (compact over the structural
+    # non-zeros (a,c)),  out = G w
+    gpos = {}
+    gterms = {}
+    for i, (a, b, c, _) in enumerate(hess):
+        for (cc, bb) in ((c, b),) if b == c else ((c, b), (b, c)):
+            gpos.setdefault((a, cc), len(gpos))
+            gterms.setdefault((a, cc), []).append("H[%d]*v[%d]" % (i, bb))
+    L.append("#define TMPC_NG %d" % max(1, len(gpos)))
+    L.append("TMPC_HD void tmpc_ode_hv(const double* H, const double* v, double* G) {")
+    L.append("  (void)H; (void)v; (void)G;")
+    for key, gi in gpos.items():
+        L.append("  G[%d] = %s;" % (gi, " + ".join(gterms[key])))
+    L.append("}")
+    L.append("TMPC_HD void tmpc_ode_gw(const double* G, const double* w, double* out) {")
+    L.append("  (void)G; (void)w;")
+    for a in range(nx):
+        terms = ["G[%d]*w[%d]" % (gi, c) for (aa, c), gi in gpos.items() if aa == a]
         L.append("  out[%d] = %s;" % (a, " + ".join(terms) if terms else "0.0"))
     L.append("}")
     c_B = sum(3 if b == c else 5 for _, b, c, _ in hess)
