@@ -63,15 +63,15 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
   S.status = status; S.iter = iter; S.flags = flags; S.fval = fval; S.nAS = nAS; S.nACtot = nACtot; S.nAC = nAC;
   std::vector<double> D((size_t)B * P.n_w), LQ((size_t)B * P.n_g), LIN((size_t)B * P.N * TM_LSZ),
       FILT((size_t)B * P.filter_cap * 2);
-  std::vector<int> nfilt(B), qpstat(B, 0), qpmode(B, 0), la(B), lb(B), lrel(B), lretry(B);
+  std::vector<int> nfilt(B), qpstat(B, 0), qpmode(B, 0), qpwork(B, 0), la(B), lb(B), lrel(B), lretry(B);
   std::vector<unsigned> almask((size_t)B * TM_ALW);
   int cnt_retry = 0;
   S.aswords = (P.N * P.nh + 31) / 32; if (S.aswords < 1) S.aswords = 1;
   std::vector<unsigned> asinit((size_t)B * S.aswords);
-  unsigned long long counters[8] = {0};
+  unsigned long long counters[TM_NCNT] = {0};
   int cnts[2] = {0, 0};
   S.D = D.data(); S.LAMQ = LQ.data(); S.LIN = LIN.data(); S.FILT = FILT.data(); S.nfilt = nfilt.data();
-  S.qpstat = qpstat.data(); S.qpmode = qpmode.data(); S.almask = almask.data(); S.list_retry = lretry.data(); S.cnt_retry = &cnt_retry; S.asinit = asinit.data(); S.counters = counters;
+  S.qpstat = qpstat.data(); S.qpmode = qpmode.data(); S.qpwork = qpwork.data(); S.almask = almask.data(); S.list_retry = lretry.data(); S.cnt_retry = &cnt_retry; S.asinit = asinit.data(); S.counters = counters;
   S.cnt_next = &cnts[0]; S.cnt_relin = &cnts[1]; S.list_relin = lrel.data();
   const int per = tm_lin_tasks_per_stage(P.hessian_exact);
   std::vector<double> wsbuf(tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact));
@@ -108,7 +108,7 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
     if (++guard > P.max_iter + 2) return 9;
   }
   for (long long i = 0; i < B; ++i) tm_shift(P, W + i * P.n_w, LAM + i * P.n_g, Wsh + i * P.n_w, Lsh + i * P.n_g);
-  if (counters_out) { counters_out[0] = (long long)counters[0]; counters_out[2] = nqp; counters_out[3] = nlin; counters_out[4] = (long long)counters[4]; counters_out[5] = (long long)counters[5]; counters_out[6] = (long long)counters[6]; counters_out[7] = (long long)counters[7]; }
+  if (counters_out) { counters_out[0] = (long long)counters[0]; counters_out[2] = nqp; counters_out[3] = nlin; counters_out[4] = (long long)counters[4]; counters_out[5] = (long long)counters[5]; counters_out[6] = (long long)counters[6]; counters_out[7] = (long long)counters[7]; for (int i = 8; i < TM_NCNT; ++i) counters_out[i] = (long long)counters[i]; }
   return 0;
 }
 

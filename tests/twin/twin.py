@@ -71,7 +71,7 @@ class Twin:
         fl = np.zeros(B, dtype=np.int32); fv = np.zeros(B); nAS = np.zeros(B, dtype=np.int32)
         nACt = np.zeros(B, dtype=np.int32); nAC = np.zeros(B, dtype=np.int32)
         Wsh = np.zeros_like(self.W); Lsh = np.zeros_like(self.LAM)
-        cnt = np.zeros(8, dtype=np.int64)
+        cnt = np.zeros(24, dtype=np.int64)
         C = np.ascontiguousarray(pb.C if pb.nh else np.zeros((1, pb.nz)))
         c = np.ascontiguousarray(pb.c if pb.nh else np.zeros(1))
         wref = np.ascontiguousarray(pb.wref); q = np.ascontiguousarray(pb.q); rdu = np.ascontiguousarray(self.tab.ref_du)

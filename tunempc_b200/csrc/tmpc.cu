@@ -43,6 +43,8 @@ struct tmpc_handle {
   std::vector<void*> tab_allocs, ws_allocs;
   int *list_a = nullptr, *list_b = nullptr, *cnts = nullptr;   // cnts[0] next, cnts[1] relin, cnts[2..3] retry ping-pong
   int *retry_a = nullptr, *retry_b = nullptr;
+  int *list_s = nullptr, *sort_bins = nullptr;                 // sorted copy of the active list, 2*SORT_BINS counters
+  bool sort_lists = true;
   double *Wsh = nullptr, *Lsh = nullptr;                       // shift targets
   double* X0buf = nullptr;                                     // device staging for tmpc_step_host
   int64_t counters_host[8] = {0};
@@ -150,6 +152,39 @@ __global__ void k_plant(const double* X, const double* U, int64_t B, double* Xn)
   tm_integrate<0>(x, u, 0, 0, xf, t1, t2, t3);
 #pragma unroll
   for (int a = 0; a < NX; ++a) Xn[b * NX + a] = xf[a];
+}
+
+// ---- scheduling: counting sort of the active list by the cost of each instance's previous QP (heaviest first) -------
+// Results do not depend on the order (instances are independent); the order only decides which instances share a warp
+// of the thread-per-instance QP kernel, i.e. how long lanes idle while the longest active-set loop of the warp finishes.
+#define SORT_BINS 64
+__global__ void k_sort_hist(const int* list, int cnt, const int* key, int* bins) {
+  __shared__ int sb[SORT_BINS];
+  if (threadIdx.x < SORT_BINS) sb[threadIdx.x] = 0;
+  __syncthreads();
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot < cnt) {
+    const int inst = list ? list[slot] : slot;
+    int k = key[inst];
+    k = k < 0 ? 0 : (k >= SORT_BINS ? SORT_BINS - 1 : k);
+    atomicAdd(&sb[k], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < SORT_BINS && sb[threadIdx.x]) atomicAdd(&bins[threadIdx.x], sb[threadIdx.x]);
+}
+__global__ void k_sort_scan(int* bins) {   // bins[SORT_BINS + b] = first output slot of bin b, descending key order
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = SORT_BINS - 1; b >= 0; --b) { bins[SORT_BINS + b] = acc; acc += bins[b]; }
+  }
+}
+__global__ void k_sort_scatter(const int* list, int cnt, const int* key, int* bins, int* out) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= cnt) return;
+  const int inst = list ? list[slot] : slot;
+  int k = key[inst];
+  k = k < 0 ? 0 : (k >= SORT_BINS ? SORT_BINS - 1 : k);
+  out[atomicAdd(&bins[SORT_BINS + k], 1)] = inst;
 }
 
 // linearise `cnt` instances (list == nullptr: identity) at the iterate (trial = 0) or at the trial point (trial = 1)
@@ -267,6 +302,8 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
       cudaFuncSetAttribute(k_lin2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm_lin2_smem_bytes());
     }
 #endif
+    const char* so = getenv("TMPC_SORT");
+    if (so) h->sort_lists = atoi(so) != 0;
     const char* tm = getenv("TMPC_QP_THREAD_MIN");
     if (tm) h->qp_thread_min = atoi(tm);
     cudaDeviceProp prop;
@@ -366,10 +403,10 @@ static int ensure_capacity(tmpc_handle* h, int64_t B) {
       dalloc(h, &S.LAMQ, b * P.n_g) || dalloc(h, &S.LIN, b * P.N * TM_LSZ) || dalloc(h, &S.G, b * P.n_g) ||
       dalloc(h, &S.FILT, b * P.filter_cap * 2) || dalloc(h, &S.fval, b) || dalloc(h, &S.nfilt, b) ||
       dalloc(h, &S.iter, b) || dalloc(h, &S.status, b) || dalloc(h, &S.flags, b) || dalloc(h, &S.nAS, b) ||
-      dalloc(h, &S.nACtot, b) || dalloc(h, &S.nAC, b) || dalloc(h, &S.qpstat, b) || dalloc(h, &S.qpmode, b) || dalloc(h, &S.almask, b * TM_ALW) ||
+      dalloc(h, &S.nACtot, b) || dalloc(h, &S.nAC, b) || dalloc(h, &S.qpstat, b) || dalloc(h, &S.qpmode, b) || dalloc(h, &S.qpwork, b) || dalloc(h, &h->list_s, b) || dalloc(h, &h->sort_bins, 2 * SORT_BINS) || dalloc(h, &S.almask, b * TM_ALW) ||
       dalloc(h, &h->retry_a, b) || dalloc(h, &h->retry_b, b) ||
       dalloc(h, &S.asinit, b * S.aswords) || dalloc(h, &h->list_a, b) || dalloc(h, &h->list_b, b) ||
-      dalloc(h, &S.list_relin, b) || dalloc(h, &h->cnts, 8) || dalloc(h, &S.counters, 8) ||
+      dalloc(h, &S.list_relin, b) || dalloc(h, &h->cnts, 8) || dalloc(h, &S.counters, TM_NCNT) ||
       dalloc(h, &h->Wsh, b * P.n_w) || dalloc(h, &h->Lsh, b * P.n_g) || dalloc(h, &h->X0buf, b * NX))
     return 1;
   h->cap = B;
@@ -398,6 +435,7 @@ int tmpc_reset(tmpc_handle* h, int64_t B) {
   k_bcast<<<(unsigned)((nw + 255) / 256), 256>>>(h->S.W, h->Wsh, B, P.n_w);
   CK(cudaDeviceSynchronize());   // Wsh row is overwritten below only by later steps; keep ordering simple
   k_bcast<<<(unsigned)((ng + 255) / 256), 256>>>(h->S.LAM, P.ref_du, B, P.n_g);
+  CK(cudaMemset(h->S.qpwork, 0, (size_t)B * sizeof(int)));
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   return 0;
@@ -426,10 +464,11 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   float ms_lin = 0, ms_qp = 0, ms_post = 0, ms;
   const unsigned wblocks = (unsigned)((B + QP_WARPS - 1) / QP_WARPS);
 
-  CK(cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(S.counters, 0, TM_NCNT * sizeof(unsigned long long), st));
   CK(cudaEventRecord(h->ev[6], st));
   k_prefilter<<<wblocks, QP_WARPS * 32, 0, st>>>(P, S);
   CK(cudaEventRecord(h->ev[0], st));
+  const bool was_uniform = h->uniform_ws;   // first step after reset: no per-instance QP cost history yet
   if (h->uniform_ws && B > 1) {
     // right after reset every instance starts from the same (w0, lam0): linearise one and replicate the record
     CK(launch_lin(h, nullptr, 1, 0, st));
@@ -448,12 +487,23 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); ms_lin += ms;
 
   const int* cur = nullptr;   // nullptr = identity list (all instances)
+  const int* src = nullptr;   // the list the previous iteration produced (list_a / list_b), before sorting
   int64_t nact = B;
   int hc[2];
   int iter_guard = 0;
   while (nact > 0) {
     const unsigned wb = (unsigned)((nact + QP_WARPS - 1) / QP_WARPS);
-    S.list_next = (cur == h->list_a) ? h->list_b : h->list_a;
+    S.list_next = (src == h->list_a) ? h->list_b : h->list_a;
+    cur = src;
+    if (h->sort_lists && h->qp_mode >= 1 && nact >= h->qp_thread_min && !(was_uniform && iter_guard == 0)) {
+      const unsigned sb = (unsigned)((nact + 255) / 256);
+      CK(cudaMemsetAsync(h->sort_bins, 0, 2 * SORT_BINS * sizeof(int), st));
+      k_sort_hist<<<sb, 256, 0, st>>>(src, (int)nact, S.qpwork, h->sort_bins);
+      k_sort_scan<<<1, 32, 0, st>>>(h->sort_bins);
+      k_sort_scatter<<<sb, 256, 0, st>>>(src, (int)nact, S.qpwork, h->sort_bins, h->list_s);
+      launches += 3;
+      cur = h->list_s;
+    }
     CK(cudaMemsetAsync(h->cnts, 0, 4 * sizeof(int), st));
     CK(cudaEventRecord(h->ev[0], st));
     for (int pass = 0; pass < 5; ++pass) {
@@ -500,7 +550,7 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
       CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); ms_lin += ms;
       CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); ms_post += ms;
     }
-    cur = S.list_next;
+    src = S.list_next;
     nact = hc[0];
     if (++iter_guard > P.max_iter + 2) { h->err = "tmpc_step: iteration guard tripped"; return 1; }
   }
@@ -517,7 +567,7 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   ++launches;
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev[7], st));
-  unsigned long long cnt_host[8];
+  unsigned long long cnt_host[TM_NCNT];
   CK(cudaMemcpyAsync(cnt_host, S.counters, sizeof cnt_host, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   { double* t = S.W; S.W = h->Wsh; h->Wsh = t; }
@@ -530,6 +580,14 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   h->counters_host[2] = n_qp;
   h->counters_host[3] = n_lin;
   h->counters_host[4] = (int64_t)cnt_host[4];
+  h->counters_host[5] = (int64_t)cnt_host[5];
+  h->counters_host[6] = (int64_t)cnt_host[6];
+  h->counters_host[7] = (int64_t)cnt_host[7];
+  if (h->trace) {
+    fprintf(stderr, "[tmpc] qp attempts %llu gi %llu ricc %llu | fresh ok/inf/npd/mask %llu %llu %llu %llu | retry %llu %llu %llu %llu | gn %llu %llu %llu %llu\n",
+            cnt_host[5], cnt_host[6], cnt_host[7], cnt_host[8], cnt_host[9], cnt_host[10], cnt_host[11], cnt_host[12],
+            cnt_host[13], cnt_host[14], cnt_host[15], cnt_host[16], cnt_host[17], cnt_host[18], cnt_host[19]);
+  }
   return 0;
 }
 

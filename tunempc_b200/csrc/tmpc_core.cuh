@@ -92,6 +92,7 @@ TM_HD TmP tm_mkp(double* base, size_t off) { return base + off; }
 #define TM_NPAIR (NZ * (NZ + 1) / 2)
 #define TM_LSZ (NX + NX * NZ + TM_NPAIR)   /* per-stage linearisation record: xf | S row-major nx*nz | W packed i<=j */
 #define TM_INF 1e300
+#define TM_NCNT 24
 #define TM_ALW 8   /* words of the augmented-Lagrangian row mask: supports N*nh <= 256 */
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -118,12 +119,14 @@ struct TmState {
   int *nfilt, *iter, *status, *flags, *nAS, *nACtot, *nAC;
   int* qpstat;            // B: result of the last QP (0 ok)
   int* qpmode;            // B: 0 fresh, 1..3 retry with the stored row mask, 100 Gauss-Newton fallback
+  int* qpwork;            // B: active-set iterations of the instance's last QP (scheduling key: the thread-per-instance
+                          //    kernel is fed instances of similar cost so that the lanes of a warp stay in step)
   unsigned* almask;       // B*TM_ALW: augmented-Lagrangian row mask carried between retries
   int *list_retry, *cnt_retry;   // instances whose QP must be re-solved (filled by tm_qp)
   unsigned* asinit;       // B*aswords bitmask of initially active inequality rows
   int aswords;
   int *list_next, *cnt_next, *list_relin, *cnt_relin;
-  unsigned long long* counters;   // [0] iterations [2] qp solves [3] stage linearisations [4] ls dynamics evals
+  unsigned long long* counters;   // TM_NCNT: [0] iterations [4] ls dynamics evals [5] QP attempts [6] active-set iterations [7] Riccati solves [8..19] attempt histogram
 };
 
 TM_HD int tm_gdyn(const TmProb& P, int k) { return NX + k * (NX + P.nh); }
@@ -499,7 +502,7 @@ TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, i
 // Exact active-set solution: inactive multipliers are exact zeros, as the reference relies on (sqp_method.py:421).
 // ---------------------------------------------------------------------------------------------------------------
 struct TmQpWs {
-  TmP AB, Q, r, b, K, Lc, hv, d, y, rhs, kk, P0, P1, PAB, F, pv, tr;
+  TmP AB, Q, r, b, K, Lc, hv, d, y, rhs, kk, kkm, P0, P1, PAB, F, pv, tr;
   TmP sl;                 // E = N*nh + nxt: current value of every constraint row (slack / terminal residual)
   TmP Mc;                 // M x E: column j = N G n_j of the dual Hessian for working-set member j (+ one candidate)
   TmP Lf;                 // M x M: Cholesky factor of the working-set Schur complement S = N_A G N_A'
@@ -518,6 +521,7 @@ TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
   n += (size_t)N * (nh > 0 ? nh : 1);   // hv
   n += 3 * (size_t)(N + 1) * NZ;   // d y rhs
   n += (size_t)N * NU;             // kk
+  n += (size_t)NX * N * NU;        // kkm (feed-forward of the multi-right-hand-side terminal sweep)
   n += 2 * NX * NX + NX * NZ + NZ * NZ;   // P0 P1 PAB F
   n += 4 * NX;                     // pv (two buffers of NX, e0, spare)
   n += (nxt > 0 ? nxt : 1);        // tr
@@ -543,6 +547,7 @@ TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s)
   TM_CARVE(y, (size_t)(N + 1) * NZ);
   TM_CARVE(rhs, (size_t)(N + 1) * NZ);
   TM_CARVE(kk, (size_t)N * NU);
+  TM_CARVE(kkm, (size_t)NX * N * NU);
   TM_CARVE(P0, NX * NX);
   TM_CARVE(P1, NX * NX);
   TM_CARVE(PAB, NX * NZ);
@@ -665,6 +670,213 @@ TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, TmP rhs, TmP out, int kfrom
     TM_SYNC();
   }
   for (int a = lane; a < NU; a += TM_NL) out[N * NZ + NX + a] = 0.0;
+  TM_SYNC();
+}
+
+// ---- dual-Hessian columns ---------------------------------------------------------------------------------------
+// Column for constraint row qe:  y = qs * G n_qe  is swept stage by stage and never stored; mq[e] = n_e' y for every
+// row e.  The NX-wide recursions are carried in registers by every lane (too small to split; no synchronisation inside
+// the sweeps); workspace traffic is the factor (AB, K, Lc), the per-stage feed-forward kk and the column itself.
+TM_HD void tm_ricc_col(const TmProb& P, TmQpWs& s, int qe, double qs, TmP mq) {
+  const int N = P.N, nh = P.nh, NI = N * nh;
+  const int lane = TM_LANE;
+  double pv[NX], rz[NZ];
+#pragma unroll
+  for (int a = 0; a < NX; ++a) pv[a] = 0.0;
+#pragma unroll
+  for (int b = 0; b < NZ; ++b) rz[b] = 0.0;
+  int kb;
+  if (qe >= NI) {
+    const int ti = P.term_idx[qe - NI];
+#pragma unroll
+    for (int a = 0; a < NX; ++a) if (a == ti) pv[a] = -qs;
+    kb = N - 1;
+  } else {
+    kb = qe / nh;
+    const double* Ci = P.C + (size_t)(qe % nh) * NZ;
+#pragma unroll
+    for (int b = 0; b < NZ; ++b) rz[b] = -qs * Ci[b];
+  }
+  for (int k = kb; k >= 0; --k) {
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NU * NX;
+    const TmP L = s.Lc + (size_t)k * NU * NU;
+    double fu[NU > 0 ? NU : 1], pn[NX];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      double v = (k == kb) ? rz[NX + a] : 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + NX + a] * pv[i];
+      fu[a] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      double v = (k == kb) ? rz[j] : 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + j] * pv[i];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) v += Kk[a * NX + j] * fu[a];
+      pn[j] = v;
+    }
+    double ku[NU > 0 ? NU : 1];
+#pragma unroll
+    for (int a = 0; a < NU; ++a) ku[a] = -fu[a];
+    tm_chol_small_solve(L, ku);
+    for (int a = lane; a < NU; a += TM_NL) s.kk[k * NU + a] = ku[a];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) pv[j] = pn[j];
+  }
+  TM_SYNC();
+  double z[NZ];
+#pragma unroll
+  for (int b = 0; b < NZ; ++b) z[b] = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NU * NX;
+#pragma unroll
+    for (int a = 0; a < NU; ++a) {
+      double v = (k <= kb) ? s.kk[k * NU + a] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) v += Kk[a * NX + j] * z[j];
+      z[NX + a] = v;
+    }
+    for (int i = lane; i < nh; i += TM_NL) {
+      const double* Ci = P.C + (size_t)i * NZ;
+      double t = 0.0;
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) t += Ci[b] * z[b];
+      mq[k * nh + i] = t;
+    }
+    double xn[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double v = 0.0;
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) v += AB[i * NZ + b] * z[b];
+      xn[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) z[i] = xn[i];
+  }
+  for (int t = lane; t < P.nxt; t += TM_NL) {
+    const int ti = P.term_idx[t];
+    double v = 0.0;
+#pragma unroll
+    for (int a = 0; a < NX; ++a) if (a == ti) v = z[a];
+    mq[NI + t] = v;
+  }
+  TM_SYNC();
+}
+
+// The columns of ALL terminal rows (sign +1) in one multi-right-hand-side sweep: column t -> Mc[t*E + e].  The factor is
+// read once for the nxt (<= NX) right-hand sides instead of once per row.
+TM_HD void tm_ricc_cols_term(const TmProb& P, TmQpWs& s, TmP Mc, int E) {
+  const int N = P.N, nh = P.nh, NI = N * nh, nxt = P.nxt;
+  const int lane = TM_LANE;
+  double pv[NX][NX];
+#pragma unroll
+  for (int c = 0; c < NX; ++c) {
+    const int ti = (c < nxt) ? P.term_idx[c] : -1;
+#pragma unroll
+    for (int a = 0; a < NX; ++a) pv[c][a] = (a == ti) ? -1.0 : 0.0;
+  }
+  for (int k = N - 1; k >= 0; --k) {
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NU * NX;
+    const TmP L = s.Lc + (size_t)k * NU * NU;
+    double ABr[NX * NZ], Kr[NU * NX > 0 ? NU * NX : 1], Lr[NU * NU > 0 ? NU * NU : 1];
+#pragma unroll
+    for (int e = 0; e < NX * NZ; ++e) ABr[e] = AB[e];
+#pragma unroll
+    for (int e = 0; e < NU * NX; ++e) Kr[e] = Kk[e];
+#pragma unroll
+    for (int e = 0; e < NU * NU; ++e) Lr[e] = L[e];
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+      double fu[NU > 0 ? NU : 1], pn[NX];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) v += ABr[i * NZ + NX + a] * pv[c][i];
+        fu[a] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) v += ABr[i * NZ + j] * pv[c][i];
+#pragma unroll
+        for (int a = 0; a < NU; ++a) v += Kr[a * NX + j] * fu[a];
+        pn[j] = v;
+      }
+      double ku[NU > 0 ? NU : 1];
+#pragma unroll
+      for (int a = 0; a < NU; ++a) ku[a] = -fu[a];
+      tm_chol_small_solve(Lr, ku);
+      for (int a = lane; a < NU; a += TM_NL) s.kkm[((size_t)c * N + k) * NU + a] = ku[a];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) pv[c][j] = pn[j];
+    }
+  }
+  TM_SYNC();
+  double z[NX][NZ];
+#pragma unroll
+  for (int c = 0; c < NX; ++c)
+#pragma unroll
+    for (int b = 0; b < NZ; ++b) z[c][b] = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NU * NX;
+    double ABr[NX * NZ], Kr[NU * NX > 0 ? NU * NX : 1];
+#pragma unroll
+    for (int e = 0; e < NX * NZ; ++e) ABr[e] = AB[e];
+#pragma unroll
+    for (int e = 0; e < NU * NX; ++e) Kr[e] = Kk[e];
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+#pragma unroll
+      for (int a = 0; a < NU; ++a) {
+        double v = s.kkm[((size_t)c * N + k) * NU + a];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) v += Kr[a * NX + j] * z[c][j];
+        z[c][NX + a] = v;
+      }
+    }
+    for (int i = lane; i < nh; i += TM_NL) {
+      const double* Ci = P.C + (size_t)i * NZ;
+#pragma unroll
+      for (int c = 0; c < NX; ++c) {
+        double t = 0.0;
+#pragma unroll
+        for (int b = 0; b < NZ; ++b) t += Ci[b] * z[c][b];
+        if (c < nxt) Mc[(size_t)c * E + k * nh + i] = t;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+      double xn[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int b = 0; b < NZ; ++b) v += ABr[i * NZ + b] * z[c][b];
+        xn[i] = v;
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) z[c][i] = xn[i];
+    }
+  }
+  for (int t = lane; t < nxt; t += TM_NL) {
+    const int ti = P.term_idx[t];
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+      double v = 0.0;
+#pragma unroll
+      for (int a = 0; a < NX; ++a) if (a == ti) v = z[c][a];
+      if (c < nxt) Mc[(size_t)c * E + NI + t] = v;
+    }
+  }
   TM_SYNC();
 }
 
@@ -920,18 +1132,48 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   const int NI = N * nh, E = NI + nxt;
   for (int e = lane; e < E; e += TM_NL) s.sl[e] = (e < NI ? s.hv[e] : s.tr[e - NI]) + tm_erow_dot(P, e, s.d);
   TM_SYNC();
-  int m = 0, neq = 0, ret = 0;
+  int m = 0, ret = 0;
   int n_gi = 0, n_ricc = 0;
+  if (nxt > 0) {
+    // the terminal equality rows enter together: their columns from one multi-right-hand-side sweep, multipliers from
+    // the nxt x nxt Schur complement (the state the one-at-a-time iteration would reach; equality multipliers are
+    // sign-free and never dropped)
+    tm_ricc_cols_term(P, s, s.Mc, E);
+    n_ricc += 1;
+    if (lane == 0) {
+      for (int t = 0; t < nxt; ++t) { s.acte[t] = (double)(NI + t); s.acts[t] = 1.0; }
+      double ok = (double)tm_schur_refactor(s, nxt, M, E);
+      if (ok != 0.0) {
+        for (int i = 0; i < nxt; ++i) {          // L L' nu = -sl_term
+          double v = -s.sl[NI + i];
+          for (int l = 0; l < i; ++l) v -= s.Lf[i * M + l] * s.nu[l];
+          s.nu[i] = v / s.Lf[i * M + i];
+        }
+        for (int i = nxt - 1; i >= 0; --i) {
+          double v = s.nu[i];
+          for (int l = i + 1; l < nxt; ++l) v -= s.Lf[l * M + i] * s.nu[l];
+          s.nu[i] = v / s.Lf[i * M + i];
+        }
+      }
+      s.sc[1] = ok;
+    }
+    TM_SYNC();
+    if (s.sc[1] == 0.0) ret = 2;
+    else {
+      for (int e = lane; e < E; e += TM_NL) {
+        double acc = 0.0;
+        for (int t = 0; t < nxt; ++t) acc += s.nu[t] * s.Mc[(size_t)t * E + e];
+        s.sl[e] += acc;
+      }
+      m = nxt;
+      TM_SYNC();
+    }
+  }
   const int maxit = 4 * E + 8;
-  for (int it = 0; it < maxit; ++it) {
+  for (int it = 0; it < maxit && !ret; ++it) {
     int qe;
     double qs = 1.0, sval;
-    if (neq < nxt) {
-      qe = NI + neq;
-      const double v = s.sl[qe];
-      qs = (v > 0.0) ? -1.0 : 1.0;
-      sval = qs * v;
-    } else {
+    {
       double best = TM_INF;
       int bid = 0x7fffffff;
       for (int e = lane; e < NI; e += TM_NL) {
@@ -949,15 +1191,9 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
       sval = s.sl[qe];
     }
     if (m >= M) { ret = 2; break; }
-    for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.rhs[e] = 0.0;
-    TM_SYNC();
-    if (lane == 0) tm_erow_axpy(P, qe, -qs, s.rhs);
-    TM_SYNC();
-    tm_ricc_solve(P, s, s.rhs, s.y, qe < NI ? qe / nh : N);
-    ++n_gi; ++n_ricc;
     TmP mq = s.Mc + (size_t)m * E;            // candidate column, becomes member m when added
-    for (int e = lane; e < E; e += TM_NL) mq[e] = tm_erow_dot(P, e, s.y);
-    TM_SYNC();
+    tm_ricc_col(P, s, qe, qs, mq);
+    ++n_gi; ++n_ricc;
     const double yq = qs * mq[qe];
     double nq = 0.0;
     int added = 0;
@@ -1016,7 +1252,6 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
         }
         TM_SYNC();
         ++m;
-        if (qe >= NI) ++neq;
         added = 1;
         break;
       }
@@ -1055,6 +1290,7 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     }
   }
   if (lane == 0) {
+    S.qpwork[inst] = n_gi;
 #ifdef __CUDA_ARCH__
     atomicAdd(S.counters + 5, 1ull); atomicAdd(S.counters + 6, (unsigned long long)n_gi); atomicAdd(S.counters + 7, (unsigned long long)n_ricc);
 #else
@@ -1427,6 +1663,14 @@ TM_HD void tm_qp(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& ws) {
     }
   }
   int ret = tm_qp_solve(P, S, inst, ws, use_exact, nmask ? mask : nullptr, bad);
+  if (TM_LANE == 0) {   // attempt histogram: [8 + 4*(0 fresh | 1 mask retry | 2 Gauss-Newton) + (0 ok | 1 infeasible | 2 not PD | 3 mask rows inactive)]
+    const int hm = mode == 0 ? 0 : (mode < 100 ? 1 : 2), hr = ret == 0 ? 0 : (ret == 2 ? 1 : (ret == 3 ? 2 : 3));
+#ifdef __CUDA_ARCH__
+    atomicAdd(S.counters + 8 + 4 * hm + hr, 1ull);
+#else
+    S.counters[8 + 4 * hm + hr] += 1;
+#endif
+  }
   int next_mode = 0;
   if (ret == 5) next_mode = (mode + 1 >= 4) ? 100 : mode + 1;
   else if (ret == 3 && use_exact) next_mode = 100;
