@@ -48,7 +48,7 @@ def test_twin_cstr_golden(env):
     rp, build_tables, Twin = env
     pb, gold = load_problem("cstr"), load_golden("cstr")
     n = 48
-    tw = Twin(pb, build_tables(pb), rho=1e6, al_gamma=1e3)
+    tw = Twin(pb, build_tables(pb), rho=3e7, al_gamma=1e3)
     tw.reset(n)
     o = tw.step(gold["X0"][:n])
     assert (o["status"] == 0).all()
@@ -64,7 +64,7 @@ def test_twin_cstr_golden(env):
 def test_twin_shift_and_closed_loop(env):
     rp, build_tables, Twin = env
     pb, gold = load_problem("cstr"), load_golden("cstr")
-    tw = Twin(pb, build_tables(pb), rho=1e6, al_gamma=1e3)
+    tw = Twin(pb, build_tables(pb), rho=3e7, al_gamma=1e3)
     st = rp.StageLib("cstr")
     n = 2
     tw.reset(n)

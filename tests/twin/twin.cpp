@@ -5,6 +5,7 @@
 // without a GPU; on the GPU box the same comparison runs against the real kernels.
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 #include <vector>
 #include "tmpc_core.cuh"
 
@@ -98,6 +99,15 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
     }
     for (long long s = 0; s < nact; ++s) for (int k = 0; k < P.N; ++k) for (int pr = 0; pr < per; ++pr) tm_lin_task(P, S, (*cur)[s], k, pr, 1);
     for (long long s = 0; s < nact; ++s) tm_post(P, S, (*cur)[s]);
+    if (getenv("TWIN_TRACE")) {
+      for (long long s = 0; s < nact; ++s) {
+        const int i = (*cur)[s];
+        double dn = 0.0; for (int e = 0; e < P.n_w; ++e) dn = fmax(dn, fabs(D[(size_t)i * P.n_w + e]));
+        int nact_l = 0; for (int e = 0; e < P.N * P.nh; ++e) nact_l += tm_is_ineq_active(P, LAM + (size_t)i * P.n_g, e);
+        fprintf(stderr, "[twin] it %d inst %d flags %d qpstat %d |d| %.3e nAS %d f %.9e viol %.3e attempts %llu gn %llu\n", guard, i, flags[i], qpstat[i], dn, nact_l,
+                FILT[((size_t)i * P.filter_cap + nfilt[i] - 1) * 2], FILT[((size_t)i * P.filter_cap + nfilt[i] - 1) * 2 + 1], counters[5], counters[16]);
+      }
+    }
     nqp += nact; nlin += nact * P.N;
     const int nrel = cnts[1];
     for (int s = 0; s < nrel; ++s) for (int k = 0; k < P.N; ++k) for (int pr = 0; pr < per; ++pr) tm_lin_task(P, S, lrel[s], k, pr, 0);

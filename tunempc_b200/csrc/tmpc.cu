@@ -228,7 +228,7 @@ void tmpc_default_opts(tmpc_opts* o) {
   o->lam_tresh = 1e-8;
   o->ls_step_factor = 0.8;
   o->reg_tol = 1e-8;
-  o->term_penalty = 1e6;
+  o->term_penalty = 3e7;   // 1e7..1e8: below, marginally convex reduced Hessians fail the base factorisation; above, round-off (profiles/r01c_summary.md)
   o->al_gamma = 1e3;
 }
 
