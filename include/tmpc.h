@@ -11,6 +11,7 @@
  *   tmpc_reset                      Pmpc.reset / __set_initial_guess                          (tunempc/pmpc.py:858-865, 930-948)
  *   tmpc_step / tmpc_step_host      Pmpc.step -> Sqp.solve for B initial states at once       (tunempc/pmpc.py:371-423, tunempc/sqp_method.py:136-183)
  *   tmpc_plant_step                 F(x0=x, p=u)['xf'] in closed_loop_sim                     (tunempc/closed_loop_tools.py:102)
+ *   tmpc_stage_log                  cost(x,u), h(x,u) logged per closed-loop sample            (tunempc/closed_loop_tools.py:64-65, 98-99)
  *   tmpc_get_*                      Pmpc.w_sol / g_sol / log / index properties               (tunempc/pmpc.py:1120-1142, 785-831)
  *
  * Conventions: return 0 = success, non-zero = API error (message via tmpc_last_error); numerical failures never
@@ -88,6 +89,11 @@ int tmpc_step_host(tmpc_handle* h, const double* X0_host, int64_t B, double* U0_
 /* plant = model integrator: Xn_dev[b] = F(X_dev[b], U_dev[b])   (closed_loop_tools.py:102) */
 int tmpc_plant_step(tmpc_handle* h, const double* X_dev, const double* U_dev, int64_t B, double* Xn_dev,
                     void* cuda_stream);
+
+/* closed-loop log of one (x,u) sample per instance: l_dev[b] = l(x_b,u_b) (economic stage cost of the model card),
+ * h_dev[b*nh+i] = (C z_b + c)_i; either may be NULL   (closed_loop_tools.py:64-65, 98-99) */
+int tmpc_stage_log(tmpc_handle* h, const double* X_dev, const double* U_dev, int64_t B, double* l_dev, double* h_dev,
+                   void* cuda_stream);
 
 /* per-step log of the last tmpc_step, copied into caller buffers of B elements each (any may be NULL); the buffers are
  * host memory if dst_is_host != 0, else device memory on the handle's device:

@@ -33,11 +33,57 @@ def sample_x0(name, pb, B, seed=0):
         X0[:, 0] += alpha * (1.0 - xs[0])                       # dx_diehl direction, examples/cstr/main.py:126-131
         X0[:, 1:] += 1e-2 * np.abs(xs[1:]) * rng.uniform(-1, 1, (B, pb.nx - 1))
         return X0
+    if name == "unicycle":
+        return xs + np.array([0.5, 0.1, 0.0, 0.0]) * rng.uniform(-1, 1, (B, pb.nx))   # examples/unicycle/main.py:172
     raise KeyError(name)
+
+
+def unicycle():
+    """config #4: periodic reference (p = N = 30), projected terminal constraint, closed loop with plant = model."""
+    name = "unicycle"
+    st = rp.StageLib(name)
+    pb, info = configs.make_problem(name, st.F)
+    pb.save(os.path.join(HERE, "problem_%s.npz" % name))
+    B = 16
+    X0 = sample_x0(name, pb, B)
+    out = {"X0": X0}
+    for tag, tol in (("t6", 1e-6), ("t9", 1e-9)):
+        ctrl = rp.Pmpc(pb, qp="qpoases", sqp_options={"tol": tol})
+        U, W, LAM, IT, ST = [], [], [], [], []
+        for b in range(B):
+            ctrl.reset()
+            u = ctrl.step(X0[b])
+            U.append(u); W.append(ctrl.w_sol); LAM.append(ctrl.lam_g)
+            IT.append(ctrl.log["iter"][-1]); ST.append(ctrl.log["status"][-1])
+        out.update({"u0_" + tag: np.array(U), "w_" + tag: np.array(W), "lam_" + tag: np.array(LAM),
+                    "iter_" + tag: np.array(IT), "status_" + tag: np.array(ST)})
+        print(name, tag, "iter hist", np.bincount(np.array(IT)), "status", np.bincount(np.array(ST)))
+    # closed loop: 8 instances x 6 steps, and 2 instances x 36 steps (wraps the period: phase index 30 -> 0)
+    for key, nb, ns in (("cl", 8, 6), ("cll", 2, 36)):
+        ctrl = rp.Pmpc(pb, qp="qpoases")
+        Xcl, Ucl, Icl = [], [], []
+        for b in range(nb):
+            ctrl.reset()
+            x = X0[b].copy()
+            xs_, us_, it_ = [x.copy()], [], []
+            for _ in range(ns):
+                u = ctrl.step(x)
+                x = st.F(x[None, :], u[None, :])[0]
+                xs_.append(x.copy()); us_.append(u.copy()); it_.append(ctrl.log["iter"][-1])
+                assert ctrl.log["status"][-1] == 0
+            Xcl.append(xs_); Ucl.append(us_); Icl.append(it_)
+        out[key + "_X"] = np.array(Xcl)
+        out[key + "_U"] = np.array(Ucl)
+        out[key + "_iter"] = np.array(Icl)
+        print(name, key, "iter hist", np.bincount(np.array(Icl).ravel()))
+    np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % name), **out)
 
 
 def main():
     rp.build()
+    if len(sys.argv) > 1 and sys.argv[1] == "unicycle":
+        unicycle()
+        return
     for name, B in (("lq", 64), ("cstr", 48)):
         st = rp.StageLib(name)
         pb, info = configs.make_problem(name, st.F)
@@ -71,6 +117,7 @@ def main():
         out["cl_X"] = np.array(Xcl)
         out["cl_U"] = np.array(Ucl)
         np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % name), **out)
+    unicycle()
 
 
 if __name__ == "__main__":

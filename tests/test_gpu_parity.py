@@ -160,3 +160,65 @@ def test_large_batch_properties(torch_mod):
     idx = torch.arange(1000, 1000 + 512, device="cuda:0")
     U2 = c2.step(X0[idx].contiguous())
     assert torch.equal(U2, U[idx]) and torch.equal(c2.w_sol, w[idx])             # neighbours / sharding invariance
+
+
+def test_unicycle_periodic_golden_and_closed_loop(torch_mod):
+    """config #4 (examples/unicycle): p = N = 30 periodic reference with time-varying tuned H, projected terminal
+    constraint; open-loop golden outputs, then the closed loop across the period wrap with the device plant step."""
+    torch = torch_mod
+    ctrl, pb = _ctrl("unicycle")
+    gold = load_golden("unicycle")
+    U = ctrl.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
+    assert (ctrl.status.cpu().numpy() == 0).all()
+    assert np.array_equal(ctrl.log["iter"][-1].cpu().numpy(), gold["iter_t6"])
+    assert _relerr(U, gold["u0_t6"]) < 1e-6
+    assert _relerr(ctrl.w_sol.cpu().numpy(), gold["w_t6"]) < 1e-6
+    assert _relerr(ctrl.lam_g.cpu().numpy(), gold["lam_t6"]) < 1e-5
+    c9, _ = _ctrl("unicycle", tol=1e-9)
+    U9 = c9.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
+    assert _relerr(U9, gold["u0_t9"]) < 1e-8 and _relerr(c9.w_sol.cpu().numpy(), gold["w_t9"]) < 1e-8
+    ctrl.reset()
+    X = torch.tensor(gold["cll_X"][:, 0], device="cuda:0")
+    for s in range(36):
+        U = ctrl.step(X)
+        assert (ctrl.status.cpu().numpy() == 0).all(), s
+        assert _relerr(U.cpu().numpy(), gold["cll_U"][:, s]) < 1e-6, s
+        assert np.array_equal(ctrl.log["iter"][-1].cpu().numpy(), gold["cll_iter"][:, s]), s
+        X = ctrl.plant_step(X, U)
+        assert _relerr(X.cpu().numpy(), gold["cll_X"][:, s + 1]) < 1e-6, s
+    assert ctrl.index == 36
+
+
+def test_closed_loop_tools_batched(torch_mod):
+    """tunempc/closed_loop_tools.py drivers with the Python loops as the batch axis: closed_loop_sim on the periodic
+    unicycle against the oracle's rollouts, check_equivalence on the CSTR alpha sweep against single solves."""
+    torch = torch_mod
+    from tunempc_b200 import closed_loop_tools as clt
+    ctrl, pb = _ctrl("unicycle")
+    gold = load_golden("unicycle")
+    log = clt.closed_loop_sim({"TUNEMPC": ctrl}, None, None, None, gold["cl_X"][:, 0], 6)
+    X = torch.stack(log["x"]["TUNEMPC"], dim=1).cpu().numpy()
+    U = torch.stack(log["u"]["TUNEMPC"], dim=1).cpu().numpy()
+    assert _relerr(X, gold["cl_X"]) < 1e-6 and _relerr(U, gold["cl_U"]) < 1e-6
+    L = torch.stack(log["l"]["TUNEMPC"], dim=1).cpu().numpy()
+    z, y, u = gold["cl_X"][:, :6, 0], gold["cl_X"][:, :6, 1], gold["cl_U"][:, :, 0]
+    assert _relerr(L, u ** 2 + z ** 2 + 5 * y ** 2) < 1e-6                      # examples/unicycle/main.py:82
+    v = clt.reduce_rollout_stats(clt.rollout_stats(log, "TUNEMPC"))
+    assert v[0] == 8 and v[1] == 6 and v[4] == 0 and abs(v[2].item() - L.sum()) < 1e-9 * L.sum()
+    # alpha sweep (examples/cstr/main.py:124-134): every alpha is one instance of one batched step
+    c2, pb2 = _ctrl("cstr")
+    xs = pb2.wref[0, :4]
+    dx = np.array([1.0 - xs[0], 0.0, 0.0, 0.0])
+    alpha = np.linspace(-0.1, 1.0, 12)
+    lg = clt.check_equivalence({"TUNEMPC": c2}, None, None, xs, dx, alpha)
+    assert (lg["status"]["TUNEMPC"].cpu().numpy() == 0).all()
+    c3, _ = _ctrl("cstr")
+    for b in (0, 5, 11):
+        c3.reset()
+        u1 = c3.step(xs + alpha[b] * dx)
+        assert _relerr(lg["u"]["TUNEMPC"][b, 0].cpu().numpy(), u1) < 1e-12
+    hv = lg["h"]["TUNEMPC"].cpu().numpy()
+    assert np.allclose(hv, lg["u"]["TUNEMPC"][:, :, 0].cpu().numpy() - 5.0)      # first row of h: Vdot - 5 >= 0
+    cB, Vd, QK = lg["x"]["TUNEMPC"][:, :, 1].cpu().numpy(), lg["u"]["TUNEMPC"][:, :, 0].cpu().numpy(), lg["u"]["TUNEMPC"][:, :, 1].cpu().numpy()
+    lref = 100 * (-cB / 5.10 + 0.1 * (1e-4 * (Vd - 14.19) ** 2 + 1e-4 * (QK + 1113.5) ** 2))   # cstr_model.py:117-129
+    assert _relerr(lg["l"]["TUNEMPC"].cpu().numpy(), lref) < 1e-12

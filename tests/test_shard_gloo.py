@@ -35,3 +35,44 @@ def test_shard_and_reduce_world2(tmp_path):
     for r in range(world):
         got = np.load(os.path.join(str(tmp_path), "r%d.npy" % r))
         assert np.array_equal(got[:13], ref)          # reduction over shards == single-process statistics
+
+
+def _worker_cl(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from tunempc_b200.closed_loop_tools import reduce_rollout_stats, rollout_stats
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    log = _fake_log(rank)
+    v = reduce_rollout_stats(rollout_stats(log, "c", l_ref=np.arange(4.0)), dist)
+    np.save(os.path.join(out_dir, "cl%d.npy" % rank), v.numpy())
+    dist.destroy_process_group()
+
+
+def _fake_log(rank):
+    import torch
+    g = torch.Generator().manual_seed(rank)
+    B, N = 5 + rank, 4
+    return {"l": {"c": [torch.rand(B, dtype=torch.float64, generator=g) for _ in range(N)]},
+            "h": {"c": [torch.rand((B, 3), dtype=torch.float64, generator=g) - 0.1 * (rank + 1) for _ in range(N)]},
+            "status": {"c": [(torch.rand(B, generator=g) < 0.2).to(torch.int32) for _ in range(N)]}}
+
+
+def test_rollout_stats_reduce_world2(tmp_path):
+    """closed-loop statistics: the only collective of a sharded rollout (north_star: 'NCCL gather only for the
+    closed-loop statistics'); gloo stands in for NCCL on CPU."""
+    import torch
+    from tunempc_b200.closed_loop_tools import rollout_stats
+    world = 2
+    mp.spawn(_worker_cl, args=(world, 29541, str(tmp_path)), nprocs=world, join=True)
+    loc = [rollout_stats(_fake_log(r), "c", l_ref=np.arange(4.0)) for r in range(world)]
+    ref = loc[0] + loc[1]
+    ref[1] = max(loc[0][1], loc[1][1])
+    ref[5] = max(loc[0][5], loc[1][5])
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), "cl%d.npy" % r))
+        assert np.allclose(got, ref.numpy(), rtol=1e-14)
+    assert ref[0] == 11 and ref[1] == 4 and ref[5] > 0

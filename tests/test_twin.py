@@ -78,3 +78,29 @@ def test_twin_shift_and_closed_loop(env):
     oc = rp.Pmpc(pb)
     ws, ls = oc._shift(o["w"][0], o["lam"][0])
     assert np.array_equal(tw.W[0], ws) and np.array_equal(tw.LAM[0], ls)
+
+
+def test_twin_unicycle_periodic(env):
+    """config #4: periodic reference (p = N = 30, time-varying H), projected terminal constraint (nx_term = 3 < nx),
+    closed loop across the period wrap (phase index 30 -> 0) with the shifted warm start."""
+    rp, build_tables, Twin = env
+    pb, gold = load_problem("unicycle"), load_golden("unicycle")
+    assert pb.p == 30 and pb.nx_term == 3
+    tw = Twin(pb, build_tables(pb), rho=3e7, al_gamma=1e3)
+    tw.reset(16)
+    o = tw.step(gold["X0"])
+    assert (o["status"] == 0).all()
+    assert np.array_equal(o["iter"], gold["iter_t6"])                  # no inequality rows: same iteration path
+    assert _relerr(o["u0"], gold["u0_t6"]) < 1e-9
+    assert _relerr(o["w"], gold["w_t6"]) < 1e-9
+    assert _relerr(o["lam"], gold["lam_t6"]) < 1e-8
+    st = rp.StageLib("unicycle")
+    tw.reset(2)
+    x = gold["X0"][:2].copy()
+    for s in range(36):
+        o = tw.step(x)
+        assert (o["status"] == 0).all()
+        assert _relerr(o["u0"], gold["cll_U"][:2, s]) < 1e-8, s
+        assert np.array_equal(o["iter"], gold["cll_iter"][:2, s]), s
+        x = st.F(x, o["u0"])
+        assert _relerr(x, gold["cll_X"][:2, s + 1]) < 1e-8, s

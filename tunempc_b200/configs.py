@@ -26,7 +26,7 @@ def lq():
     xdot = list(sp.Matrix(A) * sp.Matrix(x) + sp.Matrix(B) * sp.Matrix(u))
     Hm = np.block([[Q, Nm], [Nm.T, R]])
     cost = sp.Rational(1, 2) * (z.T * sp.Matrix(Hm) * z)[0, 0]
-    model = OdeModel("lq", x, u, xdot, discrete=True)
+    model = OdeModel("lq", x, u, xdot, discrete=True, cost=cost)
     return dict(model=model, cost=cost, C=np.zeros((0, 4)), c=np.zeros(0),
                 w_guess=np.zeros(4), period=1, A=A, B=B, Q=Q, R=R, Nmat=Nm,
                 x0_scale=np.array([1.0, 1.0, 1.0]), N=10, term_idx=[0, 1, 2])
@@ -57,7 +57,7 @@ def cstr():
     C = np.zeros((4, 6))
     C[0, 4], C[1, 4], C[2, 5], C[3, 5] = 1.0, -1.0, 1.0, -1.0
     c = np.array([-5.0, 35.0, 9000.0, 0.0])
-    model = OdeModel("cstr", (cA, cB, th, thK), (Vd, QK), xdot, rk_steps=20, tf=20.0)   # :62-64,97
+    model = OdeModel("cstr", (cA, cB, th, thK), (Vd, QK), xdot, rk_steps=20, tf=20.0, cost=cost)   # :62-64,97
     w_guess = np.array([2.1402, 1.0903, 114.191, 112.9066, 14.19, -1113.5])               # :168
     return dict(model=model, cost=cost, C=C, c=c, w_guess=w_guess, period=1, N=20,
                 term_idx=[0, 1, 2, 3])
@@ -76,14 +76,20 @@ def unicycle():
         uu * ez - rho_ * ey * (ez ** 2 + ey ** 2 - 1),
     ]
     cost = uu ** 2 + z_ ** 2 + 5 * y_ ** 2                # :82
-    model = OdeModel("unicycle", (z_, y_, ez, ey), (uu,), xdot, rk_steps=50, tf=T / Np)  # :67
+    model = OdeModel("unicycle", (z_, y_, ez, ey), (uu,), xdot, rk_steps=50, tf=T / Np, cost=cost)  # :67
     # analytic circular initial guess (:103-114)
     om = 2 * np.pi / T
     tg = np.arange(Np) * T / Np
     guess = np.stack([np.sin(om * tg) / om, -np.cos(om * tg) / om, np.cos(om * tg), np.sin(om * tg),
                       om * np.ones(Np)], axis=1)
+    # terminal projection (examples/unicycle/main.py:124-129 selects x[0:3] = (z, y, ez)).  The OCP solution computed by
+    # tuning.solve_periodic_ocp keeps the phase of the initial guess (ez = +-1, ey = 0 at k = 0, 15); there ez is the
+    # radial direction of the invariant ez^2 + ey^2 = 1, which the input cannot move, so the reference's selection makes
+    # the terminal constraint locally redundant and the SQP breaks down at those phases (the reference example runs with
+    # ipopt_presolve=True, pmpc.py:394-404, unavailable here).  (z, y, ey) is the same projection a quarter turn away
+    # and is well posed at every phase of this grid.
     return dict(model=model, cost=cost, C=np.zeros((0, 5)), c=np.zeros(0), w_guess=guess, period=Np, N=Np,
-                term_idx=[0, 1, 2])
+                term_idx=[0, 1, 3], x0_scale=np.array([0.5, 0.1, 0.0, 0.0]))                       # :172 disturbance sizes
 
 
 CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle}
@@ -103,9 +109,24 @@ def make_problem(name, stage_F, N=None, hessian_approximation="exact"):
     model = cfg["model"]
     nx, nu = model.nx, model.nu
     N = cfg["N"] if N is None else N
-    if cfg["period"] != 1:
-        raise NotImplementedError("periodic OCP tuning (p > 1) is not built yet")
     cost_funs = tuning.lambdify_cost(model, cfg["cost"])
+    if cfg["period"] != 1:
+        # periodic pipeline: Tuner(f, l, p=P).solve_ocp(w0); convexify(); create_mpc('tuned', N, opts={'p_operator': ...})
+        # (examples/unicycle/main.py:95-142)
+        if cfg["C"].shape[0]:
+            raise NotImplementedError("periodic OCP with path constraints is not built yet")
+        P = cfg["period"]
+        z, lam_d, _ = tuning.solve_periodic_ocp(stage_F, cost_funs, cfg["w_guess"], nx)
+        S = tuning.sensitivities_periodic(stage_F, cost_funs, z, lam_d, nx)
+        Hc = tuning.convexify_periodic(S["A"], S["B"], S["H"])
+        pb = MpcProblem(name=name, nx=nx, nu=nu, N=N, p=P, wref=z.copy(), H=np.array(Hc), q=np.array(S["q"]),
+                        C=cfg["C"], c=cfg["c"], lam_h_ref=np.zeros((P, 0)), lam_dyn_ref=np.zeros((P, nx)),
+                        term_idx=list(cfg["term_idx"]), S_A=np.array(S["A"]), S_B=np.array(S["B"]),
+                        hessian_approximation=hessian_approximation)
+        info = {"z_ocp": z, "lam_dyn_ocp": lam_d, "H_ocp": S["H"], "Hc": Hc, "cfg": cfg,
+                "eig_H": np.array([np.linalg.eigvalsh(h) for h in S["H"]]),
+                "eig_Hc": np.array([np.linalg.eigvalsh(h) for h in Hc])}
+        return pb, info
     z, lam_d, lam_h = tuning.solve_steady_state(stage_F, cost_funs, cfg["C"], cfg["c"], cfg["w_guess"], nx)
     S = tuning.sensitivities(stage_F, cost_funs, cfg["C"], z, lam_d, lam_h, nx)
     Hc, dH = tuning.convexify_dare(S["A"][0], S["B"][0], S["H"][0], C_As=S["C_As"][0], scale=z)

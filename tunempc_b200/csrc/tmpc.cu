@@ -154,6 +154,28 @@ __global__ void k_plant(const double* X, const double* U, int64_t B, double* Xn)
   for (int a = 0; a < NX; ++a) Xn[b * NX + a] = xf[a];
 }
 
+// closed-loop log of one (x,u) sample per instance: economic stage cost l(x,u) and the path constraint values h = C z + c
+// (tunempc/closed_loop_tools.py:64-65, 98-99)
+__global__ void k_stage_log(const double* X, const double* U, int64_t B, const double* C, const double* c, int nh,
+                            double* l_out, double* h_out) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double z[NZ];
+#pragma unroll
+  for (int a = 0; a < NX; ++a) z[a] = X[b * NX + a];
+#pragma unroll
+  for (int a = 0; a < NU; ++a) z[NX + a] = U[b * NU + a];
+  if (l_out) l_out[b] = tmpc_stage_cost(z, z + NX);
+  if (h_out) {
+    for (int i = 0; i < nh; ++i) {
+      double v = c[i];
+#pragma unroll
+      for (int j = 0; j < NZ; ++j) v += C[(size_t)i * NZ + j] * z[j];
+      h_out[b * nh + i] = v;
+    }
+  }
+}
+
 // ---- scheduling: counting sort of the active list by the cost of each instance's previous QP (heaviest first) -------
 // Results do not depend on the order (instances are independent); the order only decides which instances share a warp
 // of the thread-per-instance QP kernel, i.e. how long lanes idle while the longest active-set loop of the warp finishes.
@@ -619,6 +641,17 @@ int tmpc_plant_step(tmpc_handle* h, const double* X_dev, const double* U_dev, in
   if (!h) return 1;
   cudaSetDevice(h->device);
   k_plant<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(X_dev, U_dev, B, Xn_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int tmpc_stage_log(tmpc_handle* h, const double* X_dev, const double* U_dev, int64_t B, double* l_dev, double* h_dev,
+                   void* cuda_stream) {
+  if (!h) return 1;
+  if (!h->tables_set) { h->err = "tmpc_stage_log: tables not set"; return 1; }
+  cudaSetDevice(h->device);
+  k_stage_log<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(X_dev, U_dev, B, h->P.C, h->P.c, h->P.nh,
+                                                                                 l_dev, h->P.nh > 0 ? h_dev : nullptr);
   CK(cudaGetLastError());
   return 0;
 }

@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-std=c++17"]
 
 EXPORTS = ["tmpc_default_opts", "tmpc_model_info", "tmpc_create", "tmpc_destroy", "tmpc_last_error",
-           "tmpc_set_tables", "tmpc_reset", "tmpc_get_index", "tmpc_step", "tmpc_step_host", "tmpc_plant_step",
+           "tmpc_set_tables", "tmpc_reset", "tmpc_get_index", "tmpc_step", "tmpc_step_host", "tmpc_plant_step", "tmpc_stage_log",
            "tmpc_get_log", "tmpc_get_counters", "tmpc_get_timing", "tmpc_stage_eval_host", "tmpc_fp64_peak"]
 
 
@@ -81,6 +81,7 @@ class ModelLib:
         L.tmpc_step.argtypes = [vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
         L.tmpc_step_host.argtypes = [vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp]
         L.tmpc_plant_step.argtypes = [vp, vp, vp, ctypes.c_int64, vp, vp]
+        L.tmpc_stage_log.argtypes = [vp, vp, vp, ctypes.c_int64, vp, vp, vp]
         L.tmpc_get_log.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int]
         L.tmpc_get_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
         L.tmpc_get_timing.argtypes = [vp, _dp]

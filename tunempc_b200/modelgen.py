@@ -12,6 +12,7 @@ Emitted symbols (all `TMPC_HD static inline`, TMPC_HD = `__host__ __device__` un
   tmpc_ode_jac(x,u,f,J)               J row-major [NX][NZ], NZ = NX+NU
   tmpc_ode_d2(x,u,f,J,H)              H[TMPC_NHESS] structurally non-zero d2 f_a / dz_b dz_c, b<=c
   tmpc_ode_bilin(H,v,w,out)           out[a] = sum_bc H_abc v_b w_c   (straight-line over the non-zeros)
+  tmpc_stage_cost(x,u)                economic stage cost l(x,u) of the model card (closed-loop log only)
 plus the integrator spec (RK4 step count and step length) and op counts for the roofline.
 """
 from __future__ import annotations
@@ -55,6 +56,7 @@ class OdeModel:
     tf: float = 1.0          # integrator horizon (one MPC interval)
     discrete: bool = False   # True: xdot IS the map x+ = f(x,u) (no integrator)
     hess_nz: List[tuple] = field(default_factory=list)
+    cost: object = None      # economic stage cost l(x,u) (sympy), emitted as tmpc_stage_cost for the closed-loop log
 
     @property
     def nx(self):
@@ -279,6 +281,15 @@ def generate_header(model: OdeModel, out_path: str) -> dict:
     for a in range(nx):
         terms = ["G[%d]*w[%d]" % (gi, c) for (aa, c), gi in gpos.items() if aa == a]
         L.append("  out[%d] = %s;" % (a, " + ".join(terms) if terms else "0.0"))
+    L.append("}")
+    # economic stage cost l(x,u): logged along closed-loop runs (tunempc/closed_loop_tools.py:64,98)
+    L.append("#define TMPC_HAS_COST %d" % (1 if model.cost is not None else 0))
+    L.append("TMPC_HD double tmpc_stage_cost(const double* x, const double* u) {")
+    L.append("  (void)x; (void)u;")
+    L.append("  double l = 0.0;")
+    if model.cost is not None:
+        _emit_block(L, None, [("l", S(model.cost))])
+    L.append("  return l;")
     L.append("}")
     c_B = sum(3 if b == c else 5 for _, b, c, _ in hess)
     L.append("#define TMPC_OPS_F %d\n#define TMPC_OPS_J %d\n#define TMPC_OPS_H %d\n#define TMPC_OPS_BILIN %d" % (c_f, c_J, c_H, c_B))

@@ -223,6 +223,20 @@ class Pmpc:
                                                     X.shape[0], ctypes.c_void_p(Xn.data_ptr()), stream))
         return Xn
 
+    def stage_log(self, X, U):
+        """l(x,u) and h(x,u) = C z + c for every row (closed_loop_tools.py:64-65, 98-99): torch CUDA tensors in,
+        (l (B,), h (B,nh)) out."""
+        import torch
+        X = X.contiguous()
+        U = U.contiguous()
+        B = X.shape[0]
+        l = torch.empty(B, dtype=torch.float64, device=X.device)
+        hv = torch.empty((B, self.__pb.nh), dtype=torch.float64, device=X.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)
+        self.__check(self.__lib.lib.tmpc_stage_log(self.__h, ctypes.c_void_p(X.data_ptr()), ctypes.c_void_p(U.data_ptr()), B,
+                                                   ctypes.c_void_p(l.data_ptr()), ctypes.c_void_p(hv.data_ptr()), stream))
+        return l, hv
+
     def counters(self):
         out = (ctypes.c_int64 * 8)()
         self.__check(self.__lib.lib.tmpc_get_counters(self.__h, out))
@@ -275,6 +289,10 @@ class Pmpc:
     @property
     def options(self):
         return dict(self.__options)
+
+    @property
+    def device(self):
+        return self.__device
 
     @property
     def library_path(self):
