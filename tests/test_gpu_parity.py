@@ -48,9 +48,11 @@ def test_lq_golden(torch_mod):
     assert np.allclose(U.cpu().numpy()[:, 0], gold["X0"] @ G, atol=1e-9)
 
 
-@pytest.mark.parametrize("tag,tol", [("t6", 1e-6), ("t9", 1e-9)])
-def test_cstr_golden(torch_mod, tag, tol):
+@pytest.mark.parametrize("tag,tol,q0min", [("t6", 1e-6, None), ("t9", 1e-9, None), ("t6", 1e-6, 2), ("t9", 1e-9, 2)])
+def test_cstr_golden(torch_mod, tag, tol, q0min, monkeypatch):
     torch = torch_mod
+    if q0min is not None:
+        monkeypatch.setenv("TMPC_QP0_MIN", str(q0min))   # first QP through the shared tables (k_qp0) even at B = 48
     ctrl, pb = _ctrl("cstr", tol=tol)
     gold = load_golden("cstr")
     U = ctrl.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
@@ -157,9 +159,16 @@ def test_large_batch_properties(torch_mod):
         assert lh.max().item() <= 0.0                                            # multiplier sign
         assert (lh * g[ok][:, pb.g_h(k)]).abs().max().item() < 1e-4              # complementarity
     c2, _ = _ctrl("cstr")
-    idx = torch.arange(1000, 1000 + 512, device="cuda:0")
+    idx = torch.arange(1000, 1000 + 2048, device="cuda:0")
     U2 = c2.step(X0[idx].contiguous())
     assert torch.equal(U2, U[idx]) and torch.equal(c2.w_sol, w[idx])             # neighbours / sharding invariance
+    # a batch below TMPC_QP0_MIN takes the per-instance route for its first QP instead of the shared tables:
+    # same answers to round-off
+    c3, _ = _ctrl("cstr")
+    idx = torch.arange(5000, 5000 + 512, device="cuda:0")
+    U3 = c3.step(X0[idx].contiguous()).cpu().numpy()
+    ok3 = (c3.status.cpu().numpy() == 0) & (st[5000:5512] == 0)
+    assert _relerr(U3[ok3], U[idx].cpu().numpy()[ok3]) < 1e-6
 
 
 def test_unicycle_periodic_golden_and_closed_loop(torch_mod):

@@ -104,3 +104,34 @@ def test_twin_unicycle_periodic(env):
         assert np.array_equal(o["iter"], gold["cll_iter"][:2, s]), s
         x = st.F(x, o["u0"])
         assert _relerr(x, gold["cll_X"][:2, s + 1]) < 1e-8, s
+
+
+def test_twin_shared_first_qp(env):
+    """first QP after reset(): the table route (tm_qp0_*: one tabulated parametric QP, working-set iteration per
+    instance) against the per-instance Riccati + dual active-set route, and against the oracle's golden answers."""
+    rp, build_tables, Twin = env
+    pb, gold = load_problem("cstr"), load_golden("cstr")
+    n = 48
+    tw = Twin(pb, build_tables(pb), rho=3e7, al_gamma=1e3)
+    tw.reset(n)
+    a = tw.step(gold["X0"][:n])
+    tw.reset(n)
+    b = tw.step(gold["X0"][:n], shared_first_qp=True)
+    assert (b["status"] == 0).all() and np.array_equal(a["iter"], b["iter"]) and np.array_equal(a["nAS"], b["nAS"])
+    assert b["counters"][7] < a["counters"][7]                            # fewer Riccati sweeps
+    assert _relerr(a["u0"], b["u0"]) < 1e-9 and _relerr(a["w"], b["w"]) < 1e-9
+    assert _relerr(b["u0"], gold["u0_t6"][:n]) < 1e-6
+    for i in range(n):
+        assert set(np.nonzero(b["lam"][i])[0]) == set(np.nonzero(gold["lam_t6"][i])[0])
+    # the QP itself: stop after one SQP iteration and compare step and multipliers of the two routes
+    pb1 = load_problem("cstr")
+    pb1.max_iter = 1
+    t1 = Twin(pb1, build_tables(pb1), rho=3e7, al_gamma=1e3)
+    t1.reset(n)
+    a1 = t1.step(gold["X0"][:n])
+    t1.reset(n)
+    b1 = t1.step(gold["X0"][:n], shared_first_qp=True)
+    assert np.array_equal(a1["nAS"], b1["nAS"])
+    assert _relerr(a1["w"], b1["w"]) < 1e-9 and _relerr(a1["lam"], b1["lam"]) < 1e-6
+    for i in range(n):
+        assert set(np.nonzero(a1["lam"][i])[0]) == set(np.nonzero(b1["lam"][i])[0])     # exact zeros off the working set

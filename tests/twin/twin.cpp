@@ -46,7 +46,7 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
               const double* q, const double* ref_du, const double* C, const double* c, const int* term_idx,
               const int* relax0, int phase, long long B, const double* X0, double* W, double* LAM, double* G,
               int* status, int* iter, int* flags, double* fval, int* nAS, int* nACtot, int* nAC, double* Wsh,
-              double* Lsh, long long* counters_out) {
+              double* Lsh, long long* counters_out, int uniform) {
   TmProb P;
   P.N = dims[0]; P.nh = dims[1]; P.nxt = dims[2]; P.p = dims[3];
   P.n_w = P.N * NZ + NX;
@@ -91,6 +91,38 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
     S.list_next = nxt->data();
     cnts[0] = cnts[1] = 0;
     cnt_retry = 0;
+    if (guard == 0 && uniform && P.nh > 0) {
+      // first QP after reset: the shared-table route of the CUDA host loop (k_qp0_build / k_qp0_derive / k_qp0)
+      TmQp0Tab T;
+      T.EI = P.N * P.nh; T.EIs = T.EI | 1; T.n_out = P.n_w + P.n_g; T.nT = 1 + NX + T.EI;
+      std::vector<double> TAB((size_t)T.nT * T.n_out), SL0(T.EI), SLPHI((size_t)NX * T.EI), MCOL((size_t)T.EI * T.EIs, 0.0);
+      int bad = 0;
+      T.TAB = TAB.data(); T.SL0 = SL0.data(); T.SLPHI = SLPHI.data(); T.MCOL = MCOL.data(); T.bad = &bad;
+      for (int t = 0; t < T.nT; ++t) tm_qp0_build_row(P, S, 0, ws, T, t);
+      for (int t = 0; t < T.nT; ++t) for (int e = 0; e < T.EI; ++e) tm_qp0_derive(P, S, 0, T, t, e);
+      if (getenv("TWIN_DUMP")) {
+        FILE* f = fopen(getenv("TWIN_DUMP"), "wb");
+        int hdr[4] = {T.EI, T.EIs, T.n_out, T.nT};
+        fwrite(hdr, sizeof(int), 4, f);
+        fwrite(TAB.data(), sizeof(double), TAB.size(), f); fwrite(SL0.data(), sizeof(double), SL0.size(), f);
+        fwrite(SLPHI.data(), sizeof(double), SLPHI.size(), f); fwrite(MCOL.data(), sizeof(double), MCOL.size(), f);
+        fclose(f);
+      }
+      for (long long s = 0; s < nact; ++s) {
+        const long long i = (*cur)[s];
+        if (bad) { tm_qp0_finish(P, S, i, 2, 0); continue; }
+        double e0[NX], nu[TM_Q0_MAXM];
+        int acte[TM_Q0_MAXM], m = 0, ngi = 0;
+        for (int a = 0; a < NX; ++a) e0[a] = X0[i * NX + a] - W[i * P.n_w + a];
+        const int ret = tm_qp0_gi(P, T, e0, acte, nu, m, ngi);
+        tm_qp0_finish(P, S, i, ret, ngi);
+        if (ret) continue;
+        for (int o = 0; o < T.n_out; ++o) {
+          const double v = tm_qp0_combine(T, o, e0, acte, nu, m);
+          if (o < P.n_w) D[(size_t)i * P.n_w + o] = v; else LQ[(size_t)i * P.n_g + o - P.n_w] = v;
+        }
+      }
+    } else
     for (long long s = 0; s < nact; ++s) tm_qp(P, S, (*cur)[s], ws);
     for (int pass = 0; pass < 5 && cnt_retry > 0; ++pass) {      // re-solves (mask shrink / Gauss-Newton fallback)
       std::vector<int> todo(lretry.begin(), lretry.begin() + cnt_retry);

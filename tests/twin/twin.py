@@ -53,7 +53,7 @@ class Twin:
         self.lib.twin_stage_eval(n, _p(x), _p(u), order, _p(xf), _p(S), _p(T))
         return (xf, S, T)[: order + 1] if order else xf
 
-    def step(self, X0, hessian=None, tol=None):
+    def step(self, X0, hessian=None, tol=None, shared_first_qp=False):
         pb = self.pb
         X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, pb.nx)
         B = X0.shape[0]
@@ -78,7 +78,8 @@ class Twin:
         ret = self.lib.twin_step(_i(dims), _i(iopts), _p(dopts), _p(wref), _p(Hs), _p(q), _p(rdu), _p(C), _p(c),
                                  _i(tidx), _i(relax0), ctypes.c_int(self.index % pb.p), ctypes.c_longlong(B), _p(X0),
                                  _p(self.W), _p(self.LAM), _p(G), _i(st), _i(it), _i(fl), _p(fv), _i(nAS), _i(nACt),
-                                 _i(nAC), _p(Wsh), _p(Lsh), cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+                                 _i(nAC), _p(Wsh), _p(Lsh), cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
+                                 ctypes.c_int(1 if (shared_first_qp and self.index == 0) else 0))
         if ret:
             raise RuntimeError("twin_step returned %d" % ret)
         out = dict(w=self.W.copy(), lam=self.LAM.copy(), g=G, status=st, iter=it, flags=fl, f=fv, nAS=nAS,

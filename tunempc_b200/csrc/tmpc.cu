@@ -61,6 +61,10 @@ struct tmpc_handle {
   double* qp_ws = nullptr;     // its workspace
   size_t qp_ws_per_inst = 0;
   int* qp_counter = nullptr;
+  TmQp0Tab q0{};               // tables of the shared first QP after reset (tm_qp0_*)
+  bool q0_ok = false;          // allocated and applicable (nh > 0, smem fits)
+  int64_t q0_min = 1024;       // smallest batch for which tabulating (1 + nx + N*nh warp-level QP solves) pays off
+  std::vector<char> phase_clean;   // per phase: no reference multiplier on an inequality row (empty convexification mask)
 };
 
 static int fail(tmpc_handle* h, const char* what, cudaError_t e) {
@@ -108,6 +112,90 @@ __global__ void __launch_bounds__(QP_WARPS * 32) k_qp(TmProb P, TmState S, const
   TmQpWs ws;
   tm_qpws_carve(smem + (size_t)wid * per, P.N, P.nh, P.nxt, P.maxact, ws);
   tm_qp(P, S, inst, ws);
+}
+
+// ---- first QP after reset(): tabulate the shared parametric QP, then one thread per instance on the tables ----------
+__global__ void __launch_bounds__(QP_WARPS * 32) k_qp0_build(TmProb P, TmState S, TmQp0Tab T) {
+  extern __shared__ double smem[];
+  const int wid = threadIdx.x / 32;
+  const int t = blockIdx.x * QP_WARPS + wid;
+  if (t >= T.nT) return;
+  const size_t per = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact);
+  TmQpWs ws;
+  tm_qpws_carve(smem + (size_t)wid * per, P.N, P.nh, P.nxt, P.maxact, ws);
+  tm_qp0_build_row(P, S, 0, ws, T, t);
+}
+
+__global__ void k_qp0_derive(TmProb P, TmState S, TmQp0Tab T) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T.nT * T.EI) return;
+  tm_qp0_derive(P, S, 0, T, idx / T.EI, idx % T.EI);
+}
+
+#define Q0_THREADS 128
+#define Q0_CH 8            /* outputs per lane per chunk of the table combination */
+__global__ void __launch_bounds__(Q0_THREADS) k_qp0(TmProb P, TmState S, TmQp0Tab T, int cnt) {
+  const int64_t inst = (int64_t)blockIdx.x * Q0_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool valid = inst < cnt;
+  if (*T.bad) {                                   // tabulation failed: everybody takes the generic path
+    if (valid) tm_qp0_finish(P, S, inst, 2, 0);
+    return;
+  }
+  double e0[NX], nu[TM_Q0_MAXM];
+  int acte[TM_Q0_MAXM];
+  int m = 0, ngi = 0, ret = 2;
+  if (valid) {
+#pragma unroll
+    for (int a = 0; a < NX; ++a) e0[a] = S.X0[inst * NX + a] - S.W[inst * P.n_w + a];
+    ret = tm_qp0_gi(P, T, e0, acte, nu, m, ngi);
+    tm_qp0_finish(P, S, inst, ret, ngi);
+  } else {
+#pragma unroll
+    for (int a = 0; a < NX; ++a) e0[a] = 0.0;
+  }
+  // (d, lam) of the warp's 32 instances, one after the other, lanes across the n_w + n_g outputs (coalesced)
+  const int n_out = T.n_out;
+  for (int src = 0; src < 32; ++src) {
+    const int r = __shfl_sync(0xffffffffu, ret, src);
+    if (r != 0) continue;
+    const int mm = __shfl_sync(0xffffffffu, m, src);
+    const long long is = __shfl_sync(0xffffffffu, (long long)inst, src);
+    double es[NX];
+#pragma unroll
+    for (int a = 0; a < NX; ++a) es[a] = __shfl_sync(0xffffffffu, e0[a], src);
+    double* dout = S.D + is * P.n_w;
+    double* lout = S.LAMQ + is * P.n_g;
+    for (int base = 0; base < n_out; base += 32 * Q0_CH) {
+      double acc[Q0_CH];
+#pragma unroll
+      for (int q = 0; q < Q0_CH; ++q) {
+        const int i = base + q * 32 + lane;
+        double v = 0.0;
+        if (i < n_out) {
+          v = T.TAB[i];
+#pragma unroll
+          for (int a = 0; a < NX; ++a) v += es[a] * T.TAB[(size_t)(1 + a) * n_out + i];
+        }
+        acc[q] = v;
+      }
+      for (int j = 0; j < mm; ++j) {
+        const int aj = __shfl_sync(0xffffffffu, acte[j], src);
+        const double nj = __shfl_sync(0xffffffffu, nu[j], src);
+        const double* row = T.TAB + (size_t)(1 + NX + aj) * n_out;
+#pragma unroll
+        for (int q = 0; q < Q0_CH; ++q) {
+          const int i = base + q * 32 + lane;
+          if (i < n_out) acc[q] += nj * row[i];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < Q0_CH; ++q) {
+        const int i = base + q * 32 + lane;
+        if (i < n_out) { if (i < P.n_w) dout[i] = acc[q]; else lout[i - P.n_w] = acc[q]; }
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(QP_WARPS * 32) k_post(TmProb P, TmState S, const int* list, int cnt) {
@@ -346,6 +434,20 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
       }
     }
   }
+  if (P.nh > 0) {
+    TmQp0Tab& T = h->q0;
+    T.EI = P.N * P.nh; T.EIs = T.EI | 1; T.n_out = P.n_w + P.n_g; T.nT = 1 + NX + T.EI;
+    const char* qm = getenv("TMPC_QP0_MIN");
+    if (qm) h->q0_min = atoll(qm);
+    if (cudaMalloc(&T.TAB, (size_t)T.nT * T.n_out * sizeof(double)) == cudaSuccess &&
+        cudaMalloc(&T.SL0, (size_t)T.EI * sizeof(double)) == cudaSuccess &&
+        cudaMalloc(&T.SLPHI, (size_t)NX * T.EI * sizeof(double)) == cudaSuccess &&
+        cudaMalloc(&T.MCOL, (size_t)T.EI * T.EIs * sizeof(double)) == cudaSuccess &&
+        cudaMalloc(&T.bad, sizeof(int)) == cudaSuccess &&
+        cudaFuncSetAttribute(k_qp0_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem) == cudaSuccess)
+      h->q0_ok = h->q0_min >= 0;
+    cudaMemset(T.MCOL, 0, (size_t)T.EI * T.EIs * sizeof(double));
+  }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
   h->ev_ok = true;
   *out = h;
@@ -364,6 +466,11 @@ void tmpc_destroy(tmpc_handle* h) {
   free_list(h->ws_allocs);
   if (h->qp_ws) cudaFree(h->qp_ws);
   if (h->qp_counter) cudaFree(h->qp_counter);
+  if (h->q0.TAB) cudaFree(h->q0.TAB);
+  if (h->q0.SL0) cudaFree(h->q0.SL0);
+  if (h->q0.SLPHI) cudaFree(h->q0.SLPHI);
+  if (h->q0.MCOL) cudaFree(h->q0.MCOL);
+  if (h->q0.bad) cudaFree(h->q0.bad);
   if (h->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
   delete h;
 }
@@ -400,6 +507,13 @@ int tmpc_set_tables(tmpc_handle* h, const double* wref, const double* H, const d
   if (upload(h, h->tab_allocs, c, (size_t)P.nh, &P.c)) return 1;
   if (upload(h, h->tab_allocs, (const int*)term_idx, (size_t)P.nxt, &P.term_idx)) return 1;
   if (upload(h, h->tab_allocs, (const int*)relax0, (size_t)P.nh, &P.relax0)) return 1;
+  h->phase_clean.assign(P.p, 1);
+  for (int ph = 0; ph < P.p; ++ph)
+    for (int k = 0; k < P.N; ++k)
+      for (int i = 0; i < P.nh; ++i) {
+        if (k == 0 && relax0[i]) continue;
+        if (fabs(ref_du[(size_t)ph * P.n_g + NX + (size_t)k * (NX + P.nh) + NX + i]) >= h->opts.lam_tresh) h->phase_clean[ph] = 0;
+      }
   h->tables_set = true;
   return 0;
 }
@@ -536,7 +650,15 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
       S.cnt_retry = h->cnts + 2 + (pass & 1);
       if (pass >= 2) CK(cudaMemsetAsync(S.cnt_retry, 0, sizeof(int), st));
       const bool use_thread = h->qp_mode == 1 || (h->qp_mode == 2 && nact >= (pass == 0 ? h->qp_thread_min : 8 * (int64_t)h->qp_thread_min));
-      if (use_thread)
+      if (pass == 0 && iter_guard == 0 && was_uniform && h->q0_ok && B >= h->q0_min && B > 1 && h->phase_clean[S.phase]) {
+        // every instance shares (w0, lam0): tabulate the parametric QP once, then one thread per instance on the tables
+        const TmQp0Tab& T = h->q0;
+        CK(cudaMemsetAsync(T.bad, 0, sizeof(int), st));
+        k_qp0_build<<<(T.nT + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, h->qp_smem, st>>>(P, S, T);
+        k_qp0_derive<<<(T.nT * T.EI + 127) / 128, 128, 0, st>>>(P, S, T);
+        k_qp0<<<(unsigned)((B + Q0_THREADS - 1) / Q0_THREADS), Q0_THREADS, 0, st>>>(P, S, T, (int)B);
+        launches += 2;
+      } else if (use_thread)
         CK(tm_launch_qp_thread(P, S, plist, (int)nact, pcnt, h->qp_ws, h->qp_ws_per_inst, h->qp_blocks, h->qp_counter, st));
       else
         k_qp<<<wb, QP_WARPS * 32, h->qp_smem, st>>>(P, S, plist, (int)nact, pcnt);

@@ -927,8 +927,18 @@ TM_HD int tm_schur_refactor(TmQpWs& s, int m, int M, int E) {
 // up in the working set; rows that do not are reported in al_bad (caller removes them and re-solves).  This makes the
 // base factorisation positive definite on the null space of (dynamics + warm-start active rows) -- the space on which
 // the reference tests and regularises its reduced Hessian (sqp_method.py:335-347) -- instead of dynamics only.
+// Perturbed solve used to tabulate the solution map of the first QP after reset() (tm_qp0_*, below): the equality-
+// constrained part of the QP (dynamics, x_0, terminal rows; inequality rows ignored) is solved for modified data and
+// the result goes to (dout, lout) instead of the instance's D / LAMQ.
+struct TmQpPert {
+  int homog;      // 1: zero all offsets (gradient r, dynamics defect b, terminal residual): pure linear response; the x_0 offset is always zeroed
+  int e0_unit;    // >= 0: x_0 offset = unit vector e0_unit
+  int row;        // >= 0: gradient -= n_row (response to a unit multiplier on inequality row `row` = k*nh + i)
+  double *dout, *lout;
+};
+
 TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& s, int use_exact,
-                       const unsigned* al_mask, unsigned* al_bad) {
+                       const unsigned* al_mask, unsigned* al_bad, const TmQpPert* pert = nullptr) {
   const int N = P.N, nh = P.nh, nxt = P.nxt, M = P.maxact;
   const int lane = TM_LANE;
   const double* w = S.W + inst * P.n_w;
@@ -968,6 +978,21 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     for (int t = lane; t < nxt; t += TM_NL) s.tr[t] = w[N * NZ + P.term_idx[t]] - xrN[P.term_idx[t]];
   }
   TM_SYNC();
+  if (pert) {
+    if (pert->homog) {
+      for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.r[e] = 0.0;
+      for (int e = lane; e < N * NX; e += TM_NL) s.b[e] = 0.0;
+      for (int t = lane; t < nxt; t += TM_NL) s.tr[t] = 0.0;
+    }
+    for (int a = lane; a < NX; a += TM_NL) e0[a] = 0.0;     // the x_0 offset always enters through the table
+    TM_SYNC();
+    if (pert->e0_unit >= 0) for (int a = lane; a < NX; a += TM_NL) e0[a] = (a == pert->e0_unit) ? 1.0 : 0.0;
+    if (pert->row >= 0) {
+      const int k = pert->row / nh, i = pert->row % nh;
+      for (int b2 = lane; b2 < NZ; b2 += TM_NL) s.r[k * NZ + b2] -= P.C[(size_t)i * NZ + b2];
+    }
+    TM_SYNC();
+  }
   if (al_mask) {
     // gamma relative to the largest Hessian diagonal entry of the horizon
     double qmax = 0.0;
@@ -1169,7 +1194,7 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
       TM_SYNC();
     }
   }
-  const int maxit = 4 * E + 8;
+  const int maxit = pert ? 0 : 4 * E + 8;
   for (int it = 0; it < maxit && !ret; ++it) {
     int qe;
     double qs = 1.0, sval;
@@ -1289,7 +1314,7 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
       TM_SYNC();
     }
   }
-  if (lane == 0) {
+  if (lane == 0 && !pert) {
     S.qpwork[inst] = n_gi;
 #ifdef __CUDA_ARCH__
     atomicAdd(S.counters + 5, 1ull); atomicAdd(S.counters + 6, (unsigned long long)n_gi); atomicAdd(S.counters + 7, (unsigned long long)n_ricc);
@@ -1310,8 +1335,8 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     if (nbad) return 5;
   }
   // ---- D. outputs: step and multipliers (CasADi sign: H d + g + J' lam = 0) ------------------------------------
-  double* dout = S.D + inst * P.n_w;
-  double* lq = S.LAMQ + inst * P.n_g;
+  double* dout = pert ? pert->dout : S.D + inst * P.n_w;
+  double* lq = pert ? pert->lout : S.LAMQ + inst * P.n_g;
   for (int e = lane; e < P.n_w; e += TM_NL) dout[e] = s.d[e];
   for (int e = lane; e < P.n_g; e += TM_NL) lq[e] = 0.0;
   TM_SYNC();
@@ -1636,6 +1661,196 @@ TM_HD void tm_prefilter(const TmProb& P, const TmState& S, int64_t inst) {
   double* lam = S.LAM + inst * P.n_g;
   for (int e = TM_LANE; e < P.n_g; e += TM_NL) if (fabs(lam[e]) < P.lam_tresh) lam[e] = 0.0;
   TM_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// First QP after reset(): every instance starts from the same (w0, lam0) (pmpc.py:930-942), so all B QPs share the
+// Hessian, the constraint Jacobian and every offset except the x_0 residual e0 = x0 - w0[0:nx]: ONE parametric QP.
+// Its equality-constrained solution map is tabulated once (tm_qp_solve with TmQpPert, one warp per table row):
+//     TAB[0]          (d, lam) for e0 = 0                 TAB[1+a]       response to e0 = unit_a
+//     TAB[1+NX+e]     response to a unit multiplier on inequality row e (terminal rows stay enforced)
+//     SL0 / SLPHI     row values n_e'd of TAB[0] (+ h(w0)) / of TAB[1+a];     MCOL[e][e'] = n_e' G' n_e
+// and each instance runs only the Goldfarb-Idnani working-set iteration on these tables (thread per instance, state in
+// registers / local memory, no Riccati sweep, no per-instance workspace), then one table combination for (d, lam).
+// Same exact active-set solution as tm_qp_solve (unique: strictly convex on the feasible null space).
+// ---------------------------------------------------------------------------------------------------------------
+#define TM_Q0_MAXM 20      /* working-set capacity (inequality rows); overflow -> generic path */
+struct TmQp0Tab {
+  int EI, EIs, n_out, nT;  // inequality rows N*nh, padded row stride of MCOL (odd), n_w + n_g, 1 + NX + EI
+  double *TAB, *SL0, *SLPHI, *MCOL;
+  int* bad;                // != 0: the tabulation failed (base factorisation not PD ...) -> every instance takes the generic path
+};
+
+// returns 0 ok / 2 not solved here (overflow, dependent rows, breakdown): the caller queues the instance for tm_qp
+TM_HD int tm_qp0_gi(const TmProb& P, const TmQp0Tab& T, const double* e0, int* acte, double* nu, int& m_out, int& ngi_out) {
+  const int EI = T.EI, EIs = T.EIs, nh = P.nh;
+  double Lf[TM_Q0_MAXM * TM_Q0_MAXM], cA[TM_Q0_MAXM], rv[TM_Q0_MAXM];
+  int m = 0, ngi = 0;
+  m_out = 0; ngi_out = 0;
+  const int maxit = 4 * EI + 8;
+  for (int it = 0; it < maxit; ++it) {
+    double best = TM_INF, bval = 0.0;
+    int bid = -1;
+    for (int e = 0; e < EI; ++e) {
+      const int k = e / nh, i = e - k * nh;
+      if (k == 0 && P.relax0[i]) continue;
+      double v = T.SL0[e];
+#pragma unroll
+      for (int a = 0; a < NX; ++a) v += e0[a] * T.SLPHI[a * EI + e];
+      for (int j = 0; j < m; ++j) v += nu[j] * T.MCOL[(size_t)acte[j] * EIs + e];
+      const double sc = v / fmax(1.0, fabs(P.c[i]));
+      if (sc < best) { best = sc; bid = e; bval = v; }
+    }
+    if (!(best < -1e-10)) break;                 // primal feasible: optimal
+    int dup = 0;
+    for (int j = 0; j < m; ++j) if (acte[j] == bid) dup = 1;
+    if (dup) break;
+    if (m >= TM_Q0_MAXM) return 2;
+    const int qe = bid;
+    double sval = bval;
+    const double yq = T.MCOL[(size_t)qe * EIs + qe];
+    double nq = 0.0;
+    int added = 0;
+    ++ngi;
+    for (int inner = 0; inner < TM_Q0_MAXM + 2; ++inner) {
+      double ll = 0.0;
+      for (int i = 0; i < m; ++i) {
+        double v = T.MCOL[(size_t)qe * EIs + acte[i]];
+        for (int l = 0; l < i; ++l) v -= Lf[i * TM_Q0_MAXM + l] * cA[l];
+        v /= Lf[i * TM_Q0_MAXM + i];
+        cA[i] = v;
+        ll += v * v;
+      }
+      for (int i = m - 1; i >= 0; --i) {
+        double v = cA[i];
+        for (int l = i + 1; l < m; ++l) v -= Lf[l * TM_Q0_MAXM + i] * rv[l];
+        rv[i] = v / Lf[i * TM_Q0_MAXM + i];
+      }
+      const double zn = yq - ll;
+      double t1 = TM_INF;
+      int jd = -1;
+      for (int j = 0; j < m; ++j) {
+        if (rv[j] > 1e-14) { const double tj = nu[j] / rv[j]; if (tj < t1) { t1 = tj; jd = j; } }
+      }
+      const int dependent = !(zn > 1e-11 * fmax(yq, 1e-300));
+      double t;
+      int do_add = 0;
+      if (dependent) {
+        if (jd < 0) return 2;
+        t = t1;
+      } else {
+        const double t2 = -sval / zn;
+        if (t2 <= t1) { t = t2; do_add = 1; } else t = t1;
+        sval += t * zn;
+      }
+      for (int j = 0; j < m; ++j) nu[j] -= t * rv[j];
+      nq += t;
+      if (do_add) {
+        for (int l = 0; l < m; ++l) Lf[m * TM_Q0_MAXM + l] = cA[l];
+        Lf[m * TM_Q0_MAXM + m] = sqrt(zn);
+        acte[m] = qe; nu[m] = nq;
+        ++m;
+        added = 1;
+        break;
+      }
+      for (int a = jd; a < m - 1; ++a) { acte[a] = acte[a + 1]; nu[a] = nu[a + 1]; }
+      --m;
+      for (int i = 0; i < m; ++i)
+        for (int j = 0; j <= i; ++j) Lf[i * TM_Q0_MAXM + j] = T.MCOL[(size_t)acte[j] * EIs + acte[i]];
+      for (int c = 0; c < m; ++c) {
+        double dg = Lf[c * TM_Q0_MAXM + c];
+        for (int l = 0; l < c; ++l) dg -= Lf[c * TM_Q0_MAXM + l] * Lf[c * TM_Q0_MAXM + l];
+        if (!(dg > 0.0)) return 2;
+        const double ld = sqrt(dg);
+        Lf[c * TM_Q0_MAXM + c] = ld;
+        for (int i = c + 1; i < m; ++i) {
+          double v = Lf[i * TM_Q0_MAXM + c];
+          for (int l = 0; l < c; ++l) v -= Lf[i * TM_Q0_MAXM + l] * Lf[c * TM_Q0_MAXM + l];
+          Lf[i * TM_Q0_MAXM + c] = v / ld;
+        }
+      }
+    }
+    if (!added) return 2;
+    if (it == maxit - 1) return 2;
+  }
+  m_out = m; ngi_out = ngi;
+  return 0;
+}
+
+// (d, lam)[i] of one instance from the tables: element i of  TAB[0] + sum_a e0_a TAB[1+a] + sum_j nu_j TAB[1+NX+acte_j]
+TM_HD double tm_qp0_combine(const TmQp0Tab& T, int i, const double* e0, const int* acte, const double* nu, int m) {
+  double v = T.TAB[i];
+#pragma unroll
+  for (int a = 0; a < NX; ++a) v += e0[a] * T.TAB[(size_t)(1 + a) * T.n_out + i];
+  for (int j = 0; j < m; ++j) v += nu[j] * T.TAB[(size_t)(1 + NX + acte[j]) * T.n_out + i];
+  return v;
+}
+
+// table row t of the tabulation (one warp / one twin call per row); inst = any instance (all identical)
+TM_HD void tm_qp0_build_row(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& ws, const TmQp0Tab& T, int t) {
+  TmQpPert pt;
+  pt.homog = t > 0;
+  pt.e0_unit = (t >= 1 && t <= NX) ? t - 1 : -1;
+  pt.row = t > NX ? t - 1 - NX : -1;
+  pt.dout = T.TAB + (size_t)t * T.n_out;
+  pt.lout = pt.dout + P.n_w;
+  unsigned bad[TM_ALW];
+  const int ret = tm_qp_solve(P, S, inst, ws, P.hessian_exact, nullptr, bad, &pt);
+  if (TM_LANE == 0) {
+    if (ret != 0) {
+#ifdef __CUDA_ARCH__
+      atomicExch(T.bad, 1);
+#else
+      *T.bad = 1;
+#endif
+    } else if (pt.row >= 0) {
+      pt.lout[tm_gh(P, pt.row / P.nh) + pt.row % P.nh] = -1.0;       // the unit multiplier itself (lam_h = -nu)
+    }
+  }
+  TM_SYNC();
+}
+
+// derived tables: entry (t, e) = n_e' TAB[t].d  (+ h_e(w0) for t = 0)
+TM_HD void tm_qp0_derive(const TmProb& P, const TmState& S, int64_t inst, const TmQp0Tab& T, int t, int e) {
+  const int k = e / P.nh, i = e % P.nh;
+  const double* Ci = P.C + (size_t)i * NZ;
+  const double* d = T.TAB + (size_t)t * T.n_out + (size_t)k * NZ;
+  double v = 0.0;
+#pragma unroll
+  for (int b = 0; b < NZ; ++b) v += Ci[b] * d[b];
+  if (t == 0) {
+    const double* w = S.W + inst * P.n_w + (size_t)k * NZ;
+    double hv = P.c[i];
+#pragma unroll
+    for (int b = 0; b < NZ; ++b) hv += Ci[b] * w[b];
+    T.SL0[e] = hv + v;
+  } else if (t <= NX) {
+    T.SLPHI[(size_t)(t - 1) * T.EI + e] = v;
+  } else {
+    T.MCOL[(size_t)(t - 1 - NX) * T.EIs + e] = v;
+  }
+}
+
+// bookkeeping of one instance solved (ret == 0) or not (ret != 0 -> queued for the generic path) by the table route
+TM_HD void tm_qp0_finish(const TmProb& P, const TmState& S, int64_t inst, int ret, int ngi) {
+  if (ret == 0) {
+    S.qpmode[inst] = 0;
+    S.qpstat[inst] = 0;
+    S.qpwork[inst] = ngi;
+#ifdef __CUDA_ARCH__
+    atomicAdd(S.counters + 5, 1ull); atomicAdd(S.counters + 6, (unsigned long long)ngi); atomicAdd(S.counters + 8, 1ull);
+#else
+    S.counters[5] += 1; S.counters[6] += ngi; S.counters[8] += 1;
+#endif
+  } else {
+    S.qpmode[inst] = 0;
+#ifdef __CUDA_ARCH__
+    const int pos = atomicAdd(S.cnt_retry, 1);
+#else
+    const int pos = (*S.cnt_retry)++;
+#endif
+    S.list_retry[pos] = (int)inst;
+  }
 }
 
 // One QP attempt with the configured Hessian.  Exact mode: (1) augmented-Lagrangian convexification on the rows that
