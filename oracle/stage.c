@@ -14,6 +14,7 @@
  * are pinned by finite differences and by sympy lambdify in tests/.
  */
 #include <string.h>
+#include <math.h>
 #include TMPC_MODEL_HEADER
 
 #define NX TMPC_NX
@@ -58,6 +59,33 @@ static void rhs_sens(const double* X, const double* u, const double* dX, const d
   }
 }
 
+#ifndef TMPC_COLLOCATION
+#define TMPC_COLLOCATION 0
+#endif
+
+/* dense Gaussian elimination with partial pivoting: solves A X = B in place (A n x n row-major, destroyed; B n x m) */
+static void gauss_solve(int n, double* A, double* B, int m) {
+  for (int c = 0; c < n; ++c) {
+    int p = c;
+    for (int r = c + 1; r < n; ++r) if (fabs(A[r * n + c]) > fabs(A[p * n + c])) p = r;
+    if (p != c) {
+      for (int k = 0; k < n; ++k) { double t = A[c * n + k]; A[c * n + k] = A[p * n + k]; A[p * n + k] = t; }
+      for (int k = 0; k < m; ++k) { double t = B[c * m + k]; B[c * m + k] = B[p * m + k]; B[p * m + k] = t; }
+    }
+    for (int r = c + 1; r < n; ++r) {
+      double f = A[r * n + c] / A[c * n + c];
+      for (int k = c; k < n; ++k) A[r * n + k] -= f * A[c * n + k];
+      for (int k = 0; k < m; ++k) B[r * m + k] -= f * B[c * m + k];
+    }
+  }
+  for (int r = n - 1; r >= 0; --r)
+    for (int k = 0; k < m; ++k) {
+      double v = B[r * m + k];
+      for (int c2 = r + 1; c2 < n; ++c2) v -= A[r * n + c2] * B[c2 * m + k];
+      B[r * m + k] = v / A[r * n + r];
+    }
+}
+
 #define NS1 (NX * NZ)
 #define NS2 (NX * NZ * NZ)
 
@@ -75,6 +103,91 @@ void orc_F(const double* x, const double* u, double* xf, double* S, double* T, i
     if (order >= 1) memcpy(S, dk, sizeof dk);
     if (order >= 2) memcpy(T, ddk, sizeof ddk);
     return;
+  }
+#elif TMPC_COLLOCATION
+  /* integrator('F','collocation',ode,{'tf':..}) (reference: examples/evaporation_process/main.py:103): per finite
+   * element the 3-node Radau collocation equations (= Radau IIA), solved by Newton on the stage STATES Y_q
+   *   R_q = Y_q - X - h sum_l a_ql f(Y_l,u) = 0,   x+ = Y_3,
+   * then FULL first/second-order tensors of Y by the implicit function theorem (dense Gaussian elimination on the
+   * 3nx system).  The CUDA path iterates on the stage derivatives and propagates one direction pair at a time. */
+  {
+    const double sq6 = sqrt(6.0);
+    const double A[3][3] = {{(88 - 7 * sq6) / 360, (296 - 169 * sq6) / 1800, (-2 + 3 * sq6) / 225},
+                            {(296 + 169 * sq6) / 1800, (88 + 7 * sq6) / 360, (-2 - 3 * sq6) / 225},
+                            {(16 - sq6) / 36, (16 + sq6) / 36, 1.0 / 9}};
+    const double h = TMPC_RK_DT;
+    enum { CN = 3 * NX };
+    for (int s = 0; s < TMPC_RK_STEPS; ++s) {
+      double Y[3][NX], f[3][NX], df[3][NS1], ddf[3][NS2], dY[3][NS1], ddY[3][NS2];
+      double Jm[CN][CN], rhs[CN], J[3][NX * NZ], Hn[3][TMPC_NHESS > 0 ? TMPC_NHESS : 1];
+      for (int q = 0; q < 3; ++q) memcpy(Y[q], X, sizeof X);
+      for (int it = 0; it < 50; ++it) {
+        for (int q = 0; q < 3; ++q) tmpc_ode_d2(Y[q], u, f[q], J[q], Hn[q]);
+        double rmax = 0;
+        for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) {
+          double r = Y[q][a] - X[a];
+          for (int l = 0; l < 3; ++l) r -= h * A[q][l] * f[l][a];
+          rhs[q * NX + a] = -r;
+          if (fabs(r) > rmax) rmax = fabs(r);
+        }
+        for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) for (int l = 0; l < 3; ++l) for (int b = 0; b < NX; ++b)
+          Jm[q * NX + a][l * NX + b] = ((q == l && a == b) ? 1.0 : 0.0) - h * A[q][l] * J[l][a * NZ + b];
+        if (it > 0 && rmax < 1e-15 * (1.0 + fabs(X[0]))) break;
+        gauss_solve(CN, &Jm[0][0], rhs, 1);
+        double dmax = 0;
+        for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) { Y[q][a] += rhs[q * NX + a]; if (fabs(rhs[q * NX + a]) > dmax) dmax = fabs(rhs[q * NX + a]); }
+        if (dmax == 0.0) break;
+      }
+      if (order >= 1) {
+        /* converged Jacobian of the residual w.r.t. Y; first-order: Jm dY = dX + h sum_l a_ql (J_u part) */
+        for (int q = 0; q < 3; ++q) tmpc_ode_d2(Y[q], u, f[q], J[q], Hn[q]);
+        for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) for (int l = 0; l < 3; ++l) for (int b = 0; b < NX; ++b)
+          Jm[q * NX + a][l * NX + b] = ((q == l && a == b) ? 1.0 : 0.0) - h * A[q][l] * J[l][a * NZ + b];
+        static double R1[3 * NX * NZ];
+        for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) for (int i = 0; i < NZ; ++i) {
+          double r = dX[a * NZ + i];
+          if (i >= NX) for (int l = 0; l < 3; ++l) r += h * A[q][l] * J[l][a * NZ + i];
+          R1[(q * NX + a) * NZ + i] = r;
+        }
+        double Jc[CN][CN];
+        memcpy(Jc, Jm, sizeof Jm);
+        gauss_solve(CN, &Jc[0][0], R1, NZ);
+        for (int q = 0; q < 3; ++q) memcpy(dY[q], R1 + q * NS1, sizeof(double) * NS1);
+        if (order >= 2) {
+          /* second order: Jm ddY = ddX + h sum_l a_ql ( f_zz[dZ_l, dZ_l] ), dZ_l = [dY_l ; 0 I] */
+          static double R2[3 * NX * NZ * NZ];
+          double fz[3][NS2];
+          for (int l = 0; l < 3; ++l) {
+            double dZ[NZ * NZ];
+            memcpy(dZ, dY[l], sizeof(double) * NS1);
+            for (int b = 0; b < NU; ++b) for (int i = 0; i < NZ; ++i) dZ[(NX + b) * NZ + i] = (i == NX + b) ? 1.0 : 0.0;
+            memset(fz[l], 0, sizeof fz[l]);
+            for (int n = 0; n < TMPC_NHESS; ++n) {
+              int a = hA[n], b = hB[n], c = hC[n];
+              for (int i = 0; i < NZ; ++i) for (int j = 0; j < NZ; ++j) {
+                double t = Hn[l][n] * dZ[b * NZ + i] * dZ[c * NZ + j];
+                if (b != c) t += Hn[l][n] * dZ[c * NZ + i] * dZ[b * NZ + j];
+                fz[l][(a * NZ + i) * NZ + j] += t;
+              }
+            }
+          }
+          for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) for (int ij = 0; ij < NZ * NZ; ++ij) {
+            double r = ddX[a * NZ * NZ + ij];
+            for (int l = 0; l < 3; ++l) r += h * A[q][l] * fz[l][a * NZ * NZ + ij];
+            R2[(q * NX + a) * NZ * NZ + ij] = r;
+          }
+          memcpy(Jc, Jm, sizeof Jm);
+          gauss_solve(CN, &Jc[0][0], R2, NZ * NZ);
+          for (int q = 0; q < 3; ++q) memcpy(ddY[q], R2 + q * NS2, sizeof(double) * NS2);
+          memcpy(ddX, ddY[2], sizeof ddX);
+        }
+        memcpy(dX, dY[2], sizeof dX);
+      }
+      memcpy(X, Y[2], sizeof X);
+    }
+    memcpy(xf, X, sizeof X);
+    if (order >= 1) memcpy(S, dX, sizeof dX);
+    if (order >= 2) memcpy(T, ddX, sizeof ddX);
   }
 #else
   const double h = TMPC_RK_DT;

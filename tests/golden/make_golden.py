@@ -33,6 +33,9 @@ def sample_x0(name, pb, B, seed=0):
         X0[:, 0] += alpha * (1.0 - xs[0])                       # dx_diehl direction, examples/cstr/main.py:126-131
         X0[:, 1:] += 1e-2 * np.abs(xs[1:]) * rng.uniform(-1, 1, (B, pb.nx - 1))
         return X0
+    if name == "evaporation":
+        # X2 sits on its bound 25.0 -> perturb upward only; P2 +-1.0 (evaporation_process/main.py:178-180)
+        return xs + np.stack([0.5 * np.abs(rng.uniform(-1, 1, B)), 1.0 * rng.uniform(-1, 1, B)], axis=1)
     if name == "unicycle":
         return xs + np.array([0.5, 0.1, 0.0, 0.0]) * rng.uniform(-1, 1, (B, pb.nx))   # examples/unicycle/main.py:172
     raise KeyError(name)
@@ -79,10 +82,50 @@ def unicycle():
     np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % name), **out)
 
 
+def evaporation():
+    """config #3: collocation integrator, pure state constraints (relaxed at stage 0, pmpc.py:293-294), reference on the
+    bound X2 = 25 (non-zero reference multipliers -> type-B tuning with C_As, reduced-space convexification)."""
+    name = "evaporation"
+    st = rp.StageLib(name)
+    pb, info = configs.make_problem(name, st.F)
+    pb.save(os.path.join(HERE, "problem_%s.npz" % name))
+    B = 24
+    X0 = sample_x0(name, pb, B)
+    out = {"X0": X0}
+    for tag, tol in (("t6", 1e-6), ("t9", 1e-9)):
+        ctrl = rp.Pmpc(pb, qp="qpoases", sqp_options={"tol": tol})
+        U, W, LAM, IT, ST, NAS = [], [], [], [], [], []
+        for b in range(B):
+            ctrl.reset()
+            u = ctrl.step(X0[b])
+            U.append(u); W.append(ctrl.w_sol); LAM.append(ctrl.lam_g)
+            IT.append(ctrl.log["iter"][-1]); ST.append(ctrl.log["status"][-1]); NAS.append(ctrl.log["nAS"][-1])
+        out.update({"u0_" + tag: np.array(U), "w_" + tag: np.array(W), "lam_" + tag: np.array(LAM),
+                    "iter_" + tag: np.array(IT), "status_" + tag: np.array(ST), "nAS_" + tag: np.array(NAS)})
+        print(name, tag, "iter hist", np.bincount(np.array(IT)), "status", np.bincount(np.array(ST)), "nAS", np.bincount(np.array(NAS)))
+    ctrl = rp.Pmpc(pb, qp="qpoases")
+    Xcl, Ucl = [], []
+    for b in range(4):
+        ctrl.reset()
+        x = X0[b].copy()
+        xs_, us_ = [x.copy()], []
+        for _ in range(5):
+            u = ctrl.step(x)
+            x = st.F(x[None, :], u[None, :])[0]
+            xs_.append(x.copy()); us_.append(u.copy())
+        Xcl.append(xs_); Ucl.append(us_)
+    out["cl_X"] = np.array(Xcl)
+    out["cl_U"] = np.array(Ucl)
+    np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % name), **out)
+
+
 def main():
     rp.build()
     if len(sys.argv) > 1 and sys.argv[1] == "unicycle":
         unicycle()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "evaporation":
+        evaporation()
         return
     for name, B in (("lq", 64), ("cstr", 48)):
         st = rp.StageLib(name)
@@ -118,6 +161,7 @@ def main():
         out["cl_U"] = np.array(Ucl)
         np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % name), **out)
     unicycle()
+    evaporation()
 
 
 if __name__ == "__main__":

@@ -231,3 +231,29 @@ def test_closed_loop_tools_batched(torch_mod):
     cB, Vd, QK = lg["x"]["TUNEMPC"][:, :, 1].cpu().numpy(), lg["u"]["TUNEMPC"][:, :, 0].cpu().numpy(), lg["u"]["TUNEMPC"][:, :, 1].cpu().numpy()
     lref = 100 * (-cB / 5.10 + 0.1 * (1e-4 * (Vd - 14.19) ** 2 + 1e-4 * (QK + 1113.5) ** 2))   # cstr_model.py:117-129
     assert _relerr(lg["l"]["TUNEMPC"].cpu().numpy(), lref) < 1e-12
+
+
+@pytest.mark.parametrize("tag,tol", [("t6", 1e-6), ("t9", 1e-9)])
+def test_evaporation_golden(torch_mod, tag, tol):
+    """config #3 (examples/evaporation_process): collocation integrator on the device, pure state constraints relaxed at
+    stage 0, 29-row active set with non-zero reference multipliers; open loop + 5 closed-loop steps."""
+    torch = torch_mod
+    ctrl, pb = _ctrl("evaporation", tol=tol)
+    gold = load_golden("evaporation")
+    U = ctrl.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
+    assert (ctrl.status.cpu().numpy() == 0).all()
+    assert _relerr(U, gold["u0_" + tag]) < 1e-6
+    assert _relerr(ctrl.w_sol.cpu().numpy(), gold["w_" + tag]) < 1e-6
+    lam = ctrl.lam_g.cpu().numpy()
+    for b in range(lam.shape[0]):
+        assert set(np.nonzero(lam[b])[0]) == set(np.nonzero(gold["lam_" + tag][b])[0]), b
+    assert np.array_equal(ctrl.log["nAS"][-1].cpu().numpy(), gold["nAS_" + tag])
+    assert np.array_equal(ctrl.log["iter"][-1].cpu().numpy(), gold["iter_" + tag])
+    if tag == "t6":
+        ctrl.reset()
+        X = torch.tensor(gold["cl_X"][:, 0], device="cuda:0")
+        for s in range(5):
+            Uc = ctrl.step(X)
+            assert _relerr(Uc.cpu().numpy(), gold["cl_U"][:, s]) < 1e-6, s
+            X = ctrl.plant_step(X, Uc)
+            assert _relerr(X.cpu().numpy(), gold["cl_X"][:, s + 1]) < 1e-6, s

@@ -135,3 +135,33 @@ def test_twin_shared_first_qp(env):
     assert _relerr(a1["w"], b1["w"]) < 1e-9 and _relerr(a1["lam"], b1["lam"]) < 1e-6
     for i in range(n):
         assert set(np.nonzero(a1["lam"][i])[0]) == set(np.nonzero(b1["lam"][i])[0])     # exact zeros off the working set
+
+
+def test_twin_evaporation_collocation(env):
+    """config #3: implicit (Radau collocation) integrator with IFT sensitivities, pure state constraints relaxed at
+    stage 0, 29 active rows at the solution (reference on the bound X2 = 25), reduced-space convexification mask."""
+    rp, build_tables, Twin = env
+    pb, gold = load_problem("evaporation"), load_golden("evaporation")
+    assert pb.h_x_idx == [0, 1, 2] and pb.lam_h_ref[0, 0] < 0
+    tw = Twin(pb, build_tables(pb), rho=3e7, al_gamma=1e3)
+    rng = np.random.default_rng(3)
+    z = pb.wref[0] * (1 + 0.03 * rng.standard_normal((5, pb.nz)))
+    a = rp.StageLib("evaporation").F(z[:, :pb.nx], z[:, pb.nx:], 2)           # full-tensor IFT on the stage states
+    b = tw.stage_eval(z[:, :pb.nx], z[:, pb.nx:], 2)                          # pair-wise IFT on the stage derivatives
+    for x, y in zip(a, b):
+        assert np.max(np.abs(x - y)) <= 1e-11 * max(1.0, np.max(np.abs(x)))
+    n = 24
+    tw.reset(n)
+    o = tw.step(gold["X0"])
+    assert (o["status"] == 0).all() and (o["flags"] & 1 == 0).all()
+    assert np.array_equal(o["iter"], gold["iter_t6"]) and np.array_equal(o["nAS"], gold["nAS_t6"])
+    assert _relerr(o["u0"], gold["u0_t6"]) < 1e-9 and _relerr(o["w"], gold["w_t6"]) < 1e-9
+    for i in range(n):
+        assert set(np.nonzero(o["lam"][i])[0]) == set(np.nonzero(gold["lam_t6"][i])[0])
+    st = rp.StageLib("evaporation")
+    tw.reset(4)
+    x = gold["cl_X"][:, 0].copy()
+    for s in range(5):
+        o = tw.step(x)
+        assert _relerr(o["u0"], gold["cl_U"][:, s]) < 1e-8, s
+        x = st.F(x, o["u0"])

@@ -92,7 +92,36 @@ def unicycle():
                 term_idx=[0, 1, 3], x0_scale=np.array([0.5, 0.1, 0.0, 0.0]))                       # :172 disturbance sizes
 
 
-CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle}
+def evaporation():
+    """examples/evaporation_process/main.py:42-138 -- evaporation process, nx=2 (X2,P2), nu=2 (P100,F200), CasADi
+    'collocation' integrator over tf = 1 (:103), five linear constraints of which three are pure state constraints."""
+    a, b, c_, d, e, f_, g, h_ = 0.5616, 0.3126, 48.43, 0.507, 55.0, 0.1538, 90.0, 0.16      # :49-56
+    M, Cc, UA2, Cp, lam, lams = 20.0, 4.0, 6.84, 0.07, 38.5, 36.6                              # :58-63
+    F1, X1, F3, T1, T200 = 10.0, 5.0, 50.0, 40.0, 25.0                                         # :64-68
+    X2, P2 = sp.symbols("X2 P2")
+    P100, F200 = sp.symbols("P100 F200")
+    T2 = a * P2 + b * X2 + c_                                                                 # :77-86
+    T3 = d * P2 + e
+    T100 = f_ * P100 + g
+    UA1 = h_ * (F1 + F3)
+    Q100 = UA1 * (T100 - T2)
+    F100 = Q100 / lams
+    Q200 = UA2 * (T3 - T200) / (1.0 + UA2 / (2.0 * Cp * F200))
+    F5 = Q200 / lam
+    F4 = (Q100 - F1 * Cp * (T2 - T1)) / lam
+    F2 = F1 - F4
+    xdot = [(F1 * X1 - F2 * X2) / M, (F4 - F5) / Cc]                                          # :96-99
+    cost = 10.09 * (F2 + F3) + 600.0 * F100 + 0.6 * F200                                      # :121
+    C = np.zeros((5, 4))                                                                      # :130-136
+    C[0, 0], C[1, 1], C[2, 1], C[3, 2], C[4, 3] = 1.0, 1.0, -1.0, -1.0, -1.0
+    c = np.array([-25.0, -40.0, 80.0, 400.0, 400.0])
+    model = OdeModel("evaporation", (X2, P2), (P100, F200), xdot, rk_steps=20, tf=1.0, integrator="collocation", cost=cost)
+    w_guess = np.array([25.0, 49.743, 191.713, 215.888])                                      # :155
+    return dict(model=model, cost=cost, C=C, c=c, w_guess=w_guess, period=1, N=30, term_idx=[0, 1],
+                conv_rho=1e-3)                                                                # :157 convexify(rho = 1e-3)
+
+
+CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle, "evaporation": evaporation}
 
 
 def make_problem(name, stage_F, N=None, hessian_approximation="exact"):

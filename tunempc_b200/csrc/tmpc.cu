@@ -301,7 +301,7 @@ __global__ void k_sort_scatter(const int* list, int cnt, const int* key, int* bi
 static cudaError_t launch_lin(tmpc_handle* h, const int* list, int64_t cnt, int trial, cudaStream_t st) {
   const TmProb& P = h->P;
   const TmState& S = h->S;
-#if !TMPC_DISCRETE
+#if TMPC_RK4
   if (h->lin_mode == 2) {
     const unsigned grid = (unsigned)((cnt * P.N + 31) / 32);
     if (P.hessian_exact) k_lin2<true><<<grid, L2_THREADS, tm_lin2_smem_bytes(), st>>>(P, S, list, nullptr, (int)cnt, trial);
@@ -404,7 +404,7 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
     h->trace = getenv("TMPC_TRACE") != nullptr;
     const char* lm = getenv("TMPC_LIN_MODE");
     if (lm) h->lin_mode = atoi(lm);
-#if TMPC_DISCRETE
+#if !TMPC_RK4
     h->lin_mode = 1;
 #else
     if (tm_lin2_smem_bytes() > 48 * 1024) {

@@ -184,6 +184,138 @@ TM_HD void tm_rhs(const double* X, const double* u, const double* Si, const doub
   }
 }
 
+
+#ifndef TMPC_COLLOCATION
+#define TMPC_COLLOCATION 0
+#endif
+#define TMPC_RK4 (!TMPC_DISCRETE && !TMPC_COLLOCATION)
+
+#if TMPC_COLLOCATION
+// ---------------------------------------------------------------------------------------------------------------
+// CasADi integrator('F','collocation',ode,{'tf':..}) (reference: examples/evaporation_process/main.py:103): TMPC_RK_STEPS
+// finite elements, Radau points of interpolation order 3 per element = the 3-stage Radau IIA method, solved to
+// convergence by Newton.  Stage derivatives K_j = f(x + h sum_l a_jl K_l, u).  Sensitivities by the implicit function
+// theorem with the converged iteration matrix M = I - h (a_jl J_j):  M dK_i = J_j v_i,  M ddK = f_zz[v_i, v_j] + J_x,j T.
+// ---------------------------------------------------------------------------------------------------------------
+#define TM_CN (3 * NX)
+TM_HD void tm_lu_factor(double* M, int* piv) {          // row-major TM_CN x TM_CN, partial pivoting, in place
+  for (int c = 0; c < TM_CN; ++c) {
+    int p = c;
+    double best = fabs(M[c * TM_CN + c]);
+    for (int r = c + 1; r < TM_CN; ++r) { const double v = fabs(M[r * TM_CN + c]); if (v > best) { best = v; p = r; } }
+    piv[c] = p;
+    if (p != c) for (int k = 0; k < TM_CN; ++k) { const double t = M[c * TM_CN + k]; M[c * TM_CN + k] = M[p * TM_CN + k]; M[p * TM_CN + k] = t; }
+    const double d = 1.0 / M[c * TM_CN + c];
+    for (int r = c + 1; r < TM_CN; ++r) {
+      const double f = M[r * TM_CN + c] * d;
+      M[r * TM_CN + c] = f;
+      for (int k = c + 1; k < TM_CN; ++k) M[r * TM_CN + k] -= f * M[c * TM_CN + k];
+    }
+  }
+}
+TM_HD void tm_lu_solve(const double* M, const int* piv, double* b) {
+  for (int c = 0; c < TM_CN; ++c) {
+    const int p = piv[c];
+    if (p != c) { const double t = b[c]; b[c] = b[p]; b[p] = t; }
+    for (int r = c + 1; r < TM_CN; ++r) b[r] -= M[r * TM_CN + c] * b[c];
+  }
+  for (int r = TM_CN - 1; r >= 0; --r) {
+    double v = b[r];
+    for (int k = r + 1; k < TM_CN; ++k) v -= M[r * TM_CN + k] * b[k];
+    b[r] = v / M[r * TM_CN + r];
+  }
+}
+
+template <int ORDER>
+TM_HD void tm_integrate_colloc(const double* u, int i, int j, double* X, double* Si, double* Sj, double* T) {
+  const double sq6 = 2.449489742783178;
+  const double A[3][3] = {{(88.0 - 7.0 * sq6) / 360.0, (296.0 - 169.0 * sq6) / 1800.0, (-2.0 + 3.0 * sq6) / 225.0},
+                          {(296.0 + 169.0 * sq6) / 1800.0, (88.0 + 7.0 * sq6) / 360.0, (-2.0 - 3.0 * sq6) / 225.0},
+                          {(16.0 - sq6) / 36.0, (16.0 + sq6) / 36.0, 1.0 / 9.0}};
+  const double h = TMPC_RK_DT;
+  for (int s = 0; s < TMPC_RK_STEPS; ++s) {
+    double K[3][NX], Jst[3][NX * NZ], M[TM_CN * TM_CN], rhs[TM_CN];
+    double Hst[3][TMPC_NHESS > 0 ? TMPC_NHESS : 1];
+    int piv[TM_CN];
+    {
+      double f0[NX];
+      tmpc_ode(X, u, f0);
+      for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) K[q][a] = f0[a];
+    }
+    // Newton to convergence; the last pass (done = 1) re-evaluates J (and d2f) at the converged stage points
+    int done = 0;
+    for (int it = 0; it < 40; ++it) {
+      for (int q = 0; q < 3; ++q) {
+        double Xq[NX], fq[NX];
+        for (int a = 0; a < NX; ++a) {
+          double v = X[a];
+          for (int l = 0; l < 3; ++l) v += h * A[q][l] * K[l][a];
+          Xq[a] = v;
+        }
+        if (done && ORDER == 2) tmpc_ode_d2(Xq, u, fq, Jst[q], Hst[q]); else tmpc_ode_jac(Xq, u, fq, Jst[q]);
+        for (int a = 0; a < NX; ++a) rhs[q * NX + a] = -(K[q][a] - fq[a]);
+      }
+      for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) for (int l = 0; l < 3; ++l) for (int b = 0; b < NX; ++b)
+        M[(q * NX + a) * TM_CN + l * NX + b] = ((q == l && a == b) ? 1.0 : 0.0) - h * A[q][l] * Jst[q][a * NZ + b];
+      tm_lu_factor(M, piv);
+      if (done) break;
+      tm_lu_solve(M, piv, rhs);
+      double dmax = 0.0, kmax = 1.0;
+      for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) {
+        K[q][a] += rhs[q * NX + a];
+        dmax = fmax(dmax, fabs(rhs[q * NX + a]));
+        kmax = fmax(kmax, fabs(K[q][a]));
+      }
+      if (!(dmax > 1e-14 * kmax)) done = 1;
+      if (it == 38) done = 1;
+    }
+    double dKi[TM_CN], dKj[TM_CN], ddK[TM_CN];
+    if (ORDER >= 1) {
+      // stage-argument directions need dK, so solve first, then form v
+      for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) {
+        double t = 0.0;
+        for (int b = 0; b < NX; ++b) t += Jst[q][a * NZ + b] * Si[b];
+        if (i >= NX) t += Jst[q][a * NZ + i];
+        dKi[q * NX + a] = t;
+      }
+      tm_lu_solve(M, piv, dKi);
+    }
+    if (ORDER >= 2) {
+      for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) {
+        double t = 0.0;
+        for (int b = 0; b < NX; ++b) t += Jst[q][a * NZ + b] * Sj[b];
+        if (j >= NX) t += Jst[q][a * NZ + j];
+        dKj[q * NX + a] = t;
+      }
+      tm_lu_solve(M, piv, dKj);
+      for (int q = 0; q < 3; ++q) {
+        double vi[NZ], vj[NZ], dd[NX];
+        for (int a = 0; a < NX; ++a) {
+          double ti = Si[a], tj = Sj[a];
+          for (int l = 0; l < 3; ++l) { ti += h * A[q][l] * dKi[l * NX + a]; tj += h * A[q][l] * dKj[l * NX + a]; }
+          vi[a] = ti; vj[a] = tj;
+        }
+        for (int b = 0; b < NU; ++b) { vi[NX + b] = (i == NX + b) ? 1.0 : 0.0; vj[NX + b] = (j == NX + b) ? 1.0 : 0.0; }
+        tmpc_ode_bilin(Hst[q], vi, vj, dd);
+        for (int a = 0; a < NX; ++a) {
+          double t = dd[a];
+          for (int b = 0; b < NX; ++b) t += Jst[q][a * NZ + b] * T[b];
+          ddK[q * NX + a] = t;
+        }
+      }
+      tm_lu_solve(M, piv, ddK);
+    }
+    for (int a = 0; a < NX; ++a) {
+      for (int q = 0; q < 3; ++q) {
+        X[a] += h * A[2][q] * K[q][a];
+        if (ORDER >= 1) Si[a] += h * A[2][q] * dKi[q * NX + a];
+        if (ORDER >= 2) { Sj[a] += h * A[2][q] * dKj[q * NX + a]; T[a] += h * A[2][q] * ddK[q * NX + a]; }
+      }
+    }
+  }
+}
+#endif
+
 template <int ORDER>
 TM_HD void tm_integrate(const double* x0, const double* u, int i, int j, double* X, double* Si, double* Sj, double* T) {
 #pragma unroll
@@ -199,6 +331,8 @@ TM_HD void tm_integrate(const double* x0, const double* u, int i, int j, double*
       if (ORDER >= 2) { Sj[a] = dj[a]; T[a] = dd[a]; }
     }
   }
+#elif TMPC_COLLOCATION
+  tm_integrate_colloc<ORDER>(u, i, j, X, Si, Sj, T);
 #else
   const double h = TMPC_RK_DT;
   for (int s = 0; s < TMPC_RK_STEPS; ++s) {
@@ -386,6 +520,15 @@ TM_HD void tm_lin_group_exact(const double* x, const double* u, const double* la
 template <int G>
 TM_HD void tm_lin_group_gn(const double* x, const double* u, double* rec) {
   constexpr int ND = (NZ - 3 * G) < 3 ? (NZ - 3 * G) : 3;
+#if TMPC_COLLOCATION
+  for (int a = 0; a < ND; ++a) {                     // implicit integrator: one direction at a time
+    double Xc[NX], Sc[NX], t1[NX], t2[NX];
+    tm_integrate<1>(x, u, 3 * G + a, 3 * G + a, Xc, Sc, t1, t2);
+    for (int i = 0; i < NX; ++i) rec[NX + i * NZ + 3 * G + a] = Sc[i];
+    if (G == 0 && a == 0) for (int i = 0; i < NX; ++i) rec[i] = Xc[i];
+  }
+  return;
+#endif
   double X[NX], S[ND][NX], T[1][NX];
   tm_integrate_group<ND, 0>(x, u, [](int a) { return 3 * G + a; }, [](int) { return 0; }, [](int) { return 0; }, X, S, T);
 #pragma unroll

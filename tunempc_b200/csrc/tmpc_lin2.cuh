@@ -19,7 +19,7 @@
 #pragma once
 #include "tmpc_core.cuh"
 
-#if !TMPC_DISCRETE
+#if TMPC_RK4
 
 #define L2_NCW TMPC_L2_NCW
 #define L2_THREADS (32 * (1 + L2_NCW))
@@ -233,4 +233,4 @@ __global__ void __launch_bounds__(L2_THREADS, TMPC_L2_MINB) k_lin2(TmProb P, TmS
   }
 }
 
-#endif  // !TMPC_DISCRETE
+#endif  // TMPC_RK4

@@ -55,6 +55,7 @@ class OdeModel:
     rk_steps: int = 1        # CasADi 'rk' number_of_finite_elements
     tf: float = 1.0          # integrator horizon (one MPC interval)
     discrete: bool = False   # True: xdot IS the map x+ = f(x,u) (no integrator)
+    integrator: str = "rk4"  # 'rk4' (CasADi 'rk') or 'collocation' (CasADi 'collocation': Radau IIA, 3 nodes per element)
     hess_nz: List[tuple] = field(default_factory=list)
     cost: object = None      # economic stage cost l(x,u) (sympy), emitted as tmpc_stage_cost for the closed-loop log
 
@@ -185,6 +186,7 @@ def generate_header(model: OdeModel, out_path: str) -> dict:
     L.append('#define TMPC_MODEL_NAME "%s"' % model.name)
     L.append("#define TMPC_NX %d\n#define TMPC_NU %d\n#define TMPC_NZ %d" % (nx, nu, nz))
     L.append("#define TMPC_DISCRETE %d" % (1 if model.discrete else 0))
+    L.append("#define TMPC_COLLOCATION %d" % (1 if (model.integrator == "collocation" and not model.discrete) else 0))
     L.append("#define TMPC_RK_STEPS %d" % model.rk_steps)
     L.append("#define TMPC_RK_DT %s" % repr(float(model.tf) / model.rk_steps))
     L.append("#define TMPC_NHESS %d" % len(hess))

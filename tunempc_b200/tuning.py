@@ -63,6 +63,12 @@ def solve_steady_state(stage_F, cost_funs, C, c, z0, nx, tol=1e-12, lam_tresh=1e
     act = [i for i in range(nh) if (C @ z + c)[i] < 1e-6 * max(1.0, abs(c[i]))]
     lam_d = np.zeros(nx)
     lam_a = np.zeros(len(act))
+    if True:   # multiplier estimate from stationarity (a linear economic cost has no Hessian of its own: with lam = 0 the
+        # first KKT matrix would be singular)
+        _, Jd0 = dyn(z)
+        J0 = np.vstack([Jd0, C[act] if act else np.zeros((0, nz))])
+        le = np.linalg.lstsq(J0.T, -g_f(z), rcond=None)[0]
+        lam_d, lam_a = le[:nx].copy(), le[nx:].copy()
     for it in range(50):
         r_d, Jd = dyn(z)
         Ja = C[act] if act else np.zeros((0, nz))
