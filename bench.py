@@ -244,6 +244,21 @@ def main():
     if rank == 0:
         f_lin, f_dyn = algorithmic_flops_per_stage_lin(args.hessian == "exact")
         ach = (n_lin * f_lin) / (lin_ms * 1e-3) / 1e12 if lin_ms > 0 else 0.0
+        # DRAM traffic of the dominant kernels from the committed ncu --set full captures (profiles/r01d_summary.md):
+        # k_lin2 442.5 MB read + 973.1 MB written per launch of 131072 x 20 stage tasks; k_qp_thread 30.2 + 6.2 GB per
+        # launch of 131072 QPs.  Algorithmic bytes: a stage task reads (x,u,lam_dyn) and writes its 49-double record;
+        # a QP reads its N records + w and writes (d, lam).
+        lin_traffic_per_task = (442.472448e6 + 973.118976e6) / (131072 * 20)
+        lin_alg_bytes_per_task = 8.0 * (pb.nx + pb.nu + pb.nx) + 8.0 * (pb.nx + pb.nx * pb.nz + pb.nz * (pb.nz + 1) // 2)
+        qp_traffic_per_qp = (30.198128e9 + 6.205736e9) / 131072
+        qp_alg_bytes = 8.0 * (pb.N * (pb.nx + pb.nx * pb.nz + pb.nz * (pb.nz + 1) // 2) + 2 * pb.n_w + pb.n_g + pb.nx)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                hbm_peak = float(json.load(fh)["hbm_gbs"])
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            hbm_peak, hbm_src = 6550.0, "fallback (B200_PROFILING.md)"
+        qp_ach = n_qp * qp_alg_bytes / (qp_ms * 1e-3) / 1e9 if qp_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": world * B * K / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -256,12 +271,20 @@ def main():
                     "d2h_bytes_per_step": B * pb.nu * 8 + 3 * B * 4},
             "gpu_launches": int(n_launch),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "fp64", "kernel": "k_lin", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": ach / peak_tf if peak_tf else None, "traffic": None,
+            "roofline": {"bound": "fp64", "kernel": "k_lin2", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": ach / peak_tf if peak_tf else None,
+                         "traffic": lin_traffic_per_task * 32 * ((B * pb.N + 31) // 32),
+                         "traffic_note": "ncu dram read+write per full-batch launch (%.0f B per stage task measured at B=131072, "
+                                         "algorithmic %.0f B: DRAM traffic = the records)" % (lin_traffic_per_task, lin_alg_bytes_per_task),
                          "peak_source": "in-run DFMA micro-benchmark (tmpc_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                          "flops_per_stage_linearisation": f_lin, "stage_linearisations": int(n_lin),
                          "kernel_ms": {"k_lin": lin_ms, "k_qp": qp_ms, "k_post": post_ms, "step_total": ms_dev},
                          "hbm_GBps_boundary_io": (B * K * 8 * (pb.nx + pb.nu) + 0.0) / (ms_dev * 1e-3) / 1e9},
+            "roofline_qp": {"bound": "hbm", "kernel": "k_qp_thread (+ k_qp0, k_qp)", "achieved": qp_ach, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": qp_ach / hbm_peak, "traffic": qp_traffic_per_qp * B,
+                            "note": "algorithmic %.0f B per QP (records + w in, d + lam out); measured DRAM traffic %.0f B per QP: the "
+                                    "lane-interleaved Riccati / working-set workspace streams through HBM" % (qp_alg_bytes, qp_traffic_per_qp),
+                            "peak_source": hbm_src},
             "stats": {"sqp_iter_mean": n_it / (B * K), "qp_solves": int(n_qp), "ls_dynamics_evals": int(n_dyn),
                       "status_hist": [int(v) for v in stat_hist.tolist()], "flags_hist": [int(v) for v in fl_hist.tolist()]},
         }
