@@ -1,0 +1,157 @@
+"""Host-side mirror of the reference's user API `tunempc.Tuner` (`tunempc/tuner.py:39-264`).
+
+    tuner = Tuner(f, l, h, p)          # reference: CasADi Functions f (integrator), l, h ; here: a model card
+    wsol  = tuner.solve_ocp(w0)        # tuner.py:90-132   -> pocp.Pocp.solve
+    Hc    = tuner.convexify(rho=...)   # tuner.py:134-160  -> convexifier.convexify
+    ctrl  = tuner.create_mpc('tuned', N, opts)            # tuner.py:162-199 -> pmpc.Pmpc
+    ctrl.step(x0) / ctrl.step(X0)      # the batched CUDA solve (tunempc_b200.pmpc.Pmpc)
+
+CasADi is not available in this image, so `f`, `l`, `h` are given as a *model card*: a dict with the sympy ODE
+(`modelgen.OdeModel`), the sympy stage cost and the linear path constraints h(x,u) = C z + c >= 0 (see
+`tunempc_b200/configs.py`; every card restates one of the reference's example scripts).  Everything in this module runs
+once on the host (offline OCP solve and convexification: out of scope for CUDA); the
+controller it returns runs on the GPU through the C ABI and has no CPU fallback.
+"""
+from __future__ import annotations
+
+import copy
+import os
+
+import numpy as np
+
+from . import tuning
+from .problem import MpcProblem
+
+
+class Tuner(object):
+    def __init__(self, f, l=None, h=None, p=1, stage_eval=None):
+        """f: a model card (dict from `configs.<name>()`) or an `OdeModel`; l: sympy stage cost (default: the card's);
+        h: (C, c) of the linear path constraints h = C z + c >= 0 (default: the card's); p: period of the OCP.
+        stage_eval(x, u, order): host evaluation of the compiled model's interval map (default: the C-ABI library's
+        `tmpc_stage_eval_host`, which needs libtmpc_<model>.so but no GPU)."""
+        card = f if isinstance(f, dict) else {"model": f}
+        self.__card = card
+        self.__model = card["model"]
+        self.__l = l if l is not None else card.get("cost")
+        if self.__l is None:
+            raise ValueError("Tuner needs a stage cost l")
+        if h is not None:
+            self.__C, self.__c = np.atleast_2d(np.asarray(h[0], dtype=np.float64)), np.asarray(h[1], dtype=np.float64).ravel()
+        else:
+            self.__C = np.asarray(card.get("C", np.zeros((0, self.__model.nx + self.__model.nu))), dtype=np.float64)
+            self.__c = np.asarray(card.get("c", np.zeros(0)), dtype=np.float64)
+        self.__nx, self.__nu = self.__model.nx, self.__model.nu
+        self.__nw = self.__nx + self.__nu                                   # tuner.py:69
+        self.__p = int(p)
+        self.__cost_funs = tuning.lambdify_cost(self.__model, self.__l)
+        if stage_eval is None:
+            from .lib import ModelLib
+            stage_eval = ModelLib(self.__model.name).stage_eval
+        self.__F = stage_eval
+        self.__w_sol = None
+        self.__S = None
+        self.__lam_h = None
+        self.__lam_dyn = None
+
+    # ---- tuner.py:90-132 ---------------------------------------------------------------------------------
+    def solve_ocp(self, w0=None, lam0=None):
+        """p-periodic OCP (steady state for p = 1).  w0: flat (p*(nx+nu),) or (p, nx+nu) initial guess.  Returns the
+        solution as (p, nx+nu)."""
+        if w0 is None:
+            w0 = self.__card.get("w_guess")
+        w0 = np.asarray(w0, dtype=np.float64)
+        w0_shape = self.__p * self.__nw
+        assert w0.size == w0_shape, \
+            "Incorrect dimensions of input variable w0: expected {}x1, but received {}".format(w0_shape, w0.shape)
+        w0 = w0.reshape(self.__p, self.__nw)
+        if self.__p == 1:
+            z, lam_d, lam_h = tuning.solve_steady_state(self.__F, self.__cost_funs, self.__C, self.__c, w0[0], self.__nx)
+            self.__S = tuning.sensitivities(self.__F, self.__cost_funs, self.__C, z, lam_d, lam_h, self.__nx)
+            self.__w_sol = z[None, :].copy()
+            self.__lam_h, self.__lam_dyn = lam_h[None, :], lam_d[None, :]
+        else:
+            if self.__C.shape[0]:
+                raise NotImplementedError("periodic OCP with path constraints is not built yet")
+            z, lam_d, _ = tuning.solve_periodic_ocp(self.__F, self.__cost_funs, w0, self.__nx)
+            self.__S = tuning.sensitivities_periodic(self.__F, self.__cost_funs, z, lam_d, self.__nx)
+            self.__w_sol = z.copy()
+            self.__lam_h, self.__lam_dyn = np.zeros((self.__p, 0)), lam_d
+        return self.__w_sol
+
+    # ---- tuner.py:134-160 --------------------------------------------------------------------------------
+    def convexify(self, rho=1.0, force=False, solver="dare"):
+        """Positive definite stage cost matrices of a tracking NMPC scheme that is locally first-order equivalent to
+        economic MPC.  `solver` names the SDP back-end in the reference ('cvxopt' / 'mosek'); here the convexifying
+        storage-function change dP comes from a (periodic) Riccati + Lyapunov construction (tuning.py), any value is
+        accepted.  As in the reference (convexifier.py:80-84) an already positive definite H is returned unchanged;
+        `force` is accepted for signature compatibility and ignored."""
+        if self.__S is None:
+            raise RuntimeError("call solve_ocp() first")
+        S = self.__S
+        if self.__p == 1:
+            Hc = [tuning.convexify_dare(S["A"][0], S["B"][0], S["H"][0], C_As=S["C_As"][0], rho=rho, scale=self.__w_sol[0])[0]]
+        else:
+            Hc = tuning.convexify_periodic(S["A"], S["B"], S["H"])
+        S["Hc"] = Hc
+        return S["Hc"]
+
+    # ---- tuner.py:162-199 --------------------------------------------------------------------------------
+    def create_mpc(self, mpc_type, N, opts={}, tuning=None, device=0):
+        """Create an MPC controller of the given type and horizon.  'tuned': H = Hc, q = S['q']; 'tracking': user
+        tuning {'H': [...], 'q': [...]} (tuner.py:191-195).  'economic' is not built."""
+        if mpc_type not in ["economic", "tuned", "tracking"]:
+            raise ValueError("Provided MPC type not supported.")                           # tuner.py:168-169
+        if mpc_type == "economic":
+            raise NotImplementedError("economic MPC controller is not built yet (needs the exact-Hessian path with the "
+                                      "economic stage cost on the device)")
+        if self.__w_sol is None:
+            raise RuntimeError("call solve_ocp() first")
+        if mpc_type == "tracking":
+            if tuning is None:
+                raise ValueError("Tracking type MPC controller requires user-provided tuning!")   # tuner.py:193
+        elif mpc_type == "tuned":
+            if "Hc" not in self.__S:
+                raise RuntimeError("call convexify() first")
+            tuning = {"H": self.__S["Hc"], "q": self.__S["q"]}                              # tuner.py:195
+        from .pmpc import Pmpc
+        p = self.__p
+        Hs = [np.asarray(Hk, dtype=np.float64) for Hk in tuning["H"]]
+        qs = [np.asarray(qk, dtype=np.float64).ravel() for qk in tuning["q"]]
+        if len(Hs) == 1 and p > 1:
+            Hs = Hs * p
+        if len(qs) == 1 and p > 1:
+            qs = qs * p
+        opts = dict(opts)
+        term_idx = opts.pop("p_operator", None)
+        if term_idx is None:
+            term_idx = self.__card.get("term_idx", list(range(self.__nx)))
+        pb = MpcProblem(name=self.__model.name, nx=self.__nx, nu=self.__nu, N=int(N), p=p, wref=self.__w_sol.copy(),
+                        H=np.array(Hs), q=np.array(qs), C=self.__C, c=self.__c, lam_h_ref=self.__lam_h.copy(),
+                        lam_dyn_ref=np.zeros((p, self.__nx)),                               # tuner.py:186-189: lam_g0['dyn'] = 0
+                        term_idx=[int(i) for i in term_idx], S_A=np.array(self.__S["A"]), S_B=np.array(self.__S["B"]))
+        return Pmpc(pb, options=opts, device=device)
+
+    # ---- properties (tuner.py:201-264) -------------------------------------------------------------------
+    @property
+    def S(self):
+        return self.__S
+
+    @property
+    def sys(self):
+        return {"f": self.__model, "h": (self.__C, self.__c), "vars": {"x": self.__model.x, "u": self.__model.u}}
+
+    @property
+    def l(self):
+        return self.__cost_funs[0]
+
+    @property
+    def w_sol(self):
+        return self.__w_sol
+
+    @property
+    def lam_g(self):
+        return {"dyn": self.__lam_dyn, "h": self.__lam_h}
+
+    @property
+    def p(self):
+        return self.__p
