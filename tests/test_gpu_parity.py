@@ -257,3 +257,72 @@ def test_evaporation_golden(torch_mod, tag, tol):
             assert _relerr(Uc.cpu().numpy(), gold["cl_U"][:, s]) < 1e-6, s
             X = ctrl.plant_step(X, Uc)
             assert _relerr(X.cpu().numpy(), gold["cl_X"][:, s + 1]) < 1e-6, s
+
+
+def test_edge_cases(torch_mod):
+    """ragged / tiny / empty batches, infeasible and non-finite instances inside a batch, iteration cap, reset semantics"""
+    torch = torch_mod
+    from oracle import reference_port as rp
+    ctrl, pb = _ctrl("cstr")
+    gold = load_golden("cstr")
+    xs = pb.wref[0, :4]
+    # batch sizes that are not multiples of the warp / CTA sizes give the same per-instance answers
+    ref = None
+    for B in (1, 2, 31, 33, 47):
+        ctrl.reset(B)
+        U = ctrl.step(torch.tensor(gold["X0"][:B], device="cuda:0")).cpu().numpy()
+        assert U.shape == (B, 2) and (ctrl.status.cpu().numpy() == 0).all()
+        if ref is None:
+            ref = U[0]
+        assert np.array_equal(U[0], ref)                                         # independent of the neighbours: bitwise
+        assert _relerr(U, gold["u0_t6"][:B]) < 1e-6
+    # empty batch: no launch, empty outputs, the phase index still advances (pmpc.py:415)
+    ctrl.reset(0)
+    U = ctrl.step(torch.empty((0, 4), dtype=torch.float64, device="cuda:0"))
+    assert U.shape == (0, 2) and ctrl.index == 1
+    U = ctrl.step(np.empty((0, 4)))
+    assert U.shape == (0, 2) and ctrl.index == 2
+    # an infeasible and a non-finite instance do not disturb their neighbours: per-instance status instead of the
+    # reference's exception (CasADi conic raises on the infeasible QP; here status 2 / 4)
+    X0 = gold["X0"][:6].copy()
+    X0[2] = xs
+    X0[2, 0] += 2.5 * (1.0 - xs[0])                                              # negative concentration: terminal set unreachable
+    X0[4, 2] = np.nan
+    ctrl.reset(6)
+    U = ctrl.step(torch.tensor(X0, device="cuda:0")).cpu().numpy()
+    st = ctrl.status.cpu().numpy()
+    assert st[2] == 2 and st[4] == 4 and (st[[0, 1, 3, 5]] == 0).all()
+    assert _relerr(U[[0, 1, 3, 5]], gold["u0_t6"][[0, 1, 3, 5]]) < 1e-6
+    oc = rp.Pmpc(pb)
+    with pytest.raises(RuntimeError):
+        oc.step(X0[2])                                                           # the oracle's QP solver reports infeasibility
+    # iteration cap (sqp_method.py:281): status 1 after exactly max_iter iterations
+    c1, _ = _ctrl("cstr", max_iter=2)
+    c1.step(torch.tensor(gold["X0"][:8], device="cuda:0"))
+    it = c1.log["iter"][-1].cpu().numpy()
+    st = c1.status.cpu().numpy()
+    assert (it <= 2).all() and ((st == 1) == (gold["iter_t6"][:8] > 2)).sum() >= 6 and (it[st == 1] == 2).all()
+    # reset(): phase index and log cleared, warm start back at the reference (pmpc.py:858-865)
+    ctrl.reset(3)
+    a = ctrl.step(torch.tensor(gold["X0"][:3], device="cuda:0")).clone()
+    ctrl.step(torch.tensor(gold["X0"][3:6], device="cuda:0"))
+    assert ctrl.index == 2 and len(ctrl.log["u0"]) == 2
+    ctrl.reset()
+    assert ctrl.index == 0 and len(ctrl.log["u0"]) == 0
+    b = ctrl.step(torch.tensor(gold["X0"][:3], device="cuda:0"))
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        ctrl.step(torch.tensor(gold["X0"][:5], device="cuda:0"))                 # batch size change without reset()
+    with pytest.raises(TypeError):
+        ctrl.step(torch.tensor(gold["X0"][:3], device="cuda:0", dtype=torch.float32))
+
+
+def test_gauss_newton_other_configs(torch_mod):
+    """hessian_approximation='gauss_newton' (pmpc.py:327-333) on the collocation and the periodic config: same solution"""
+    torch = torch_mod
+    for name in ("evaporation", "unicycle"):
+        gold = load_golden(name)
+        c, pb = _ctrl(name, hessian_approximation="gauss_newton", tol=1e-9)
+        U = c.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
+        assert (c.status.cpu().numpy() == 0).all()
+        assert _relerr(U, gold["u0_t9"]) < 1e-6

@@ -553,7 +553,9 @@ extern "C" {
 int tmpc_reset(tmpc_handle* h, int64_t B) {
   if (!h) return 1;
   if (!h->tables_set) { h->err = "tmpc_reset: tables not set"; return 1; }
+  if (B < 0) { h->err = "tmpc_reset: negative batch size"; return 1; }
   cudaSetDevice(h->device);
+  if (B == 0) { h->index = 0; h->S.B = 0; h->uniform_ws = true; return 0; }
   if (ensure_capacity(h, B)) return 1;
   h->index = 0;
   h->S.B = B;
@@ -586,7 +588,9 @@ int tmpc_get_index(const tmpc_handle* h, int64_t* index) {
 int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, double* W_dev, double* LAM_dev,
               double* G_dev, int32_t* status_dev, int32_t* iter_dev, int32_t* flags_dev, void* cuda_stream) {
   if (!h) return 1;
+  if (B < 0) { h->err = "tmpc_step: negative batch size"; return 1; }
   if (!h->tables_set || h->cap < B || h->S.B != B) { h->err = "tmpc_step: call tmpc_reset(B) first"; return 1; }
+  if (B == 0) { h->index += 1; return 0; }                   // empty batch: nothing to solve, the phase still advances
   cudaSetDevice(h->device);
   cudaStream_t st = (cudaStream_t)cuda_stream;
   TmProb& P = h->P;
@@ -739,6 +743,7 @@ int tmpc_step_host(tmpc_handle* h, const double* X0_host, int64_t B, double* U0_
                    double* LAM_host, double* G_host, int32_t* status_host, int32_t* iter_host, int32_t* flags_host) {
   if (!h) return 1;
   if (h->cap < B) { h->err = "tmpc_step_host: call tmpc_reset(B) first"; return 1; }
+  if (B == 0) return tmpc_step(h, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   cudaSetDevice(h->device);
   TmProb& P = h->P;
   const size_t b = (size_t)B;

@@ -107,8 +107,7 @@ class Pmpc:
             self.__B = int(B)
         self.__index = 0
         self.__initialize_log()
-        if self.__B:
-            self.__check(self.__lib.lib.tmpc_reset(self.__h, self.__B))
+        self.__check(self.__lib.lib.tmpc_reset(self.__h, self.__B))
 
     def __ensure_batch(self, B):
         if B != self.__B:
@@ -185,6 +184,10 @@ class Pmpc:
     def __log_append(self, torch_dev=None):                           # pmpc.py:815-831
         o = self.__out
         lg = self.__log
+        if self.__B == 0:                                             # empty batch: nothing ran on the device
+            for k in _LOG_KEYS:
+                lg[k].append(o.get({"sol_x": "w"}.get(k, k)))
+            return
         lg["cpu"].append(self.timing()["step_ms"] * 1e-3)
         lg["iter"].append(o["iter"])
         lg["status"].append(o["status"])
