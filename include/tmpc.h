@@ -57,6 +57,8 @@ typedef struct {
   double reg_tol;          /* sqp_method.py:54 (1e-8): pivot threshold of the reduced-Hessian PD test */
   double term_penalty;     /* rho of the exact terminal penalty used inside the Riccati base factorisation */
   double al_gamma;         /* relative weight of the exact augmented-Lagrangian convexification on warm-start active rows (0 = off) */
+  int32_t economic;        /* 1: economic MPC -- stage cost = the compiled model's l(x,u), exact Hessian forced (pmpc.py:97-107,
+                              173-183, 299-301); 0: tuned / tracking cost from the H, q tables (mtools.py:43-57) */
 } tmpc_opts;
 
 void tmpc_default_opts(tmpc_opts* o);

@@ -260,6 +260,37 @@ class TrackingNlp:
         return Hm
 
 
+class EconomicNlp(TrackingNlp):
+    """economic MPC NLP (pmpc.py:97-107,173-183,299-301): same constraints, stage cost l(x_k,u_k) given as python callables
+    (l, grad l, hess l) of z = (x,u); the Hessian is always exact (pmpc.py:101-104)."""
+
+    def __init__(self, pb, cost_funs, stage=None):
+        super().__init__(pb, stage)
+        self.l_f, self.g_f, self.H_f = cost_funs
+
+    def f(self, w, p):
+        Z, _, _, _ = self._split(w)
+        return float(sum(self.l_f(Z[k]) for k in range(self.pb.N)))
+
+    def jacf(self, w, p):
+        pb = self.pb
+        Z, _, _, _ = self._split(w)
+        gr = np.zeros(pb.n_w)
+        for k in range(pb.N):
+            gr[pb.iz(k)] = self.g_f(Z[k])
+        return gr
+
+    def hess(self, w, p, lam, mode):
+        pb = self.pb
+        Z, _, _, _ = self._split(w)
+        Hm = np.zeros((pb.n_w, pb.n_w))
+        _, _, T2 = self.g(w, p, order=2)
+        for k in range(pb.N):
+            Hk = np.asarray(self.H_f(Z[k]), dtype=np.float64)
+            Hm[pb.iz(k), pb.iz(k)] = 0.5 * (Hk + Hk.T) + np.einsum("a,aij->ij", lam[pb.g_dyn(k)], T2[k])
+        return Hm
+
+
 # ------------------------------------------------------------------------------------------------------
 #  Sqp  (tunempc/sqp_method.py)
 # ------------------------------------------------------------------------------------------------------
@@ -384,12 +415,18 @@ class Sqp:
 #  Pmpc  (tunempc/pmpc.py) -- tracking/tuned type only
 # ------------------------------------------------------------------------------------------------------
 class Pmpc:
-    def __init__(self, pb, tables=None, qp="auto", sqp_options=None):
+    def __init__(self, pb, tables=None, qp="auto", sqp_options=None, cost_funs=None):
         from tunempc_b200.problem import build_tables   # host-side table builder (restates pmpc.py:676-783)
         self.pb = pb
         self.tab = tables if tables is not None else build_tables(pb)
-        self.nlp = TrackingNlp(pb)
-        so = {"hessian_approximation": pb.hessian_approximation, "max_iter": pb.max_iter, "tol": pb.tol}
+        if getattr(pb, "mpc_type", "tuned") == "economic":
+            if cost_funs is None:
+                raise ValueError("economic controller: pass cost_funs = (l, grad l, hess l)")
+            self.nlp = EconomicNlp(pb, cost_funs)
+        else:
+            self.nlp = TrackingNlp(pb)
+        so = {"hessian_approximation": "exact" if getattr(pb, "mpc_type", "tuned") == "economic" else pb.hessian_approximation,
+              "max_iter": pb.max_iter, "tol": pb.tol}
         so.update(sqp_options or {})
         self.sqp = Sqp(self.nlp, so, qp=qp)
         self.reset()

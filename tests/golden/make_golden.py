@@ -119,8 +119,36 @@ def evaporation():
     np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % name), **out)
 
 
+def economic():
+    """create_mpc('economic') (tuner.py:180-182; pmpc.py:97-107): stage cost l(x,u), exact Hessian, OCP multipliers as dual
+    reference -- the controller the tuned one is first-order equivalent to (closed_loop_tools.check_equivalence)."""
+    from tunempc_b200 import tuning
+    for name, B in (("cstr", 24), ("evaporation", 16)):
+        st = rp.StageLib(name)
+        pb, info = configs.make_problem(name, st.F, mpc_type="economic")
+        pb.save(os.path.join(HERE, "problem_%s_economic.npz" % name))
+        cf = tuning.lambdify_cost(info["cfg"]["model"], info["cfg"]["cost"])
+        X0 = sample_x0(name, pb, B)
+        out = {"X0": X0}
+        for tag, tol in (("t6", 1e-6), ("t9", 1e-9)):
+            ctrl = rp.Pmpc(pb, qp="qpoases", sqp_options={"tol": tol}, cost_funs=cf)
+            U, W, LAM, IT, ST, NAS = [], [], [], [], [], []
+            for b in range(B):
+                ctrl.reset()
+                u = ctrl.step(X0[b])
+                U.append(u); W.append(ctrl.w_sol); LAM.append(ctrl.lam_g)
+                IT.append(ctrl.log["iter"][-1]); ST.append(ctrl.log["status"][-1]); NAS.append(ctrl.log["nAS"][-1])
+            out.update({"u0_" + tag: np.array(U), "w_" + tag: np.array(W), "lam_" + tag: np.array(LAM),
+                        "iter_" + tag: np.array(IT), "status_" + tag: np.array(ST), "nAS_" + tag: np.array(NAS)})
+            print(name, "economic", tag, "iter hist", np.bincount(np.array(IT)), "status", np.bincount(np.array(ST)), "n_reg", ctrl.sqp.n_reg)
+        np.savez_compressed(os.path.join(HERE, "golden_%s_economic.npz" % name), **out)
+
+
 def main():
     rp.build()
+    if len(sys.argv) > 1 and sys.argv[1] == "economic":
+        economic()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "unicycle":
         unicycle()
         return
@@ -162,6 +190,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % name), **out)
     unicycle()
     evaporation()
+    economic()
 
 
 if __name__ == "__main__":

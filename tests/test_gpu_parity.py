@@ -326,3 +326,40 @@ def test_gauss_newton_other_configs(torch_mod):
         U = c.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
         assert (c.status.cpu().numpy() == 0).all()
         assert _relerr(U, gold["u0_t9"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["cstr", "evaporation"])
+def test_economic_controller(torch_mod, name):
+    """economic MPC (tuner.py:180-182, pmpc.py:97-107) on the device: golden outputs of the oracle, and the property the
+    whole reference is about -- the tuned tracking controller is first-order equivalent to the economic one at the
+    reference (closed_loop_tools.check_equivalence; paper eq. (6)): equal feedback slopes du0/dalpha as alpha -> 0."""
+    torch = torch_mod
+    from tunempc_b200 import closed_loop_tools as clt
+    ce, pe = _ctrl(name + "_economic")
+    gold = load_golden(name + "_economic")
+    U = ce.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
+    assert (ce.status.cpu().numpy() == 0).all()
+    assert _relerr(U, gold["u0_t6"]) < 1e-6
+    assert _relerr(ce.w_sol.cpu().numpy(), gold["w_t6"]) < 1e-5
+    lam = ce.lam_g.cpu().numpy()
+    for b in range(lam.shape[0]):
+        assert set(np.nonzero(lam[b])[0]) == set(np.nonzero(gold["lam_t6"][b])[0]), b
+    c9, _ = _ctrl(name + "_economic", tol=1e-9)
+    U9 = c9.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
+    assert (c9.status.cpu().numpy() == 0).all() and _relerr(U9, gold["u0_t9"]) < 1e-6
+    # first-order equivalence tuned <-> economic: sweep x0 = x_ref + alpha*dx for small alpha, compare slopes
+    ct, pt = _ctrl(name, tol=1e-10)
+    ce2, _ = _ctrl(name + "_economic", tol=1e-10)
+    xs = pt.wref[0, :pt.nx]
+    dx = np.zeros(pt.nx)
+    dx[-1 if name == "evaporation" else 0] = 1.0                                 # P2 (evaporation main.py:178-180) / cA
+    alpha = np.array([0.0, 1e-3, 2e-3])
+    lg = clt.check_equivalence({"tuned": ct, "economic": ce2}, None, None, xs, dx, alpha)
+    ut = lg["u"]["tuned"][:, 0].cpu().numpy()
+    ue = lg["u"]["economic"][:, 0].cpu().numpy()
+    assert np.allclose(ut[0], pt.wref[0, pt.nx:], rtol=1e-9) and np.allclose(ue[0], pt.wref[0, pt.nx:], rtol=1e-9)
+    st, se = (ut[1] - ut[0]) / alpha[1], (ue[1] - ue[0]) / alpha[1]
+    assert np.max(np.abs(st - se)) < 1e-3 * np.max(np.abs(se)), (st, se)          # equal slopes; what remains is O(alpha)
+    d1 = np.max(np.abs((ut[1] - ut[0]) - (ue[1] - ue[0])))
+    d2 = np.max(np.abs((ut[2] - ut[0]) - (ue[2] - ue[0])))
+    assert 3.5 < d2 / d1 < 4.5, (d1, d2)                                         # the difference is second order in alpha

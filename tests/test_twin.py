@@ -165,3 +165,26 @@ def test_twin_evaporation_collocation(env):
         o = tw.step(x)
         assert _relerr(o["u0"], gold["cl_U"][:, s]) < 1e-8, s
         x = st.F(x, o["u0"])
+
+
+def test_twin_economic_controller(env):
+    """create_mpc('economic') (tuner.py:180-182, pmpc.py:97-107): stage cost l(x,u) of the model card, exact Hessian,
+    non-zero dynamics multipliers in the dual reference.  Same converged points and active sets as the oracle."""
+    rp, build_tables, Twin = env
+    for name in ("cstr", "evaporation"):
+        pb, gold = load_problem(name + "_economic"), load_golden(name + "_economic")
+        assert pb.mpc_type == "economic" and np.abs(pb.lam_dyn_ref).max() > 0
+        n = gold["X0"].shape[0]
+        tw = Twin(pb, build_tables(pb), rho=3e7, al_gamma=1e3)
+        tw.reset(n)
+        o = tw.step(gold["X0"])
+        assert (o["status"] == 0).all()
+        assert _relerr(o["u0"], gold["u0_t6"]) < 1e-6 and _relerr(o["w"], gold["w_t6"]) < 1e-5
+        for b in range(n):
+            assert set(np.nonzero(o["lam"][b])[0]) == set(np.nonzero(gold["lam_t6"][b])[0]), (name, b)
+        clean = (o["flags"] & 1) == 0
+        assert np.array_equal(o["iter"][clean], gold["iter_t6"][clean])
+        # at the reference the economic controller returns the reference input in one iteration (P1)
+        tw.reset(1)
+        o = tw.step(pb.wref[0, :pb.nx][None])
+        assert o["iter"][0] == 1 and np.allclose(o["u0"][0], pb.wref[0, pb.nx:], rtol=1e-9)

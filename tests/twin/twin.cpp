@@ -41,7 +41,7 @@ void twin_stage_eval(int n, const double* x, const double* u, int order, double*
   }
 }
 
-// dims: N nh nxt p ; iopts: hessian_exact max_iter max_ls maxact ; dopts: tol lam_tresh beta reg_tol rho al_gamma
+// dims: N nh nxt p ; iopts: hessian_exact max_iter max_ls maxact economic ; dopts: tol lam_tresh beta reg_tol rho al_gamma
 int twin_step(const int* dims, const int* iopts, const double* dopts, const double* wref, const double* H,
               const double* q, const double* ref_du, const double* C, const double* c, const int* term_idx,
               const int* relax0, int phase, long long B, const double* X0, double* W, double* LAM, double* G,
@@ -56,6 +56,8 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
   P.max_iter = iopts[1] < P.filter_cap - 1 ? iopts[1] : P.filter_cap - 1;
   P.max_ls = iopts[2];
   P.maxact = iopts[3];
+  P.economic = iopts[4];
+  if (P.economic) P.hessian_exact = 1;
   P.tol = dopts[0]; P.lam_tresh = dopts[1]; P.beta = dopts[2]; P.reg_tol = dopts[3]; P.rho = dopts[4]; P.al_gamma = dopts[5];
   P.wref = wref; P.H = H; P.q = q; P.ref_du = ref_du; P.C = C; P.c = c; P.term_idx = term_idx; P.relax0 = relax0;
   TmState S;

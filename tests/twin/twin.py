@@ -60,7 +60,8 @@ class Twin:
         assert B == self.B
         dims = np.array([pb.N, pb.nh, pb.nx_term, pb.p], dtype=np.int32)
         hm = pb.hessian_approximation if hessian is None else hessian
-        iopts = np.array([1 if hm == "exact" else 0, pb.max_iter, 300, self.maxact], dtype=np.int32)
+        iopts = np.array([1 if hm == "exact" else 0, pb.max_iter, 300, self.maxact,
+                          1 if getattr(pb, "mpc_type", "tuned") == "economic" else 0], dtype=np.int32)
         dopts = np.array([pb.tol if tol is None else tol, 1e-8, 0.8, 1e-8, self.rho, self.al_gamma], dtype=np.float64)
         Hs = np.ascontiguousarray(0.5 * (pb.H + np.transpose(pb.H, (0, 2, 1))))
         relax0 = np.zeros(max(pb.nh, 1), dtype=np.int32)

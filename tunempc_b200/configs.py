@@ -124,7 +124,7 @@ def evaporation():
 CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle, "evaporation": evaporation}
 
 
-def make_problem(name, stage_F, N=None, hessian_approximation="exact"):
+def make_problem(name, stage_F, N=None, hessian_approximation="exact", mpc_type="tuned"):
     """Run the offline pipeline (tuning.py) for a config and return (MpcProblem, info).
 
     `stage_F(x, u, order)` evaluates the compiled model's one-interval map and derivatives on the host
@@ -165,4 +165,11 @@ def make_problem(name, stage_F, N=None, hessian_approximation="exact"):
                     hessian_approximation=hessian_approximation)
     info = {"z_ss": z, "lam_dyn_ocp": lam_d, "lam_h_ocp": lam_h, "H_ocp": S["H"][0], "Hc": Hc,
             "eig_H": np.linalg.eigvalsh(S["H"][0]), "eig_Hc": np.linalg.eigvalsh(Hc), "cfg": cfg}
+    if mpc_type == "economic":
+        # create_mpc('economic') (tuner.py:180-182): cost = l, full OCP multipliers as dual reference, no tuning tables
+        pb.mpc_type = "economic"
+        pb.hessian_approximation = "exact"                               # pmpc.py:101-104
+        pb.lam_dyn_ref = lam_d[None, :].copy()
+        pb.H = np.zeros_like(pb.H)
+        pb.q = np.zeros_like(pb.q)
     return pb, info

@@ -340,6 +340,7 @@ void tmpc_default_opts(tmpc_opts* o) {
   o->reg_tol = 1e-8;
   o->term_penalty = 3e7;   // 1e7..1e8: below, marginally convex reduced Hessians fail the base factorisation; above, round-off (profiles/r01c_summary.md)
   o->al_gamma = 1e3;
+  o->economic = 0;
 }
 
 const char* tmpc_model_info(int32_t* nx, int32_t* nu, int32_t* rk_steps, double* dt) {
@@ -378,7 +379,8 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
   P.N = dims->N; P.nh = dims->nh; P.nxt = dims->nx_term; P.p = dims->p;
   P.n_w = dims->N * NZ + NX;
   P.n_g = NX + dims->N * (NX + dims->nh) + dims->nx_term;
-  P.hessian_exact = h->opts.hessian_exact;
+  P.economic = h->opts.economic ? 1 : 0;
+  P.hessian_exact = (h->opts.hessian_exact || P.economic) ? 1 : 0;   // economic MPC: exact Hessian forced (pmpc.py:97-107)
   P.filter_cap = 64;
   P.max_iter = h->opts.max_iter < P.filter_cap - 1 ? h->opts.max_iter : P.filter_cap - 1;
   P.max_ls = h->opts.max_ls_iter;

@@ -101,6 +101,7 @@ TM_HD TmP tm_mkp(double* base, size_t off) { return base + off; }
 struct TmProb {
   int N, nh, nxt, p, n_w, n_g;
   int hessian_exact, max_iter, max_ls, filter_cap, maxact;
+  int economic;           // 1: stage cost = the model card's l(x,u) (economic MPC, pmpc.py:97-107), 0: tuned tracking cost (mtools.py:43-57)
   double tol, lam_tresh, beta, reg_tol, rho, al_gamma;
   const double *wref, *H, *q, *ref_du, *C, *c;   // wref p*nz | H p*nz*nz (symmetric) | q p*nz | ref_du p*n_g | C nh*nz | c nh
   const int *term_idx, *relax0;
@@ -1089,22 +1090,41 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   // ---- A. stage data ------------------------------------------------------------------------------------------
   for (int e = lane; e < N * NX * NZ; e += TM_NL) { int k = e / (NX * NZ), o = e % (NX * NZ); s.AB[e] = lin[(size_t)k * TM_LSZ + NX + o]; }
   for (int e = lane; e < N * NX; e += TM_NL) { int k = e / NX, a = e % NX; s.b[e] = lin[(size_t)k * TM_LSZ + a] - w[(k + 1) * NZ + a]; }
-  for (int e = lane; e < N * NZ * NZ; e += TM_NL) {
-    int k = e / (NZ * NZ), o = e % (NZ * NZ), i = o / NZ, j = o % NZ;
-    int ph = (S.phase + k) % P.p;
-    double v = P.H[(size_t)ph * NZ * NZ + o];
-    if (use_exact) v += lin[(size_t)k * TM_LSZ + NX + NX * NZ + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
-    s.Q[e] = v;
-  }
-  for (int e = lane; e < N * NZ; e += TM_NL) {
-    int k = e / NZ, i = e % NZ;
-    int ph = (S.phase + k) % P.p;
-    const double* Hk = P.H + (size_t)ph * NZ * NZ + (size_t)i * NZ;
-    const double* wr = P.wref + (size_t)ph * NZ;
-    double v = P.q[(size_t)ph * NZ + i];
+  if (P.economic) {
+    // economic stage cost: Q_k = d2l/dz2 (+ lam' d2F), r_k = dl/dz at the iterate
+    for (int k = lane; k < N; k += TM_NL) {
+      double z[NZ], gl[NZ], Hl[NZ * NZ];
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) v += Hk[j] * (w[k * NZ + j] - wr[j]);
-    s.r[e] = v;
+      for (int b = 0; b < NZ; ++b) z[b] = w[k * NZ + b];
+      tmpc_cost_grad(z, z + NX, gl);
+      tmpc_cost_hess(z, z + NX, Hl);
+      for (int i = 0; i < NZ; ++i) {
+        for (int j = 0; j < NZ; ++j) {
+          double v = 0.5 * (Hl[i * NZ + j] + Hl[j * NZ + i]);
+          if (use_exact) v += lin[(size_t)k * TM_LSZ + NX + NX * NZ + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
+          s.Q[(size_t)k * NZ * NZ + i * NZ + j] = v;
+        }
+        s.r[k * NZ + i] = gl[i];
+      }
+    }
+  } else {
+    for (int e = lane; e < N * NZ * NZ; e += TM_NL) {
+      int k = e / (NZ * NZ), o = e % (NZ * NZ), i = o / NZ, j = o % NZ;
+      int ph = (S.phase + k) % P.p;
+      double v = P.H[(size_t)ph * NZ * NZ + o];
+      if (use_exact) v += lin[(size_t)k * TM_LSZ + NX + NX * NZ + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
+      s.Q[e] = v;
+    }
+    for (int e = lane; e < N * NZ; e += TM_NL) {
+      int k = e / NZ, i = e % NZ;
+      int ph = (S.phase + k) % P.p;
+      const double* Hk = P.H + (size_t)ph * NZ * NZ + (size_t)i * NZ;
+      const double* wr = P.wref + (size_t)ph * NZ;
+      double v = P.q[(size_t)ph * NZ + i];
+#pragma unroll
+      for (int j = 0; j < NZ; ++j) v += Hk[j] * (w[k * NZ + j] - wr[j]);
+      s.r[e] = v;
+    }
   }
   for (int a = lane; a < NZ; a += TM_NL) s.r[N * NZ + a] = 0.0;
   for (int e = lane; e < N * nh; e += TM_NL) {
@@ -1553,12 +1573,16 @@ TM_HD void tm_eval_point(const TmProb& P, const TmState& S, int64_t inst, double
 #pragma unroll
     for (int b = 0; b < NZ; ++b) dz[b] = z[b] - wr[b];
     double fk = 0.0;
+    if (P.economic) {
+      fk = tmpc_stage_cost(z, z + NX);
+    } else {
 #pragma unroll
-    for (int a = 0; a < NZ; ++a) {
-      double t = 0.0;
+      for (int a = 0; a < NZ; ++a) {
+        double t = 0.0;
 #pragma unroll
-      for (int b = 0; b < NZ; ++b) t += Hk[a * NZ + b] * dz[b];
-      fk += dz[a] * (0.5 * t + qk[a]);
+        for (int b = 0; b < NZ; ++b) t += Hk[a * NZ + b] * dz[b];
+        fk += dz[a] * (0.5 * t + qk[a]);
+      }
     }
     f += fk;
 #pragma unroll
@@ -1611,14 +1635,22 @@ TM_HD double tm_dual_infeas(const TmProb& P, const TmState& S, int64_t inst) {
     const double* AB = lin + (size_t)k * TM_LSZ + NX;
     const double* ld = lam + tm_gdyn(P, k);
     const double* lh = lam + tm_gh(P, k);
-    double dz[NZ];
+    double dz[NZ], gl[NZ];
 #pragma unroll
     for (int b = 0; b < NZ; ++b) dz[b] = w[k * NZ + b] - wr[b];
+    if (P.economic) {
+      double z[NZ];
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) z[b] = w[k * NZ + b];
+      tmpc_cost_grad(z, z + NX, gl);
+    }
 #pragma unroll
     for (int a = 0; a < NZ; ++a) {
-      double v = qk[a];
+      double v = P.economic ? gl[a] : qk[a];
+      if (!P.economic) {
 #pragma unroll
-      for (int b = 0; b < NZ; ++b) v += Hk[a * NZ + b] * dz[b];
+        for (int b = 0; b < NZ; ++b) v += Hk[a * NZ + b] * dz[b];
+      }
 #pragma unroll
       for (int i = 0; i < NX; ++i) v += AB[i * NZ + a] * ld[i];
       for (int i = 0; i < nh; ++i) v += P.C[(size_t)i * NZ + a] * lh[i];

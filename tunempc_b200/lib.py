@@ -33,7 +33,8 @@ class TmpcDims(ctypes.Structure):
 class TmpcOpts(ctypes.Structure):
     _fields_ = [("hessian_exact", ctypes.c_int32), ("max_iter", ctypes.c_int32), ("max_ls_iter", ctypes.c_int32),
                 ("tol", ctypes.c_double), ("lam_tresh", ctypes.c_double), ("ls_step_factor", ctypes.c_double),
-                ("reg_tol", ctypes.c_double), ("term_penalty", ctypes.c_double), ("al_gamma", ctypes.c_double)]
+                ("reg_tol", ctypes.c_double), ("term_penalty", ctypes.c_double), ("al_gamma", ctypes.c_double),
+                ("economic", ctypes.c_int32)]
 
 
 def lib_path(name):

@@ -293,6 +293,22 @@ def generate_header(model: OdeModel, out_path: str) -> dict:
         _emit_block(L, None, [("l", S(model.cost))])
     L.append("  return l;")
     L.append("}")
+    # gradient and Hessian of l w.r.t. z = (x,u): the economic-MPC stage cost on the device (pmpc.py:97-107,299-301)
+    L.append("TMPC_HD void tmpc_cost_grad(const double* x, const double* u, double* g) {")
+    L.append("  (void)x; (void)u;")
+    if model.cost is not None:
+        cg = [sp.diff(model.cost, zz) for zz in z]
+        _emit_block(L, None, [("g[%d]" % i, S(cg[i])) for i in range(nz)])
+    else:
+        L.append("  for (int i = 0; i < %d; ++i) g[i] = 0.0;" % nz)
+    L.append("}")
+    L.append("TMPC_HD void tmpc_cost_hess(const double* x, const double* u, double* H) {")
+    L.append("  (void)x; (void)u;")
+    if model.cost is not None:
+        _emit_block(L, None, [("H[%d]" % (i * nz + j), S(sp.diff(model.cost, z[i], z[j]))) for i in range(nz) for j in range(nz)])
+    else:
+        L.append("  for (int i = 0; i < %d; ++i) H[i] = 0.0;" % (nz * nz))
+    L.append("}")
     c_B = sum(3 if b == c else 5 for _, b, c, _ in hess)
     L.append("#define TMPC_OPS_F %d\n#define TMPC_OPS_J %d\n#define TMPC_OPS_H %d\n#define TMPC_OPS_BILIN %d" % (c_f, c_J, c_H, c_B))
     L.append("#endif")

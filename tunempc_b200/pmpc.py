@@ -58,6 +58,7 @@ class Pmpc:
         dims = TmpcDims(problem.nx, problem.nu, problem.nh, problem.nx_term, problem.N, problem.p)
         o = self.__lib.default_opts()
         o.hessian_exact = 1 if problem.hessian_approximation == "exact" else 0
+        o.economic = 1 if problem.mpc_type == "economic" else 0          # pmpc.py:97-107: exact Hessian forced
         o.max_iter = int(problem.max_iter)
         o.tol = float(problem.tol)
         for k, v in (solver_options or {}).items():

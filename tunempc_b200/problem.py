@@ -38,6 +38,7 @@ class MpcProblem:
     hessian_approximation: str = "exact"   # pmpc.py:153
     max_iter: int = 2000                   # pmpc.py:155
     tol: float = 1e-6                      # sqp_method.py:55
+    mpc_type: str = "tuned"                # 'tuned' / 'tracking' (cost from H, q) or 'economic' (cost = the model card's l)
     meta: dict = field(default_factory=dict)
 
     # ---- sizes -----------------------------------------------------------------------------------
@@ -117,7 +118,8 @@ class MpcProblem:
                  term_idx=np.array(self.term_idx, dtype=np.int64),
                  S_A=self.S_A if self.S_A is not None else np.zeros(0),
                  S_B=self.S_B if self.S_B is not None else np.zeros(0),
-                 hessian_approximation=self.hessian_approximation, max_iter=self.max_iter, tol=self.tol)
+                 hessian_approximation=self.hessian_approximation, max_iter=self.max_iter, tol=self.tol,
+                 mpc_type=self.mpc_type)
 
     @staticmethod
     def load(path):
@@ -127,7 +129,7 @@ class MpcProblem:
                           lam_dyn_ref=d["lam_dyn_ref"], term_idx=[int(i) for i in d["term_idx"]],
                           S_A=d["S_A"] if d["S_A"].size else None, S_B=d["S_B"] if d["S_B"].size else None,
                           hessian_approximation=str(d["hessian_approximation"]), max_iter=int(d["max_iter"]),
-                          tol=float(d["tol"]))
+                          tol=float(d["tol"]), mpc_type=str(d["mpc_type"]) if "mpc_type" in d else "tuned")
 
 
 @dataclass

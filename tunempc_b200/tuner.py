@@ -98,14 +98,14 @@ class Tuner(object):
     # ---- tuner.py:162-199 --------------------------------------------------------------------------------
     def create_mpc(self, mpc_type, N, opts={}, tuning=None, device=0):
         """Create an MPC controller of the given type and horizon.  'tuned': H = Hc, q = S['q']; 'tracking': user
-        tuning {'H': [...], 'q': [...]} (tuner.py:191-195).  'economic' is not built."""
+        tuning {'H': [...], 'q': [...]} (tuner.py:191-195); 'economic': the stage cost l itself with the OCP's multipliers as
+        dual reference and the exact Hessian (tuner.py:180-182, pmpc.py:97-107), p = 1 only."""
         if mpc_type not in ["economic", "tuned", "tracking"]:
             raise ValueError("Provided MPC type not supported.")                           # tuner.py:168-169
-        if mpc_type == "economic":
-            raise NotImplementedError("economic MPC controller is not built yet (needs the exact-Hessian path with the "
-                                      "economic stage cost on the device)")
         if self.__w_sol is None:
             raise RuntimeError("call solve_ocp() first")
+        if mpc_type == "economic" and self.__p != 1:
+            raise NotImplementedError("economic MPC on a periodic reference is not built yet")
         if mpc_type == "tracking":
             if tuning is None:
                 raise ValueError("Tracking type MPC controller requires user-provided tuning!")   # tuner.py:193
@@ -115,6 +115,9 @@ class Tuner(object):
             tuning = {"H": self.__S["Hc"], "q": self.__S["q"]}                              # tuner.py:195
         from .pmpc import Pmpc
         p = self.__p
+        if mpc_type == "economic":                                                           # tuner.py:180-182
+            nz = self.__nw
+            tuning = {"H": [np.zeros((nz, nz))] * p, "q": [np.zeros(nz)] * p}
         Hs = [np.asarray(Hk, dtype=np.float64) for Hk in tuning["H"]]
         qs = [np.asarray(qk, dtype=np.float64).ravel() for qk in tuning["q"]]
         if len(Hs) == 1 and p > 1:
@@ -127,8 +130,10 @@ class Tuner(object):
             term_idx = self.__card.get("term_idx", list(range(self.__nx)))
         pb = MpcProblem(name=self.__model.name, nx=self.__nx, nu=self.__nu, N=int(N), p=p, wref=self.__w_sol.copy(),
                         H=np.array(Hs), q=np.array(qs), C=self.__C, c=self.__c, lam_h_ref=self.__lam_h.copy(),
-                        lam_dyn_ref=np.zeros((p, self.__nx)),                               # tuner.py:186-189: lam_g0['dyn'] = 0
-                        term_idx=[int(i) for i in term_idx], S_A=np.array(self.__S["A"]), S_B=np.array(self.__S["B"]))
+                        lam_dyn_ref=(self.__lam_dyn.copy() if mpc_type == "economic"          # tuner.py:180-182: full lam_g
+                                     else np.zeros((p, self.__nx))),                        # tuner.py:186-189: lam_g0['dyn'] = 0
+                        term_idx=[int(i) for i in term_idx], S_A=np.array(self.__S["A"]), S_B=np.array(self.__S["B"]),
+                        mpc_type="economic" if mpc_type == "economic" else "tuned")
         return Pmpc(pb, options=opts, device=device)
 
     # ---- properties (tuner.py:201-264) -------------------------------------------------------------------
