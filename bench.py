@@ -114,7 +114,7 @@ def run_reference_arm(args):
     from oracle import reference_port as rp
     rp.build(("cstr",))
     cores = len(os.sched_getaffinity(0))
-    per_core = 3
+    per_core = 6                                   # ~2 s of CPU work per core and step
     n = cores * per_core
     chunks = [(list(range(c, n, cores)), 1000) for c in range(cores)]
     ctx = mp.get_context("fork")
@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=1 << 20, help="instances per GPU per step")
     ap.add_argument("--hessian", default="exact")
-    ap.add_argument("--cpu-sample", type=int, default=12)
+    ap.add_argument("--cpu-sample", type=int, default=40, help="x0 of the batch timed on the CPU oracle port (about 12 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
