@@ -1859,7 +1859,8 @@ struct TmQp0Tab {
 // returns 0 ok / 2 not solved here (overflow, dependent rows, breakdown): the caller queues the instance for tm_qp
 TM_HD int tm_qp0_gi(const TmProb& P, const TmQp0Tab& T, const double* e0, int* acte, double* nu, int& m_out, int& ngi_out) {
   const int EI = T.EI, EIs = T.EIs, nh = P.nh;
-  double Lf[TM_Q0_MAXM * TM_Q0_MAXM], cA[TM_Q0_MAXM], rv[TM_Q0_MAXM];
+  double Lf[TM_Q0_MAXM * (TM_Q0_MAXM + 1) / 2], cA[TM_Q0_MAXM], rv[TM_Q0_MAXM];   // Lf: packed lower triangle
+#define TM_LF(i, j) Lf[(i) * ((i) + 1) / 2 + (j)]
   int m = 0, ngi = 0;
   m_out = 0; ngi_out = 0;
   const int maxit = 4 * EI + 8;
@@ -1891,15 +1892,15 @@ TM_HD int tm_qp0_gi(const TmProb& P, const TmQp0Tab& T, const double* e0, int* a
       double ll = 0.0;
       for (int i = 0; i < m; ++i) {
         double v = T.MCOL[(size_t)qe * EIs + acte[i]];
-        for (int l = 0; l < i; ++l) v -= Lf[i * TM_Q0_MAXM + l] * cA[l];
-        v /= Lf[i * TM_Q0_MAXM + i];
+        for (int l = 0; l < i; ++l) v -= TM_LF(i, l) * cA[l];
+        v /= TM_LF(i, i);
         cA[i] = v;
         ll += v * v;
       }
       for (int i = m - 1; i >= 0; --i) {
         double v = cA[i];
-        for (int l = i + 1; l < m; ++l) v -= Lf[l * TM_Q0_MAXM + i] * rv[l];
-        rv[i] = v / Lf[i * TM_Q0_MAXM + i];
+        for (int l = i + 1; l < m; ++l) v -= TM_LF(l, i) * rv[l];
+        rv[i] = v / TM_LF(i, i);
       }
       const double zn = yq - ll;
       double t1 = TM_INF;
@@ -1921,8 +1922,8 @@ TM_HD int tm_qp0_gi(const TmProb& P, const TmQp0Tab& T, const double* e0, int* a
       for (int j = 0; j < m; ++j) nu[j] -= t * rv[j];
       nq += t;
       if (do_add) {
-        for (int l = 0; l < m; ++l) Lf[m * TM_Q0_MAXM + l] = cA[l];
-        Lf[m * TM_Q0_MAXM + m] = sqrt(zn);
+        for (int l = 0; l < m; ++l) TM_LF(m, l) = cA[l];
+        TM_LF(m, m) = sqrt(zn);
         acte[m] = qe; nu[m] = nq;
         ++m;
         added = 1;
@@ -1931,17 +1932,17 @@ TM_HD int tm_qp0_gi(const TmProb& P, const TmQp0Tab& T, const double* e0, int* a
       for (int a = jd; a < m - 1; ++a) { acte[a] = acte[a + 1]; nu[a] = nu[a + 1]; }
       --m;
       for (int i = 0; i < m; ++i)
-        for (int j = 0; j <= i; ++j) Lf[i * TM_Q0_MAXM + j] = T.MCOL[(size_t)acte[j] * EIs + acte[i]];
+        for (int j = 0; j <= i; ++j) TM_LF(i, j) = T.MCOL[(size_t)acte[j] * EIs + acte[i]];
       for (int c = 0; c < m; ++c) {
-        double dg = Lf[c * TM_Q0_MAXM + c];
-        for (int l = 0; l < c; ++l) dg -= Lf[c * TM_Q0_MAXM + l] * Lf[c * TM_Q0_MAXM + l];
+        double dg = TM_LF(c, c);
+        for (int l = 0; l < c; ++l) dg -= TM_LF(c, l) * TM_LF(c, l);
         if (!(dg > 0.0)) return 2;
         const double ld = sqrt(dg);
-        Lf[c * TM_Q0_MAXM + c] = ld;
+        TM_LF(c, c) = ld;
         for (int i = c + 1; i < m; ++i) {
-          double v = Lf[i * TM_Q0_MAXM + c];
-          for (int l = 0; l < c; ++l) v -= Lf[i * TM_Q0_MAXM + l] * Lf[c * TM_Q0_MAXM + l];
-          Lf[i * TM_Q0_MAXM + c] = v / ld;
+          double v = TM_LF(i, c);
+          for (int l = 0; l < c; ++l) v -= TM_LF(i, l) * TM_LF(c, l);
+          TM_LF(i, c) = v / ld;
         }
       }
     }
@@ -1951,6 +1952,7 @@ TM_HD int tm_qp0_gi(const TmProb& P, const TmQp0Tab& T, const double* e0, int* a
   m_out = m; ngi_out = ngi;
   return 0;
 }
+#undef TM_LF
 
 // (d, lam)[i] of one instance from the tables: element i of  TAB[0] + sum_a e0_a TAB[1+a] + sum_j nu_j TAB[1+NX+acte_j]
 TM_HD double tm_qp0_combine(const TmQp0Tab& T, int i, const double* e0, const int* acte, const double* nu, int m) {

@@ -13,8 +13,11 @@
 #include "tmpc_core.cuh"
 
 #define QT_THREADS 128
+#ifndef QT_MINB
+#define QT_MINB 4          /* resident CTAs / SM the register allocation aims for (128 registers at 4) */
+#endif
 
-__global__ void __launch_bounds__(QT_THREADS) k_qp_thread(TmProb P, TmState S, const int* list, int cnt, const int* cnt_dev,
+__global__ void __launch_bounds__(QT_THREADS, QT_MINB) k_qp_thread(TmProb P, TmState S, const int* list, int cnt, const int* cnt_dev,
                                                           double* wsbase, size_t ws_per_inst, int* work_counter) {
   if (cnt_dev) cnt = *cnt_dev;
   const int lane = threadIdx.x & 31;
