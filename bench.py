@@ -17,6 +17,11 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # CPU arm: one single-threaded worker process per core -- keep the BLAS / OpenMP pools from oversubscribing the box
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_v] = "1"
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -94,14 +99,16 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------------------
 def _oracle_worker(args):
     idx_list, seed = args
+    from threadpoolctl import threadpool_limits
     from oracle import reference_port as rp
     pb = load_problem()
     ctrl = rp.Pmpc(pb)
     X0 = sample_x0(pb, max(idx_list) + 1, seed)
     t = time.perf_counter()
-    for i in idx_list:
-        ctrl.reset()                                   # closed_loop_tools.py:68
-        ctrl.step(X0[i])                               # closed_loop_tools.py:56
+    with threadpool_limits(limits=1):
+        for i in idx_list:
+            ctrl.reset()                                   # closed_loop_tools.py:68
+            ctrl.step(X0[i])                               # closed_loop_tools.py:56
     return time.perf_counter() - t, len(idx_list)
 
 
@@ -294,11 +301,13 @@ def main():
             oc = rp.Pmpc(load_problem())
             n = args.cpu_sample
             xs = x_np[0][:n]
-            t0 = time.perf_counter()
-            for i in range(n):
-                oc.reset()
-                oc.step(xs[i])
-            dt = time.perf_counter() - t0
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=1):              # "cores": 1 means one thread, BLAS included
+                t0 = time.perf_counter()
+                for i in range(n):
+                    oc.reset()
+                    oc.step(xs[i])
+                dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": "first %d x0 of the same batch, oracle port (numpy + C stage functions + qpOASES_e)" % n}
         except Exception as e:   # the oracle is a checker, its absence must not hide the GPU number
