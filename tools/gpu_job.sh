@@ -1,12 +1,12 @@
 #!/bin/bash
-# experiment: occupancy of the thread-per-instance QP kernel (register cap 128 / 80 / 64 -> 512 / 768 / 1024 threads per SM)
-run() { python bench.py --steps 2 --warmup 3 --cpu-sample 1 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$1', round(d['value']), d['roofline']['kernel_ms'])"; }
-cp tunempc_b200/libtmpc_cstr.so /tmp/base.so
-TMPC_QP_THREADS_PER_SM=512 run base512
-cp tunempc_b200/exp_minb6.so tunempc_b200/libtmpc_cstr.so
-TMPC_QP_THREADS_PER_SM=768 run minb6_768
-cp tunempc_b200/exp_minb8.so tunempc_b200/libtmpc_cstr.so
-TMPC_QP_THREADS_PER_SM=1024 run minb8_1024
-TMPC_QP_THREADS_PER_SM=768 run minb8_768
-cp /tmp/base.so tunempc_b200/libtmpc_cstr.so
+# round-1 capture D: launch list + full captures of the production kernels (profiles/r01d_summary.md)
+set -x
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r01d_launches.csv \
+    python bench.py --batch 131072 --steps 1 --warmup 3 --cpu-sample 1 > gpurun_out/r01d_launch_run.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_qp0$' -s 0 -c 1 -f -o gpurun_out/r01d_prof \
+    python bench.py --batch 131072 --steps 1 --warmup 3 --cpu-sample 1 > gpurun_out/r01d_prof_run.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_lin2 -s 1 -c 1 -f -o gpurun_out/r01d_lin2 \
+    python bench.py --batch 131072 --steps 1 --warmup 3 --cpu-sample 1 > gpurun_out/r01d_lin2_run.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_qp_thread -s 4 -c 1 -f -o gpurun_out/r01d_qpt \
+    python bench.py --batch 131072 --steps 1 --warmup 3 --cpu-sample 1 > gpurun_out/r01d_qpt_run.log 2>&1
+for f in gpurun_out/r01d_prof gpurun_out/r01d_lin2 gpurun_out/r01d_qpt; do python tools/ncu_summary.py $f.ncu-rep; done
