@@ -150,7 +150,19 @@ def lin2_roles(nz, npart=3):
         if len(best) <= max(lower, nz):
             break
     roles = best
-    return [(r[0], r[1], list(r[2])) for r in roles]
+    # warp w of the CTA runs on scheduler w % 4; warp 0 is the producer (the heaviest role), consumer role r is warp r + 1.
+    # Put the lightest roles (no first-order column to integrate) on the producer's scheduler: positions r with (r+1) % 4 == 0.
+    light = [r for r in roles if not r[1]]
+    heavy = [r for r in roles if r[1]]
+    out = []
+    for pos in range(len(roles)):
+        if (pos + 1) % 4 == 0 and light:
+            out.append(light.pop(0))
+        elif heavy:
+            out.append(heavy.pop(0))
+        else:
+            out.append(light.pop(0))
+    return [(r[0], r[1], list(r[2])) for r in out]
 
 
 def generate_header(model: OdeModel, out_path: str) -> dict:
