@@ -36,6 +36,8 @@ def sample_x0(name, pb, B, seed=0):
     if name == "evaporation":
         # X2 sits on its bound 25.0 -> perturb upward only; P2 +-1.0 (evaporation_process/main.py:178-180)
         return xs + np.stack([0.5 * np.abs(rng.uniform(-1, 1, B)), 1.0 * rng.uniform(-1, 1, B)], axis=1)
+    if name == "chain":
+        return xs + np.array([0.5, 0.5, 0.5, 0.8, 0.8, 0.8]) * rng.uniform(-1, 1, (B, pb.nx))
     if name == "unicycle":
         return xs + np.array([0.5, 0.1, 0.0, 0.0]) * rng.uniform(-1, 1, (B, pb.nx))   # examples/unicycle/main.py:172
     raise KeyError(name)
@@ -144,8 +146,32 @@ def economic():
         np.savez_compressed(os.path.join(HERE, "golden_%s_economic.npz" % name), **out)
 
 
+def chain():
+    """synthetic nz = 8 model (configs.chain): generic-dimension paths"""
+    name = "chain"
+    st = rp.StageLib(name)
+    pb, info = configs.make_problem(name, st.F)
+    pb.save(os.path.join(HERE, "problem_%s.npz" % name))
+    B = 32
+    X0 = sample_x0(name, pb, B)
+    out = {"X0": X0}
+    ctrl = rp.Pmpc(pb, qp="qpoases")
+    U, W, LAM, IT, NAS = [], [], [], [], []
+    for b in range(B):
+        ctrl.reset()
+        U.append(ctrl.step(X0[b])); W.append(ctrl.w_sol); LAM.append(ctrl.lam_g)
+        IT.append(ctrl.log["iter"][-1]); NAS.append(ctrl.log["nAS"][-1])
+        assert ctrl.log["status"][-1] == 0
+    out.update({"u0_t6": np.array(U), "w_t6": np.array(W), "lam_t6": np.array(LAM), "iter_t6": np.array(IT), "nAS_t6": np.array(NAS)})
+    print(name, "iter hist", np.bincount(np.array(IT)), "nAS hist", np.bincount(np.array(NAS)))
+    np.savez_compressed(os.path.join(HERE, "golden_%s.npz" % name), **out)
+
+
 def main():
     rp.build()
+    if len(sys.argv) > 1 and sys.argv[1] == "chain":
+        chain()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "economic":
         economic()
         return
@@ -191,6 +217,7 @@ def main():
     unicycle()
     evaporation()
     economic()
+    chain()
 
 
 if __name__ == "__main__":

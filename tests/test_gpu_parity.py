@@ -363,3 +363,20 @@ def test_economic_controller(torch_mod, name):
     d1 = np.max(np.abs((ut[1] - ut[0]) - (ue[1] - ue[0])))
     d2 = np.max(np.abs((ut[2] - ut[0]) - (ue[2] - ue[0])))
     assert 3.5 < d2 / d1 < 4.5, (d1, d2)                                         # the difference is second order in alpha
+
+
+@pytest.mark.parametrize("lin_mode", [None, "1"])
+def test_generic_dimensions_chain(torch_mod, lin_mode, monkeypatch):
+    """synthetic nz = 8 model (configs.chain): both linearisation kernels (warp-specialised with 12 consumer warps, and
+    pair-per-thread) and both first-QP routes against the oracle's golden outputs"""
+    torch = torch_mod
+    if lin_mode:
+        monkeypatch.setenv("TMPC_LIN_MODE", lin_mode)
+    monkeypatch.setenv("TMPC_QP0_MIN", "2" if lin_mode else "1024")
+    ctrl, pb = _ctrl("chain")
+    gold = load_golden("chain")
+    U = ctrl.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
+    assert (ctrl.status.cpu().numpy() == 0).all()
+    assert _relerr(U, gold["u0_t6"]) < 1e-6 and _relerr(ctrl.w_sol.cpu().numpy(), gold["w_t6"]) < 1e-6
+    assert np.array_equal(ctrl.log["iter"][-1].cpu().numpy(), gold["iter_t6"])
+    assert np.array_equal(ctrl.log["nAS"][-1].cpu().numpy(), gold["nAS_t6"])

@@ -188,3 +188,20 @@ def test_twin_economic_controller(env):
         tw.reset(1)
         o = tw.step(pb.wref[0, :pb.nx][None])
         assert o["iter"][0] == 1 and np.allclose(o["u0"][0], pb.wref[0, pb.nx:], rtol=1e-9)
+
+
+def test_twin_generic_dimensions_chain(env):
+    """synthetic nx = 6, nu = 2 model (configs.chain, not in the reference): nothing in the device code is tied to the
+    dimensions of the four reference configs"""
+    rp, build_tables, Twin = env
+    pb, gold = load_problem("chain"), load_golden("chain")
+    assert pb.nz == 8
+    tw = Twin(pb, build_tables(pb), rho=3e7, al_gamma=1e3)
+    n = gold["X0"].shape[0]
+    tw.reset(n)
+    o = tw.step(gold["X0"])
+    assert (o["status"] == 0).all() and np.array_equal(o["iter"], gold["iter_t6"]) and np.array_equal(o["nAS"], gold["nAS_t6"])
+    assert _relerr(o["u0"], gold["u0_t6"]) < 1e-9 and _relerr(o["w"], gold["w_t6"]) < 1e-9
+    tw.reset(n)
+    o2 = tw.step(gold["X0"], shared_first_qp=True)
+    assert _relerr(o2["u0"], gold["u0_t6"]) < 1e-9 and np.array_equal(o2["iter"], gold["iter_t6"])

@@ -121,7 +121,30 @@ def evaporation():
                 conv_rho=1e-3)                                                                # :157 convexify(rho = 1e-3)
 
 
-CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle, "evaporation": evaporation}
+def chain():
+    """SYNTHETIC (not in the reference): three masses on a line coupled by hardening springs, forces on the outer two.
+    nx = 6, nu = 2 (nz = 8): exercises the generic-dimension paths (greedy direction groups in modelgen, the
+    pair-per-thread linearisation when the warp-specialised kernel does not fit the register file)."""
+    p = sp.symbols("p1:4")
+    v = sp.symbols("v1:4")
+    f = sp.symbols("f1 f3")
+    k1, k3, dmp = 2.0, 0.8, 0.3
+    spring = lambda dlt: k1 * dlt + k3 * dlt ** 3
+    acc = [-spring(p[0]) + spring(p[1] - p[0]) - dmp * v[0] + f[0],
+           -spring(p[1] - p[0]) + spring(p[2] - p[1]) - dmp * v[1],
+           -spring(p[2] - p[1]) - dmp * v[2] + f[1]]
+    xdot = [v[0], v[1], v[2]] + acc
+    cost = (p[0] - 0.4) ** 2 + (p[1] - 0.7) ** 2 + 2 * (p[2] - 1.0) ** 2 + 0.1 * (v[0] ** 2 + v[1] ** 2 + v[2] ** 2) \
+        + 0.05 * (f[0] ** 2 + f[1] ** 2)
+    C = np.zeros((4, 8))
+    C[0, 6], C[1, 6], C[2, 7], C[3, 7] = 1.0, -1.0, 1.0, -1.0
+    c = np.array([1.0, 1.2, 1.0, 2.5])                                   # -1 <= f1 <= 1.2, -1 <= f3 <= 2.5
+    model = OdeModel("chain", p + v, f, xdot, rk_steps=8, tf=0.4, cost=cost)
+    return dict(model=model, cost=cost, C=C, c=c, w_guess=np.array([0.4, 0.7, 1.0, 0, 0, 0, 0.5, 1.0]), period=1, N=15,
+                term_idx=[0, 1, 2, 3, 4, 5])
+
+
+CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle, "evaporation": evaporation, "chain": chain}
 
 
 def make_problem(name, stage_F, N=None, hessian_approximation="exact", mpc_type="tuned"):

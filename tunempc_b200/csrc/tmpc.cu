@@ -413,6 +413,15 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
       cudaFuncSetAttribute(k_lin2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm_lin2_smem_bytes());
       cudaFuncSetAttribute(k_lin2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm_lin2_smem_bytes());
     }
+    {
+      // the warp-specialised kernel needs one warp per role: for larger models a CTA no longer fits the register file
+      // or the thread limit -> pair-per-thread kernel
+      int nb = 0;
+      cudaError_t oe = (L2_THREADS <= 1024 && tm_lin2_smem_bytes() <= 227 * 1024)
+                           ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lin2<true>, L2_THREADS, tm_lin2_smem_bytes())
+                           : cudaErrorInvalidConfiguration;
+      if (oe != cudaSuccess || nb < 1) { h->lin_mode = 1; cudaGetLastError(); }
+    }
 #endif
     const char* so = getenv("TMPC_SORT");
     if (so) h->sort_lists = atoi(so) != 0;

@@ -96,14 +96,26 @@ def lin_groups(nz, d=3):
     pairs = [(i, j) for i in range(nz) for j in range(i + 1, nz)]
     triples = list(itertools.combinations(range(nz), d))
     groups = None
-    for ng in range(1, len(pairs) + 2):
-        for gs in itertools.combinations(triples, ng):
-            cov = set(p for g in gs for p in itertools.combinations(g, 2))
-            if len(cov) == len(pairs) and set(x for g in gs for x in g) == set(range(nz)):
-                groups = list(gs)
+    if nz <= 6:
+        for ng in range(1, len(pairs) + 2):
+            for gs in itertools.combinations(triples, ng):
+                cov = set(p for g in gs for p in itertools.combinations(g, 2))
+                if len(cov) == len(pairs) and set(x for g in gs for x in g) == set(range(nz)):
+                    groups = list(gs)
+                    break
+            if groups:
                 break
-        if groups:
-            break
+    else:
+        # greedy set cover (the exhaustive search explodes beyond 6 directions)
+        left = set(pairs)
+        groups = []
+        while left:
+            g = max(triples, key=lambda t: len(left & set(itertools.combinations(t, 2))))
+            groups.append(g)
+            left -= set(itertools.combinations(g, 2))
+        for x in range(nz):
+            if not any(x in g for g in groups):
+                groups.append(tuple(sorted((x, (x + 1) % nz, (x + 2) % nz))))
     allp = [(i, j) for i in range(nz) for j in range(i, nz)]
     load = [[] for _ in groups]
     opts = lambda p: [g for g, t in enumerate(groups) if p[0] in t and p[1] in t]
