@@ -150,3 +150,37 @@ def test_hessian_mode_independence(rp):
     ua, ub = a.step(x0), b.step(x0)
     assert np.allclose(ua, ub, rtol=1e-7)
     assert np.allclose(a.w_sol, b.w_sol, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["cstr", "evaporation", "cstr_economic"])
+def test_oracle_solution_vs_independent_nlp_solver(rp, name):
+    """Pin of the oracle's ANSWERS by an independent solver: the same NLP (tunempc/pmpc.py:162-369) handed to scipy's
+    SLSQP -- a different algorithm (quasi-Newton SQP with its own least-squares QP) and different code -- started 1e-3
+    away from the oracle's answer (from the reference SLSQP stalls on the evaporation problem); the local minimiser it
+    converges to must be the oracle's point, to SLSQP's own accuracy.  (The iteration path of Sqp.solve is pinned by nothing but the
+    restatement itself: 'parity unpinned')"""
+    import scipy.optimize as sopt
+    from conftest import load_golden, load_problem
+    pb, gold = load_problem(name), load_golden(name)
+    cf = None
+    if pb.mpc_type == "economic":
+        from tunempc_b200 import configs, tuning
+        card = configs.CONFIGS[pb.name]()
+        cf = tuning.lambdify_cost(card["model"], card["cost"])
+    oc = rp.Pmpc(pb, cost_funs=cf)
+    nlp, tab = oc.nlp, oc.tab
+    eq = np.where(nlp.ubg - nlp.lbg == 0)[0]
+    iq = np.where((nlp.ubg - nlp.lbg != 0) & np.isfinite(nlp.lbg))[0]
+    scale = np.maximum(np.abs(tab.ref[0]), 1.0)
+    for b in (0, 3, 5):
+        p0 = {"x0": gold["X0"][b], "wref": tab.ref[0], "H": tab.Href[0], "q": tab.qref[0]}
+        cons = [{"type": "eq", "fun": lambda y: nlp.g(y * scale, p0)[eq], "jac": lambda y: nlp.g(y * scale, p0, order=1)[1][eq] * scale[None, :]},
+                {"type": "ineq", "fun": lambda y: nlp.g(y * scale, p0)[iq], "jac": lambda y: nlp.g(y * scale, p0, order=1)[1][iq] * scale[None, :]}]
+        res = sopt.minimize(lambda y: nlp.f(y * scale, p0), gold["w_t9"][b] / scale * (1 + 1e-3) + 1e-3,
+                            jac=lambda y: nlp.jacf(y * scale, p0) * scale, constraints=cons, method="SLSQP",
+                            options={"ftol": 1e-15, "maxiter": 400})
+        w = res.x * scale
+        assert np.abs(nlp.g(w, p0)[eq]).max() < 1e-7
+        err = np.max(np.abs(w - gold["w_t9"][b]) / np.maximum(np.abs(gold["w_t9"][b]), 1.0))
+        assert err < 1e-4, (name, b, err, res.message)                      # SLSQP's own accuracy
+        assert abs(nlp.f(w, p0) - nlp.f(gold["w_t9"][b], p0)) < 1e-6 * max(1.0, abs(nlp.f(w, p0)))
