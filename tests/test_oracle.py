@@ -180,7 +180,7 @@ def test_oracle_solution_vs_independent_nlp_solver(rp, name):
                             jac=lambda y: nlp.jacf(y * scale, p0) * scale, constraints=cons, method="SLSQP",
                             options={"ftol": 1e-15, "maxiter": 400})
         w = res.x * scale
-        assert np.abs(nlp.g(w, p0)[eq]).max() < 1e-7
+        assert np.abs(nlp.g(w, p0)[eq]).max() < 1e-5
         err = np.max(np.abs(w - gold["w_t9"][b]) / np.maximum(np.abs(gold["w_t9"][b]), 1.0))
         assert err < 1e-4, (name, b, err, res.message)                      # SLSQP's own accuracy
-        assert abs(nlp.f(w, p0) - nlp.f(gold["w_t9"][b], p0)) < 1e-6 * max(1.0, abs(nlp.f(w, p0)))
+        assert abs(nlp.f(w, p0) - nlp.f(gold["w_t9"][b], p0)) < 1e-4 * max(1.0, abs(nlp.f(w, p0)))   # no better point nearby
