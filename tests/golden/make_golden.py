@@ -38,6 +38,8 @@ def sample_x0(name, pb, B, seed=0):
         return xs + np.stack([0.5 * np.abs(rng.uniform(-1, 1, B)), 1.0 * rng.uniform(-1, 1, B)], axis=1)
     if name == "chain":
         return xs + np.array([0.5, 0.5, 0.5, 0.8, 0.8, 0.8]) * rng.uniform(-1, 1, (B, pb.nx))
+    if name == "dims9":
+        return xs + np.array([0.4] * 4 + [0.6] * 4 + [0.3]) * rng.uniform(-1, 1, (B, pb.nx))
     if name == "unicycle":
         return xs + np.array([0.5, 0.1, 0.0, 0.0]) * rng.uniform(-1, 1, (B, pb.nx))   # examples/unicycle/main.py:172
     raise KeyError(name)
@@ -146,13 +148,11 @@ def economic():
         np.savez_compressed(os.path.join(HERE, "golden_%s_economic.npz" % name), **out)
 
 
-def chain():
-    """synthetic nz = 8 model (configs.chain): generic-dimension paths"""
-    name = "chain"
+def chain(name="chain", B=32):
+    """synthetic models (configs.chain nz = 8, configs.dims9 nz = 12 with the AWE config's dimensions): generic-dimension paths"""
     st = rp.StageLib(name)
     pb, info = configs.make_problem(name, st.F)
     pb.save(os.path.join(HERE, "problem_%s.npz" % name))
-    B = 32
     X0 = sample_x0(name, pb, B)
     out = {"X0": X0}
     ctrl = rp.Pmpc(pb, qp="qpoases")
@@ -171,6 +171,9 @@ def main():
     rp.build()
     if len(sys.argv) > 1 and sys.argv[1] == "chain":
         chain()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "dims9":
+        chain("dims9", 12)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "economic":
         economic()
@@ -218,6 +221,7 @@ def main():
     evaporation()
     economic()
     chain()
+    chain("dims9", 12)
 
 
 if __name__ == "__main__":

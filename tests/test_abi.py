@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(built):
     from tunempc_b200.lib import ModelLib, EXPORTS
     syms = _declared_symbols()
     assert set(syms) == set(EXPORTS)
-    for name in ("lq", "cstr", "unicycle", "evaporation", "chain"):
+    for name in ("lq", "cstr", "unicycle", "evaporation", "chain", "dims9"):
         lib = ModelLib(name)
         for s in syms:
             assert hasattr(lib.lib, s), "%s missing in %s" % (s, lib.path)

@@ -365,16 +365,17 @@ def test_economic_controller(torch_mod, name):
     assert 3.5 < d2 / d1 < 4.5, (d1, d2)                                         # the difference is second order in alpha
 
 
-@pytest.mark.parametrize("lin_mode", [None, "1"])
-def test_generic_dimensions_chain(torch_mod, lin_mode, monkeypatch):
-    """synthetic nz = 8 model (configs.chain): both linearisation kernels (warp-specialised with 12 consumer warps, and
+@pytest.mark.parametrize("name,lin_mode", [("chain", None), ("chain", "1"), ("dims9", None), ("dims9", "1")])
+def test_generic_dimensions(torch_mod, name, lin_mode, monkeypatch):
+    """synthetic models beyond the reference configs' dimensions -- chain (nz = 8) and dims9 (nz = 12: the AWE config's
+    dimensions, one warp-level QP per CTA): both linearisation kernels (warp-specialised with 12 / 26 consumer warps, and
     pair-per-thread) and both first-QP routes against the oracle's golden outputs"""
     torch = torch_mod
     if lin_mode:
         monkeypatch.setenv("TMPC_LIN_MODE", lin_mode)
     monkeypatch.setenv("TMPC_QP0_MIN", "2" if lin_mode else "1024")
-    ctrl, pb = _ctrl("chain")
-    gold = load_golden("chain")
+    ctrl, pb = _ctrl(name)
+    gold = load_golden(name)
     U = ctrl.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
     assert (ctrl.status.cpu().numpy() == 0).all()
     assert _relerr(U, gold["u0_t6"]) < 1e-6 and _relerr(ctrl.w_sol.cpu().numpy(), gold["w_t6"]) < 1e-6

@@ -205,3 +205,21 @@ def test_twin_generic_dimensions_chain(env):
     tw.reset(n)
     o2 = tw.step(gold["X0"], shared_first_qp=True)
     assert _relerr(o2["u0"], gold["u0_t6"]) < 1e-9 and np.array_equal(o2["iter"], gold["iter_t6"])
+
+
+def test_twin_awe_dimensions_dims9(env):
+    """synthetic stand-in with the dimensions of the AWE config (nx = 9, nu = 3, 14 constraint rows, N = 20, 7-row projected
+    terminal constraint; configs.dims9): state-only rows relaxed at stage 0, mixed rows, 280 inequality rows"""
+    rp, build_tables, Twin = env
+    pb, gold = load_problem("dims9"), load_golden("dims9")
+    assert (pb.nx, pb.nu, pb.nh, pb.nx_term, pb.n_w, pb.n_g) == (9, 3, 14, 7, 249, 476)
+    tw = Twin(pb, build_tables(pb), rho=3e7, al_gamma=1e3)
+    n = gold["X0"].shape[0]
+    tw.reset(n)
+    o = tw.step(gold["X0"], shared_first_qp=True)
+    assert (o["status"] == 0).all() and np.array_equal(o["iter"], gold["iter_t6"]) and np.array_equal(o["nAS"], gold["nAS_t6"])
+    assert _relerr(o["u0"], gold["u0_t6"]) < 1e-9 and _relerr(o["w"], gold["w_t6"]) < 1e-9
+    ineq = np.concatenate([np.arange(pb.g_h(k).start, pb.g_h(k).stop) for k in range(pb.N)])
+    for b in range(n):                    # active sets = inequality rows with a non-zero multiplier (sqp_method.py:417-423)
+        assert set(np.nonzero(o["lam"][b][ineq])[0]) == set(np.nonzero(gold["lam_t6"][b][ineq])[0])
+    assert _relerr(o["lam"], gold["lam_t6"]) < 1e-8

@@ -144,7 +144,49 @@ def chain():
                 term_idx=[0, 1, 2, 3, 4, 5])
 
 
-CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle, "evaporation": evaporation, "chain": chain}
+def dims9():
+    """SYNTHETIC (not in the reference): stand-in with the DIMENSIONS of the AWE config (#5, SURVEY.md 8.0: nx = 9, nu = 3,
+    14 path-constraint rows, N = 20, 7-row projected terminal constraint x[1:3], x[4:]); the reference's kite model is an
+    opaque CasADi pickle.  Four masses with hardening springs, an actuator lag state, state-only, input-only and mixed
+    constraint rows.  Exercises nz = 12: one warp-level QP per CTA (shared-memory fit), 280 inequality rows."""
+    p = sp.symbols("p1:5")
+    v = sp.symbols("v1:5")
+    a = sp.symbols("a")
+    u = sp.symbols("u1 u2 u3")
+    k1, k3, dmp, tau = 1.5, 0.6, 0.25, 0.5
+    spring = lambda dlt: k1 * dlt + k3 * dlt ** 3
+    acc = [-spring(p[0]) + spring(p[1] - p[0]) - dmp * v[0] + u[0],
+           -spring(p[1] - p[0]) + spring(p[2] - p[1]) - dmp * v[1] + a,
+           -spring(p[2] - p[1]) + spring(p[3] - p[2]) - dmp * v[2],
+           -spring(p[3] - p[2]) - dmp * v[3] + u[1] * (1 + 0.2 * p[3])]
+    xdot = list(v) + acc + [(u[2] - a) / tau]
+    cost = ((p[0] - 0.3) ** 2 + (p[1] - 0.6) ** 2 + (p[2] - 0.8) ** 2 + 2 * (p[3] - 1.1) ** 2
+            + 0.1 * sum(vi ** 2 for vi in v) + 0.05 * a ** 2 + 0.05 * (u[0] ** 2 + u[1] ** 2) + 0.02 * u[2] ** 2)
+    nz = 12
+    rows = []
+    def row(coefs, const):
+        r = np.zeros(nz)
+        for idx, val in coefs:
+            r[idx] = val
+        rows.append((r, const))
+    for j, (lo, hi) in zip((9, 10, 11), ((-1.0, 1.0), (-1.0, 2.0), (-1.5, 1.5))):      # input bounds (6 rows)
+        row([(j, 1.0)], -lo)
+        row([(j, -1.0)], hi)
+    row([(8, 1.0)], 1.2)                                                               # actuator state bounds (state only)
+    row([(8, -1.0)], 1.2)
+    for j, hi in zip((0, 1, 2), (0.9, 1.2, 1.4)):                                      # position upper bounds (state only)
+        row([(j, -1.0)], hi)
+    row([(9, -1.0), (0, -0.5)], 1.1)                                                   # mixed row: u1 + 0.5 p1 <= 1.1
+    row([(7, 1.0)], 1.5)                                                               # |v4| <= 1.5
+    row([(7, -1.0)], 1.5)
+    C = np.array([r for r, _ in rows])
+    cc = np.array([c0 for _, c0 in rows])
+    model = OdeModel("dims9", p + v + (a,), u, xdot, rk_steps=10, tf=0.3, cost=cost)
+    w_guess = np.array([0.3, 0.6, 0.8, 1.1, 0, 0, 0, 0, 0.3, 0.2, 0.8, 0.3])
+    return dict(model=model, cost=cost, C=C, c=cc, w_guess=w_guess, period=1, N=20, term_idx=[1, 2, 4, 5, 6, 7, 8])
+
+
+CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle, "evaporation": evaporation, "chain": chain, "dims9": dims9}
 
 
 def make_problem(name, stage_F, N=None, hessian_approximation="exact", mpc_type="tuned"):

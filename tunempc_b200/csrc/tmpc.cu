@@ -52,6 +52,7 @@ struct tmpc_handle {
   cudaEvent_t ev[8];
   bool ev_ok = false;
   size_t qp_smem = 0;
+  int qp_warps = QP_WARPS;     // instances per CTA of the warp-per-instance QP kernels: 2, 1, or 0 (workspace exceeds shared memory)
   int qp_mode = 2;             // 2: hybrid (thread per instance for big launches, warp per instance for the tail), 1: thread, 0: warp
   int qp_thread_min = 16384;   // hybrid: launches with fewer candidate instances use the low-latency warp kernel
   bool trace = false;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) k_qp(TmProb P, TmState S, const
   extern __shared__ double smem[];
   if (cnt_dev) cnt = *cnt_dev;
   const int wid = threadIdx.x / 32;
-  const int64_t slot = (int64_t)blockIdx.x * QP_WARPS + wid;
+  const int64_t slot = (int64_t)blockIdx.x * (blockDim.x / 32) + wid;   // 1 or QP_WARPS instances per CTA (shared-memory fit)
   if (slot >= cnt) return;
   const int64_t inst = list ? list[slot] : slot;
   const size_t per = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact);
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) k_qp(TmProb P, TmState S, const
 __global__ void __launch_bounds__(QP_WARPS * 32) k_qp0_build(TmProb P, TmState S, TmQp0Tab T) {
   extern __shared__ double smem[];
   const int wid = threadIdx.x / 32;
-  const int t = blockIdx.x * QP_WARPS + wid;
+  const int t = blockIdx.x * (blockDim.x / 32) + wid;
   if (t >= T.nT) return;
   const size_t per = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact);
   TmQpWs ws;
@@ -388,20 +389,22 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
   if (P.maxact < P.nxt + 4) P.maxact = P.nxt + 4;
   P.tol = h->opts.tol; P.lam_tresh = h->opts.lam_tresh; P.beta = h->opts.ls_step_factor;
   P.reg_tol = h->opts.reg_tol; P.rho = h->opts.term_penalty; P.al_gamma = h->opts.al_gamma;
-  h->qp_smem = QP_WARPS * tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact) * sizeof(double);
-  if (h->qp_smem > 227 * 1024) {
-    fprintf(stderr, "tmpc_create: QP workspace %zu B exceeds shared memory\n", h->qp_smem);
-    delete h;
-    return 4;
-  }
-  if (cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem) != cudaSuccess) {
-    fprintf(stderr, "tmpc_create: cannot reserve %zu B of shared memory\n", h->qp_smem);
-    delete h;
-    return 4;
+  {
+    // warp-per-instance QP kernels keep the workspace of their instances in shared memory: 2 per CTA if that fits, else
+    // 1, else those kernels are not used at all (thread-per-instance kernel for every launch, no shared first QP)
+    const size_t per = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact) * sizeof(double);
+    h->qp_warps = (QP_WARPS * per <= 227 * 1024) ? QP_WARPS : (per <= 227 * 1024 ? 1 : 0);
+    h->qp_smem = (size_t)h->qp_warps * per;
+    if (h->qp_warps > 0 &&
+        cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem) != cudaSuccess) {
+      cudaGetLastError();
+      h->qp_warps = 0;
+    }
+    if (h->qp_warps == 0) h->qp_mode = 1;
   }
   {
     const char* m = getenv("TMPC_QP_MODE");
-    if (m && m[0] == 'w') h->qp_mode = 0;
+    if (m && m[0] == 'w' && h->qp_warps > 0) h->qp_mode = 0;
     if (m && m[0] == 't') h->qp_mode = 1;
     h->trace = getenv("TMPC_TRACE") != nullptr;
     const char* lm = getenv("TMPC_LIN_MODE");
@@ -455,6 +458,7 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
         cudaMalloc(&T.SLPHI, (size_t)NX * T.EI * sizeof(double)) == cudaSuccess &&
         cudaMalloc(&T.MCOL, (size_t)T.EI * T.EIs * sizeof(double)) == cudaSuccess &&
         cudaMalloc(&T.bad, sizeof(int)) == cudaSuccess &&
+        h->qp_warps > 0 &&
         cudaFuncSetAttribute(k_qp0_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem) == cudaSuccess)
       h->q0_ok = h->q0_min >= 0;
     cudaMemset(T.MCOL, 0, (size_t)T.EI * T.EIs * sizeof(double));
@@ -669,14 +673,14 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
         // every instance shares (w0, lam0): tabulate the parametric QP once, then one thread per instance on the tables
         const TmQp0Tab& T = h->q0;
         CK(cudaMemsetAsync(T.bad, 0, sizeof(int), st));
-        k_qp0_build<<<(T.nT + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, h->qp_smem, st>>>(P, S, T);
+        k_qp0_build<<<(T.nT + h->qp_warps - 1) / h->qp_warps, h->qp_warps * 32, h->qp_smem, st>>>(P, S, T);
         k_qp0_derive<<<(T.nT * T.EI + 127) / 128, 128, 0, st>>>(P, S, T);
         k_qp0<<<(unsigned)((B + Q0_THREADS - 1) / Q0_THREADS), Q0_THREADS, 0, st>>>(P, S, T, (int)B);
         launches += 2;
       } else if (use_thread)
         CK(tm_launch_qp_thread(P, S, plist, (int)nact, pcnt, h->qp_ws, h->qp_ws_per_inst, h->qp_blocks, h->qp_counter, st));
       else
-        k_qp<<<wb, QP_WARPS * 32, h->qp_smem, st>>>(P, S, plist, (int)nact, pcnt);
+        k_qp<<<(unsigned)((nact + h->qp_warps - 1) / h->qp_warps), h->qp_warps * 32, h->qp_smem, st>>>(P, S, plist, (int)nact, pcnt);
       ++launches;
     }
     CK(cudaEventRecord(h->ev[1], st));

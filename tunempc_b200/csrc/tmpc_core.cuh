@@ -93,7 +93,7 @@ TM_HD TmP tm_mkp(double* base, size_t off) { return base + off; }
 #define TM_LSZ (NX + NX * NZ + TM_NPAIR)   /* per-stage linearisation record: xf | S row-major nx*nz | W packed i<=j */
 #define TM_INF 1e300
 #define TM_NCNT 24
-#define TM_ALW 8   /* words of the augmented-Lagrangian row mask: supports N*nh <= 256 */
+#define TM_ALW 12  /* words of the augmented-Lagrangian row mask: supports N*nh <= 384 */
 
 // ---------------------------------------------------------------------------------------------------------------
 // problem constants and per-batch state (plain pointers; device memory in the product, malloc in the twin)
