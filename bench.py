@@ -252,13 +252,13 @@ def main():
     if rank == 0:
         f_lin, f_dyn = algorithmic_flops_per_stage_lin(args.hessian == "exact")
         ach = (n_lin * f_lin) / (lin_ms * 1e-3) / 1e12 if lin_ms > 0 else 0.0
-        # DRAM traffic of the dominant kernels from the committed ncu --set full captures (profiles/r01d_summary.md):
-        # k_lin2 442.5 MB read + 973.1 MB written per launch of 131072 x 20 stage tasks; k_qp_thread 30.2 + 6.2 GB per
+        # DRAM traffic of the dominant kernels from the committed ncu --set full captures (profiles/r01e_summary.md):
+        # k_lin2 440.0 MB read + 972.8 MB written per launch of 131072 x 20 stage tasks; k_qp_thread 30.3 + 6.2 GB per
         # launch of 131072 QPs.  Algorithmic bytes: a stage task reads (x,u,lam_dyn) and writes its 49-double record;
         # a QP reads its N records + w and writes (d, lam).
-        lin_traffic_per_task = (442.472448e6 + 973.118976e6) / (131072 * 20)
+        lin_traffic_per_task = (439.988992e6 + 972.843008e6) / (131072 * 20)
         lin_alg_bytes_per_task = 8.0 * (pb.nx + pb.nu + pb.nx) + 8.0 * (pb.nx + pb.nx * pb.nz + pb.nz * (pb.nz + 1) // 2)
-        qp_traffic_per_qp = (30.198128e9 + 6.205736e9) / 131072
+        qp_traffic_per_qp = (30.312675e9 + 6.179678e9) / 131072
         qp_alg_bytes = 8.0 * (pb.N * (pb.nx + pb.nx * pb.nz + pb.nz * (pb.nz + 1) // 2) + 2 * pb.n_w + pb.n_g + pb.nx)
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
