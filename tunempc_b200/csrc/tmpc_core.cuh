@@ -317,6 +317,109 @@ TM_HD void tm_integrate_colloc(const double* u, int i, int j, double* X, double*
 }
 #endif
 
+#if TMPC_COLLOCATION
+// Whole linearisation record of one stage in ONE task: the Newton solve and the LU factorisation of an element are done
+// once and shared by all NZ first-order and NZ(NZ+1)/2 second-order right-hand sides (the pair-per-task route repeats
+// them for every pair).  order 1: xf, S;  order 2: + W = lam' d2F/dz2.  rec layout as everywhere: xf | S row-major | W.
+TM_HD void tm_colloc_stage(const double* x0, const double* u, int order, const double* lam, double* rec) {
+  const double sq6 = 2.449489742783178;
+  const double A[3][3] = {{(88.0 - 7.0 * sq6) / 360.0, (296.0 - 169.0 * sq6) / 1800.0, (-2.0 + 3.0 * sq6) / 225.0},
+                          {(296.0 + 169.0 * sq6) / 1800.0, (88.0 + 7.0 * sq6) / 360.0, (-2.0 - 3.0 * sq6) / 225.0},
+                          {(16.0 - sq6) / 36.0, (16.0 + sq6) / 36.0, 1.0 / 9.0}};
+  const double h = TMPC_RK_DT;
+  double X[NX], Sm[NZ][NX], Tm[TM_NPAIR][NX];
+  for (int a = 0; a < NX; ++a) X[a] = x0[a];
+  for (int i = 0; i < NZ; ++i) for (int a = 0; a < NX; ++a) Sm[i][a] = (a == i) ? 1.0 : 0.0;
+  for (int p = 0; p < TM_NPAIR; ++p) for (int a = 0; a < NX; ++a) Tm[p][a] = 0.0;
+  for (int s = 0; s < TMPC_RK_STEPS; ++s) {
+    double K[3][NX], Jst[3][NX * NZ], M[TM_CN * TM_CN], rhs[TM_CN];
+    double Hst[3][TMPC_NHESS > 0 ? TMPC_NHESS : 1];
+    int piv[TM_CN];
+    {
+      double f0[NX];
+      tmpc_ode(X, u, f0);
+      for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) K[q][a] = f0[a];
+    }
+    int done = 0;
+    for (int it = 0; it < 40; ++it) {                  // same Newton iteration as tm_integrate_colloc
+      for (int q = 0; q < 3; ++q) {
+        double Xq[NX], fq[NX];
+        for (int a = 0; a < NX; ++a) {
+          double v = X[a];
+          for (int l = 0; l < 3; ++l) v += h * A[q][l] * K[l][a];
+          Xq[a] = v;
+        }
+        if (done && order == 2) tmpc_ode_d2(Xq, u, fq, Jst[q], Hst[q]); else tmpc_ode_jac(Xq, u, fq, Jst[q]);
+        for (int a = 0; a < NX; ++a) rhs[q * NX + a] = -(K[q][a] - fq[a]);
+      }
+      for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) for (int l = 0; l < 3; ++l) for (int b = 0; b < NX; ++b)
+        M[(q * NX + a) * TM_CN + l * NX + b] = ((q == l && a == b) ? 1.0 : 0.0) - h * A[q][l] * Jst[q][a * NZ + b];
+      tm_lu_factor(M, piv);
+      if (done) break;
+      tm_lu_solve(M, piv, rhs);
+      double dmax = 0.0, kmax = 1.0;
+      for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) {
+        K[q][a] += rhs[q * NX + a];
+        dmax = fmax(dmax, fabs(rhs[q * NX + a]));
+        kmax = fmax(kmax, fabs(K[q][a]));
+      }
+      if (!(dmax > 1e-14 * kmax)) done = 1;
+      if (it == 38) done = 1;
+    }
+    // first order: all NZ directions against the same factorisation; V[i][q] = stage-argument direction
+    double dK[NZ][TM_CN], V[NZ][3][NZ];
+    for (int i = 0; i < NZ; ++i) {
+      for (int q = 0; q < 3; ++q) for (int a = 0; a < NX; ++a) {
+        double t = 0.0;
+        for (int b = 0; b < NX; ++b) t += Jst[q][a * NZ + b] * Sm[i][b];
+        if (i >= NX) t += Jst[q][a * NZ + i];
+        dK[i][q * NX + a] = t;
+      }
+      tm_lu_solve(M, piv, dK[i]);
+      for (int q = 0; q < 3; ++q) {
+        for (int a = 0; a < NX; ++a) {
+          double t = Sm[i][a];
+          for (int l = 0; l < 3; ++l) t += h * A[q][l] * dK[i][l * NX + a];
+          V[i][q][a] = t;
+        }
+        for (int b = 0; b < NU; ++b) V[i][q][NX + b] = (i == NX + b) ? 1.0 : 0.0;
+      }
+    }
+    if (order == 2) {
+      for (int i = 0; i < NZ; ++i)
+        for (int j = i; j < NZ; ++j) {
+          const int p = tm_pair_idx(i, j);
+          double ddK[TM_CN];
+          for (int q = 0; q < 3; ++q) {
+            double dd[NX];
+            tmpc_ode_bilin(Hst[q], V[i][q], V[j][q], dd);
+            for (int a = 0; a < NX; ++a) {
+              double t = dd[a];
+              for (int b = 0; b < NX; ++b) t += Jst[q][a * NZ + b] * Tm[p][b];
+              ddK[q * NX + a] = t;
+            }
+          }
+          tm_lu_solve(M, piv, ddK);
+          for (int a = 0; a < NX; ++a) for (int q = 0; q < 3; ++q) Tm[p][a] += h * A[2][q] * ddK[q * NX + a];
+        }
+    }
+    for (int a = 0; a < NX; ++a)
+      for (int q = 0; q < 3; ++q) {
+        X[a] += h * A[2][q] * K[q][a];
+        for (int i = 0; i < NZ; ++i) Sm[i][a] += h * A[2][q] * dK[i][q * NX + a];
+      }
+  }
+  for (int a = 0; a < NX; ++a) rec[a] = X[a];
+  for (int a = 0; a < NX; ++a) for (int i = 0; i < NZ; ++i) rec[NX + a * NZ + i] = Sm[i][a];
+  if (order == 2)
+    for (int p = 0; p < TM_NPAIR; ++p) {
+      double wij = 0.0;
+      for (int a = 0; a < NX; ++a) wij += lam[a] * Tm[p][a];
+      rec[NX + NX * NZ + p] = wij;
+    }
+}
+#endif
+
 template <int ORDER>
 TM_HD void tm_integrate(const double* x0, const double* u, int i, int j, double* X, double* Si, double* Sj, double* T) {
 #pragma unroll
@@ -542,7 +645,9 @@ TM_HD void tm_lin_group_gn(const double* x, const double* u, double* rec) {
   }
 }
 
-#ifdef TMPC_LIN_GROUPED
+#if TMPC_COLLOCATION
+TM_HD int tm_lin_tasks_per_stage(int) { return 1; }     // tm_colloc_stage: the whole record in one task
+#elif defined(TMPC_LIN_GROUPED)
 TM_HD int tm_lin_tasks_per_stage(int hessian_exact) { return hessian_exact ? TMPC_LIN_NG : TM_GN_NG; }
 #else
 TM_HD int tm_lin_tasks_per_stage(int hessian_exact) { return hessian_exact ? TM_NPAIR : TM_GN_NG; }
@@ -565,6 +670,16 @@ TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, i
     for (int b = 0; b < NU; ++b) u[b] += d[NX + b];
   }
   double* rec = S.LIN + (inst * P.N + k) * (int64_t)TM_LSZ;
+#if TMPC_COLLOCATION
+  {
+    double lamc[NX];
+    const double* lamq = (trial ? S.LAMQ : S.LAM) + inst * P.n_g + tm_gdyn(P, k);
+    for (int a = 0; a < NX; ++a) lamc[a] = P.hessian_exact ? lamq[a] : 0.0;
+    tm_colloc_stage(x, u, P.hessian_exact ? 2 : 1, lamc, rec);
+    (void)g;
+    return;
+  }
+#endif
   if (P.hessian_exact) {
     const double* lamp = (trial ? S.LAMQ : S.LAM) + inst * P.n_g + tm_gdyn(P, k);
     double lam[NX];
