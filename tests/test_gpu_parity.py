@@ -365,7 +365,7 @@ def test_economic_controller(torch_mod, name):
     assert 3.5 < d2 / d1 < 4.5, (d1, d2)                                         # the difference is second order in alpha
 
 
-@pytest.mark.parametrize("name,lin_mode", [("chain", None), ("chain", "1"), ("dims9", None), ("dims9", "1")])
+@pytest.mark.parametrize("name,lin_mode", [("chain", "2"), ("chain", "1"), ("dims9", "2"), ("dims9", "1"), ("dims9", None)])
 def test_generic_dimensions(torch_mod, name, lin_mode, monkeypatch):
     """synthetic models beyond the reference configs' dimensions -- chain (nz = 8) and dims9 (nz = 12: the AWE config's
     dimensions, one warp-level QP per CTA): both linearisation kernels (warp-specialised with 12 / 26 consumer warps, and
@@ -373,7 +373,7 @@ def test_generic_dimensions(torch_mod, name, lin_mode, monkeypatch):
     torch = torch_mod
     if lin_mode:
         monkeypatch.setenv("TMPC_LIN_MODE", lin_mode)
-    monkeypatch.setenv("TMPC_QP0_MIN", "2" if lin_mode else "1024")
+    monkeypatch.setenv("TMPC_QP0_MIN", "2" if lin_mode == "1" else "1024")   # lin_mode None: the library's own choice
     ctrl, pb = _ctrl(name)
     gold = load_golden(name)
     U = ctrl.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()

@@ -424,6 +424,10 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
                            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lin2<true>, L2_THREADS, tm_lin2_smem_bytes())
                            : cudaErrorInvalidConfiguration;
       if (oe != cudaSuccess || nb < 1) { h->lin_mode = 1; cudaGetLastError(); }
+      // ... or only with the registers capped so low that the state spills (dims9, 27 warps: 1.4 KB of stack per thread, 3.3x
+      // slower than the pair-per-thread kernel; chain, 13 warps: 0.4 KB, on par; the reference configs: none)
+      cudaFuncAttributes fa;
+      if (h->lin_mode == 2 && !lm && cudaFuncGetAttributes(&fa, k_lin2<true>) == cudaSuccess && fa.localSizeBytes > 1024) h->lin_mode = 1;
     }
 #endif
     const char* so = getenv("TMPC_SORT");
