@@ -138,7 +138,8 @@ def run_reference_arm(args):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "cstr N=20 tuned NMPC, exact Hessian", "sample": "%d x0 per step" % n},
+            "config": {"workload": "cstr N=20 tuned NMPC (examples/cstr), exact Hessian, reset+step per x0",
+                       "sample": "%d x0 per step (bounded sample of the B=2^20-per-GPU workload of the B200 arm)" % n},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d instances per step (oracle port: numpy + C stage functions + qpOASES_e), %d steps" % (n, len(times))},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
