@@ -34,9 +34,13 @@ typedef struct tmpc_handle tmpc_handle;
 #define TMPC_QP_INFEASIBLE 2   /* QP infeasible / working set overflow (reference: CasADi conic raises)            */
 #define TMPC_NOT_PD 3          /* reduced Hessian not positive definite (reference: AssertionError sqp_method.py:201) */
 #define TMPC_NAN 4             /* non-finite iterate                                                                */
+#define TMPC_WS_OVERFLOW 5     /* dual active set needed more than opts.max_working_set rows                        */
 /* flag bits OR-ed into `flags` output */
-#define TMPC_FLAG_GN_FALLBACK 1  /* >=1 iteration used the Gauss-Newton Hessian because the exact one was not PD on the
-                                    dynamics null space (the reference would eigen-clip, sqp_method.py:345-376)   */
+#define TMPC_FLAG_GN_FALLBACK 1  /* >=1 iteration used the Gauss-Newton Hessian because the exact one was not PD on the null
+                                    space of [equalities; rows active in the multipliers] -- exactly where the reference
+                                    eigen-clips its reduced Hessian (sqp_method.py:345-376)                         */
+#define TMPC_FLAG_GN_RESOLVE 4   /* >=1 QP fell back to the Gauss-Newton Hessian after releasing wrong-signed base rows
+                                    (the reference's QP is non-convex there)                                        */
 #define TMPC_FLAG_DAMPED 2       /* >=1 line-search backtrack (alpha < 1)                                           */
 
 typedef struct {
@@ -55,8 +59,12 @@ typedef struct {
   double lam_tresh;        /* sqp_method.py:56 (1e-8) */
   double ls_step_factor;   /* sqp_method.py:58 (0.8) */
   double reg_tol;          /* sqp_method.py:54 (1e-8): pivot threshold of the reduced-Hessian PD test */
-  double term_penalty;     /* rho of the exact terminal penalty used inside the Riccati base factorisation */
-  double al_gamma;         /* relative weight of the exact augmented-Lagrangian convexification on warm-start active rows (0 = off) */
+  double term_weight;      /* weight (relative to the largest Hessian diagonal entry) of the augmented-Lagrangian term the base
+                              factorisation carries for the terminal rows; the rows themselves are enforced exactly through their
+                              multipliers in the Schur complement, so the QP solution does not depend on it */
+  int32_t max_working_set; /* rows the dual active set may ADD to the base rows of one QP (default 32, clipped to N*nh); the base rows
+                              (terminal rows + rows active in the multipliers) live in the factorisation and do not count.
+                              Overflow is reported per instance as status TMPC_WS_OVERFLOW, never as "infeasible" */
   int32_t economic;        /* 1: economic MPC -- stage cost = the compiled model's l(x,u), exact Hessian forced (pmpc.py:97-107,
                               173-183, 299-301); 0: tuned / tracking cost from the H, q tables (mtools.py:43-57) */
 } tmpc_opts;

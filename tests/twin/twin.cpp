@@ -41,7 +41,7 @@ void twin_stage_eval(int n, const double* x, const double* u, int order, double*
   }
 }
 
-// dims: N nh nxt p ; iopts: hessian_exact max_iter max_ls maxact economic ; dopts: tol lam_tresh beta reg_tol rho al_gamma
+// dims: N nh nxt p ; iopts: hessian_exact max_iter max_ls maxact economic ; dopts: tol lam_tresh beta reg_tol rho_rel
 int twin_step(const int* dims, const int* iopts, const double* dopts, const double* wref, const double* H,
               const double* q, const double* ref_du, const double* C, const double* c, const int* term_idx,
               const int* relax0, int phase, long long B, const double* X0, double* W, double* LAM, double* G,
@@ -53,12 +53,12 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
   P.n_g = NX + P.N * (NX + P.nh) + P.nxt;
   P.hessian_exact = iopts[0];
   P.filter_cap = 64;
-  P.max_iter = iopts[1] < P.filter_cap - 1 ? iopts[1] : P.filter_cap - 1;
+  P.max_iter = iopts[1];
   P.max_ls = iopts[2];
-  P.maxact = iopts[3];
+  P.maxact = (iopts[3] < P.N * P.nh ? iopts[3] : P.N * P.nh) + P.nxt; if (P.maxact < 1) P.maxact = 1;
   P.economic = iopts[4];
   if (P.economic) P.hessian_exact = 1;
-  P.tol = dopts[0]; P.lam_tresh = dopts[1]; P.beta = dopts[2]; P.reg_tol = dopts[3]; P.rho = dopts[4]; P.al_gamma = dopts[5];
+  P.tol = dopts[0]; P.lam_tresh = dopts[1]; P.beta = dopts[2]; P.reg_tol = dopts[3]; P.rho_rel = dopts[4];
   P.wref = wref; P.H = H; P.q = q; P.ref_du = ref_du; P.C = C; P.c = c; P.term_idx = term_idx; P.relax0 = relax0;
   TmState S;
   memset(&S, 0, sizeof S);
@@ -126,7 +126,7 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
       }
     } else
     for (long long s = 0; s < nact; ++s) tm_qp(P, S, (*cur)[s], ws);
-    for (int pass = 0; pass < 5 && cnt_retry > 0; ++pass) {      // re-solves (mask shrink / Gauss-Newton fallback)
+    if (cnt_retry > 0) {                                         // instances the shared-table route handed back
       std::vector<int> todo(lretry.begin(), lretry.begin() + cnt_retry);
       cnt_retry = 0;
       for (int v : todo) tm_qp(P, S, v, ws);

@@ -22,6 +22,7 @@ def _i(a):
 def build(name):
     out = os.path.join(_HERE, "libtwin_%s.so" % name)
     srcs = [os.path.join(_HERE, "twin.cpp"), os.path.join(_ROOT, "tunempc_b200/csrc/tmpc_core.cuh"),
+            os.path.join(_ROOT, "tunempc_b200/csrc/tmpc_qp.cuh"),
             os.path.join(_ROOT, "tunempc_b200/csrc/gen/model_%s.h" % name)]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
         return out
@@ -32,10 +33,10 @@ def build(name):
 
 
 class Twin:
-    def __init__(self, pb, tables, maxact=32, rho=1.0, al_gamma=1e3):
+    def __init__(self, pb, tables, maxact=32, rho_rel=1e4, **_ignored):
         self.pb, self.tab = pb, tables
         self.lib = ctypes.CDLL(build(pb.name))
-        self.maxact, self.rho, self.al_gamma = maxact, rho, al_gamma
+        self.maxact, self.rho_rel = maxact, rho_rel
         self.reset(1)
 
     def reset(self, B):
@@ -62,7 +63,7 @@ class Twin:
         hm = pb.hessian_approximation if hessian is None else hessian
         iopts = np.array([1 if hm == "exact" else 0, pb.max_iter, 300, self.maxact,
                           1 if getattr(pb, "mpc_type", "tuned") == "economic" else 0], dtype=np.int32)
-        dopts = np.array([pb.tol if tol is None else tol, 1e-8, 0.8, 1e-8, self.rho, self.al_gamma], dtype=np.float64)
+        dopts = np.array([pb.tol if tol is None else tol, 1e-8, 0.8, 1e-8, self.rho_rel], dtype=np.float64)
         Hs = np.ascontiguousarray(0.5 * (pb.H + np.transpose(pb.H, (0, 2, 1))))
         relax0 = np.zeros(max(pb.nh, 1), dtype=np.int32)
         for i in pb.h_x_idx:

@@ -339,8 +339,8 @@ void tmpc_default_opts(tmpc_opts* o) {
   o->lam_tresh = 1e-8;
   o->ls_step_factor = 0.8;
   o->reg_tol = 1e-8;
-  o->term_penalty = 3e7;   // 1e7..1e8: below, marginally convex reduced Hessians fail the base factorisation; above, round-off (profiles/r01c_summary.md)
-  o->al_gamma = 1e3;
+  o->max_working_set = 32;
+  o->term_weight = 1e4;
   o->economic = 0;
 }
 
@@ -382,13 +382,23 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
   P.n_g = NX + dims->N * (NX + dims->nh) + dims->nx_term;
   P.economic = h->opts.economic ? 1 : 0;
   P.hessian_exact = (h->opts.hessian_exact || P.economic) ? 1 : 0;   // economic MPC: exact Hessian forced (pmpc.py:97-107)
-  P.filter_cap = 64;
-  P.max_iter = h->opts.max_iter < P.filter_cap - 1 ? h->opts.max_iter : P.filter_cap - 1;
+  P.filter_cap = 64;                      // rows of the pruned filter (tm_post): bounds memory, not the iteration count
+  P.max_iter = h->opts.max_iter;           // pmpc.py:155 (2000), honoured as given
   P.max_ls = h->opts.max_ls_iter;
-  P.maxact = 32;
-  if (P.maxact < P.nxt + 4) P.maxact = P.nxt + 4;
+  // capacity of the dual active set's working set (rows ADDED to the base rows of one QP; the base rows -- terminal rows and
+  // the rows active in the multipliers -- live in the factorisation and do not count): every inequality row if that is small
+  P.maxact = h->opts.max_working_set > 0 ? h->opts.max_working_set : 32;
+  if (P.maxact > P.N * P.nh) P.maxact = P.N * P.nh;
+  P.maxact += P.nxt;                       // the terminal rows are permanent members of the Schur complement
+  if (P.maxact < 1) P.maxact = 1;
+  if (P.N * P.nh > 32 * TM_ALW) {
+    h->err = "tmpc_create: N*nh exceeds the row-mask capacity";
+    fprintf(stderr, "tmpc_create: N*nh = %d exceeds the %d-row capacity of the working-set masks (TM_ALW)\n", P.N * P.nh, 32 * TM_ALW);
+    delete h;
+    return 6;
+  }
   P.tol = h->opts.tol; P.lam_tresh = h->opts.lam_tresh; P.beta = h->opts.ls_step_factor;
-  P.reg_tol = h->opts.reg_tol; P.rho = h->opts.term_penalty; P.al_gamma = h->opts.al_gamma;
+  P.reg_tol = h->opts.reg_tol; P.rho_rel = h->opts.term_weight;
   {
     // warp-per-instance QP kernels keep the workspace of their instances in shared memory: 2 per CTA if that fits, else
     // 1, else those kernels are not used at all (thread-per-instance kernel for every launch, no shared first QP)
@@ -665,14 +675,15 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
     }
     CK(cudaMemsetAsync(h->cnts, 0, 4 * sizeof(int), st));
     CK(cudaEventRecord(h->ev[0], st));
-    for (int pass = 0; pass < 5; ++pass) {
-      // pass 0: the active list (host-known count); passes 1..4: re-solves queued by the previous pass (device count)
-      const int* plist = pass == 0 ? cur : ((pass & 1) ? h->retry_a : h->retry_b);
-      const int* pcnt = pass == 0 ? nullptr : h->cnts + 2 + ((pass - 1) & 1);
-      S.list_retry = (pass & 1) ? h->retry_b : h->retry_a;
-      S.cnt_retry = h->cnts + 2 + (pass & 1);
-      if (pass >= 2) CK(cudaMemsetAsync(S.cnt_retry, 0, sizeof(int), st));
-      const bool use_thread = h->qp_mode == 1 || (h->qp_mode == 2 && nact >= (pass == 0 ? h->qp_thread_min : 8 * (int64_t)h->qp_thread_min));
+    for (int pass = 0; pass < 2; ++pass) {
+      // pass 0: the active list (host-known count); pass 1: instances the shared-table route of the first QP handed
+      // back (device count).  Re-solves of one instance's QP (released base rows, Gauss-Newton fallback) happen inside tm_qp.
+      const int* plist = pass == 0 ? cur : h->retry_a;
+      const int* pcnt = pass == 0 ? nullptr : h->cnts + 2;
+      S.list_retry = h->retry_a;
+      S.cnt_retry = h->cnts + 2;
+      const bool use_thread = h->qp_mode == 1 || (h->qp_mode == 2 && nact >= h->qp_thread_min);
+      bool q0 = false;
       if (pass == 0 && iter_guard == 0 && was_uniform && h->q0_ok && B >= h->q0_min && B > 1 && h->phase_clean[S.phase]) {
         // every instance shares (w0, lam0): tabulate the parametric QP once, then one thread per instance on the tables
         const TmQp0Tab& T = h->q0;
@@ -681,11 +692,15 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
         k_qp0_derive<<<(T.nT * T.EI + 127) / 128, 128, 0, st>>>(P, S, T);
         k_qp0<<<(unsigned)((B + Q0_THREADS - 1) / Q0_THREADS), Q0_THREADS, 0, st>>>(P, S, T, (int)B);
         launches += 2;
+        q0 = true;
+      } else if (pass == 1 && !(iter_guard == 0 && was_uniform)) {
+        break;                                     // nothing can be queued outside the shared-table route
       } else if (use_thread)
         CK(tm_launch_qp_thread(P, S, plist, (int)nact, pcnt, h->qp_ws, h->qp_ws_per_inst, h->qp_blocks, h->qp_counter, st));
       else
         k_qp<<<(unsigned)((nact + h->qp_warps - 1) / h->qp_warps), h->qp_warps * 32, h->qp_smem, st>>>(P, S, plist, (int)nact, pcnt);
       ++launches;
+      if (pass == 0 && !q0) break;
     }
     CK(cudaEventRecord(h->ev[1], st));
     CK(launch_lin(h, cur, nact, 1, st));

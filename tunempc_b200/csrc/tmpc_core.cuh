@@ -102,7 +102,7 @@ struct TmProb {
   int N, nh, nxt, p, n_w, n_g;
   int hessian_exact, max_iter, max_ls, filter_cap, maxact;
   int economic;           // 1: stage cost = the model card's l(x,u) (economic MPC, pmpc.py:97-107), 0: tuned tracking cost (mtools.py:43-57)
-  double tol, lam_tresh, beta, reg_tol, rho, al_gamma;
+  double tol, lam_tresh, beta, reg_tol, rho_rel;
   const double *wref, *H, *q, *ref_du, *C, *c;   // wref p*nz | H p*nz*nz (symmetric) | q p*nz | ref_du p*n_g | C nh*nz | c nh
   const int *term_idx, *relax0;
 };
@@ -754,906 +754,7 @@ TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, i
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// K3: QP.  Riccati factorisation of the dynamics-constrained base problem (exact terminal penalty rho), then a
-// Goldfarb-Idnani dual active-set iteration in which every other constraint (terminal equality rows first, then the
-// violated inequality rows one at a time) lives in a small dense Schur complement S = N' G N, G = base inverse.
-// Exact active-set solution: inactive multipliers are exact zeros, as the reference relies on (sqp_method.py:421).
-// ---------------------------------------------------------------------------------------------------------------
-struct TmQpWs {
-  TmP AB, Q, r, b, K, Lc, hv, d, y, rhs, kk, kkm, P0, P1, PAB, F, pv, tr;
-  TmP sl;                 // E = N*nh + nxt: current value of every constraint row (slack / terminal residual)
-  TmP Mc;                 // M x E: column j = N G n_j of the dual Hessian for working-set member j (+ one candidate)
-  TmP Lf;                 // M x M: Cholesky factor of the working-set Schur complement S = N_A G N_A'
-  TmP cA, rv, nu, acts, acte, sc;   // per member: L^-1 S_Aq, S^-1 S_Aq, multiplier, sign, row id; scalars
-};
-
-TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
-  const size_t E = (size_t)N * nh + nxt;
-  size_t n = 0;
-  n += (size_t)N * NX * NZ;        // AB
-  n += (size_t)N * NZ * NZ;        // Q
-  n += (size_t)(N + 1) * NZ;       // r
-  n += (size_t)N * NX;             // b
-  n += (size_t)N * NU * NX;        // K
-  n += (size_t)N * NU * NU;        // Lc
-  n += (size_t)N * (nh > 0 ? nh : 1);   // hv
-  n += 3 * (size_t)(N + 1) * NZ;   // d y rhs
-  n += (size_t)N * NU;             // kk
-  n += (size_t)NX * N * NU;        // kkm (feed-forward of the multi-right-hand-side terminal sweep)
-  n += 2 * NX * NX + NX * NZ + NZ * NZ;   // P0 P1 PAB F
-  n += 4 * NX;                     // pv (two buffers of NX, e0, spare)
-  n += (nxt > 0 ? nxt : 1);        // tr
-  n += (E > 0 ? E : 1);            // sl
-  n += (size_t)(M + 1) * (E > 0 ? E : 1);   // Mc (+1 candidate column)
-  n += (size_t)M * M;              // Lf
-  n += 5 * (size_t)M + 8;          // cA rv nu acts acte sc
-  return n;
-}
-
-TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s) {
-  const size_t E = (size_t)N * nh + nxt;
-  size_t o = 0;
-#define TM_CARVE(member, n) s.member = tm_mkp(base, o); o += (size_t)(n)
-  TM_CARVE(AB, (size_t)N * NX * NZ);
-  TM_CARVE(Q, (size_t)N * NZ * NZ);
-  TM_CARVE(r, (size_t)(N + 1) * NZ);
-  TM_CARVE(b, (size_t)N * NX);
-  TM_CARVE(K, (size_t)N * NU * NX);
-  TM_CARVE(Lc, (size_t)N * NU * NU);
-  TM_CARVE(hv, (size_t)N * (nh > 0 ? nh : 1));
-  TM_CARVE(d, (size_t)(N + 1) * NZ);
-  TM_CARVE(y, (size_t)(N + 1) * NZ);
-  TM_CARVE(rhs, (size_t)(N + 1) * NZ);
-  TM_CARVE(kk, (size_t)N * NU);
-  TM_CARVE(kkm, (size_t)NX * N * NU);
-  TM_CARVE(P0, NX * NX);
-  TM_CARVE(P1, NX * NX);
-  TM_CARVE(PAB, NX * NZ);
-  TM_CARVE(F, NZ * NZ);
-  TM_CARVE(pv, 4 * NX);
-  TM_CARVE(tr, (nxt > 0 ? nxt : 1));
-  TM_CARVE(sl, (E > 0 ? E : 1));
-  TM_CARVE(Mc, (size_t)(M + 1) * (E > 0 ? E : 1));
-  TM_CARVE(Lf, (size_t)M * M);
-  TM_CARVE(cA, M);
-  TM_CARVE(rv, M);
-  TM_CARVE(nu, M);
-  TM_CARVE(acts, M);
-  TM_CARVE(acte, M);
-  TM_CARVE(sc, 8);
-#undef TM_CARVE
-}
-
-// Cholesky of the NU x NU block Fuu (row-major, in registers of every lane): returns 0 if a pivot <= thr
-TM_HD int tm_chol_small(const double* Fuu, double* L, double thr) {
-#pragma unroll
-  for (int i = 0; i < NU * NU; ++i) L[i] = 0.0;
-  for (int c = 0; c < NU; ++c) {
-    double dg = Fuu[c * NU + c];
-    for (int l = 0; l < c; ++l) dg -= L[c * NU + l] * L[c * NU + l];
-    if (!(dg > thr)) return 0;
-    const double ld = sqrt(dg);
-    L[c * NU + c] = ld;
-    for (int rr = c + 1; rr < NU; ++rr) {
-      double v = Fuu[rr * NU + c];
-      for (int l = 0; l < c; ++l) v -= L[rr * NU + l] * L[c * NU + l];
-      L[rr * NU + c] = v / ld;
-    }
-  }
-  return 1;
-}
-// solve (L L') x = rhs in place
-template <class PL>
-TM_HD void tm_chol_small_solve(PL L, double* x) {
-  for (int i = 0; i < NU; ++i) {
-    double v = x[i];
-    for (int l = 0; l < i; ++l) v -= L[i * NU + l] * x[l];
-    x[i] = v / L[i * NU + i];
-  }
-  for (int i = NU - 1; i >= 0; --i) {
-    double v = x[i];
-    for (int l = i + 1; l < NU; ++l) v -= L[l * NU + i] * x[l];
-    x[i] = v / L[i * NU + i];
-  }
-}
-
-// homogeneous base solve:  out = argmin 1/2 d'Qd + rhs'd  s.t. d_x0 = 0, d_x(k+1) = A d_x + B d_u   ( = -G rhs )
-// kfrom: last stage with a non-zero right-hand side (N = the x_N block): the backward sweep starts there.
-TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, TmP rhs, TmP out, int kfrom) {
-  const int N = P.N;
-  const int lane = TM_LANE;
-  TmP pv0 = s.pv;
-  TmP pv1 = s.pv + NX;
-  for (int a = lane; a < NX; a += TM_NL) pv0[a] = (kfrom >= N) ? rhs[N * NZ + a] : 0.0;
-  TM_SYNC();
-  const int kb = (kfrom >= N) ? N - 1 : kfrom;
-  for (int k = kb; k >= 0; --k) {
-    const TmP AB = s.AB + (size_t)k * NX * NZ;
-    const TmP Kk = s.K + (size_t)k * NU * NX;
-    const TmP L = s.Lc + (size_t)k * NU * NU;
-    const TmP rk = rhs + k * NZ;
-    double pvr[NX];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) pvr[i] = pv0[i];
-    double fu[NU];
-#pragma unroll
-    for (int a = 0; a < NU; ++a) {
-      double v = rk[NX + a];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) v += AB[i * NZ + NX + a] * pvr[i];
-      fu[a] = v;
-    }
-    for (int j = lane; j < NX; j += TM_NL) {
-      double v = rk[j];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) v += AB[i * NZ + j] * pvr[i];
-#pragma unroll
-      for (int a = 0; a < NU; ++a) v += Kk[a * NX + j] * fu[a];
-      pv1[j] = v;
-    }
-    double ku[NU];
-#pragma unroll
-    for (int a = 0; a < NU; ++a) ku[a] = -fu[a];
-    tm_chol_small_solve(L, ku);
-    for (int a = lane; a < NU; a += TM_NL) s.kk[k * NU + a] = ku[a];
-    TM_SYNC();
-    TmP t = pv0; pv0 = pv1; pv1 = t;
-  }
-  for (int a = lane; a < NX; a += TM_NL) out[a] = 0.0;
-  TM_SYNC();
-  for (int k = 0; k < N; ++k) {
-    const TmP AB = s.AB + (size_t)k * NX * NZ;
-    const TmP Kk = s.K + (size_t)k * NU * NX;
-    const TmP dx = out + k * NZ;
-    double dxr[NX];
-#pragma unroll
-    for (int j = 0; j < NX; ++j) dxr[j] = dx[j];
-    double du[NU];
-#pragma unroll
-    for (int a = 0; a < NU; ++a) {
-      double v = (k <= kb) ? s.kk[k * NU + a] : 0.0;
-#pragma unroll
-      for (int j = 0; j < NX; ++j) v += Kk[a * NX + j] * dxr[j];
-      du[a] = v;
-    }
-    for (int a = lane; a < NU; a += TM_NL) out[k * NZ + NX + a] = du[a];
-    for (int i = lane; i < NX; i += TM_NL) {
-      double v = 0.0;
-#pragma unroll
-      for (int j = 0; j < NX; ++j) v += AB[i * NZ + j] * dxr[j];
-#pragma unroll
-      for (int a = 0; a < NU; ++a) v += AB[i * NZ + NX + a] * du[a];
-      out[(k + 1) * NZ + i] = v;
-    }
-    TM_SYNC();
-  }
-  for (int a = lane; a < NU; a += TM_NL) out[N * NZ + NX + a] = 0.0;
-  TM_SYNC();
-}
-
-// ---- dual-Hessian columns ---------------------------------------------------------------------------------------
-// Column for constraint row qe:  y = qs * G n_qe  is swept stage by stage and never stored; mq[e] = n_e' y for every
-// row e.  The NX-wide recursions are carried in registers by every lane (too small to split; no synchronisation inside
-// the sweeps); workspace traffic is the factor (AB, K, Lc), the per-stage feed-forward kk and the column itself.
-TM_HD void tm_ricc_col(const TmProb& P, TmQpWs& s, int qe, double qs, TmP mq) {
-  const int N = P.N, nh = P.nh, NI = N * nh;
-  const int lane = TM_LANE;
-  double pv[NX], rz[NZ];
-#pragma unroll
-  for (int a = 0; a < NX; ++a) pv[a] = 0.0;
-#pragma unroll
-  for (int b = 0; b < NZ; ++b) rz[b] = 0.0;
-  int kb;
-  if (qe >= NI) {
-    const int ti = P.term_idx[qe - NI];
-#pragma unroll
-    for (int a = 0; a < NX; ++a) if (a == ti) pv[a] = -qs;
-    kb = N - 1;
-  } else {
-    kb = qe / nh;
-    const double* Ci = P.C + (size_t)(qe % nh) * NZ;
-#pragma unroll
-    for (int b = 0; b < NZ; ++b) rz[b] = -qs * Ci[b];
-  }
-  for (int k = kb; k >= 0; --k) {
-    const TmP AB = s.AB + (size_t)k * NX * NZ;
-    const TmP Kk = s.K + (size_t)k * NU * NX;
-    const TmP L = s.Lc + (size_t)k * NU * NU;
-    double fu[NU > 0 ? NU : 1], pn[NX];
-#pragma unroll
-    for (int a = 0; a < NU; ++a) {
-      double v = (k == kb) ? rz[NX + a] : 0.0;
-#pragma unroll
-      for (int i = 0; i < NX; ++i) v += AB[i * NZ + NX + a] * pv[i];
-      fu[a] = v;
-    }
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {
-      double v = (k == kb) ? rz[j] : 0.0;
-#pragma unroll
-      for (int i = 0; i < NX; ++i) v += AB[i * NZ + j] * pv[i];
-#pragma unroll
-      for (int a = 0; a < NU; ++a) v += Kk[a * NX + j] * fu[a];
-      pn[j] = v;
-    }
-    double ku[NU > 0 ? NU : 1];
-#pragma unroll
-    for (int a = 0; a < NU; ++a) ku[a] = -fu[a];
-    tm_chol_small_solve(L, ku);
-    for (int a = lane; a < NU; a += TM_NL) s.kk[k * NU + a] = ku[a];
-#pragma unroll
-    for (int j = 0; j < NX; ++j) pv[j] = pn[j];
-  }
-  TM_SYNC();
-  double z[NZ];
-#pragma unroll
-  for (int b = 0; b < NZ; ++b) z[b] = 0.0;
-  for (int k = 0; k < N; ++k) {
-    const TmP AB = s.AB + (size_t)k * NX * NZ;
-    const TmP Kk = s.K + (size_t)k * NU * NX;
-#pragma unroll
-    for (int a = 0; a < NU; ++a) {
-      double v = (k <= kb) ? s.kk[k * NU + a] : 0.0;
-#pragma unroll
-      for (int j = 0; j < NX; ++j) v += Kk[a * NX + j] * z[j];
-      z[NX + a] = v;
-    }
-    for (int i = lane; i < nh; i += TM_NL) {
-      const double* Ci = P.C + (size_t)i * NZ;
-      double t = 0.0;
-#pragma unroll
-      for (int b = 0; b < NZ; ++b) t += Ci[b] * z[b];
-      mq[k * nh + i] = t;
-    }
-    double xn[NX];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      double v = 0.0;
-#pragma unroll
-      for (int b = 0; b < NZ; ++b) v += AB[i * NZ + b] * z[b];
-      xn[i] = v;
-    }
-#pragma unroll
-    for (int i = 0; i < NX; ++i) z[i] = xn[i];
-  }
-  for (int t = lane; t < P.nxt; t += TM_NL) {
-    const int ti = P.term_idx[t];
-    double v = 0.0;
-#pragma unroll
-    for (int a = 0; a < NX; ++a) if (a == ti) v = z[a];
-    mq[NI + t] = v;
-  }
-  TM_SYNC();
-}
-
-// The columns of ALL terminal rows (sign +1) in one multi-right-hand-side sweep: column t -> Mc[t*E + e].  The factor is
-// read once for the nxt (<= NX) right-hand sides instead of once per row.
-TM_HD void tm_ricc_cols_term(const TmProb& P, TmQpWs& s, TmP Mc, int E) {
-  const int N = P.N, nh = P.nh, NI = N * nh, nxt = P.nxt;
-  const int lane = TM_LANE;
-  double pv[NX][NX];
-#pragma unroll
-  for (int c = 0; c < NX; ++c) {
-    const int ti = (c < nxt) ? P.term_idx[c] : -1;
-#pragma unroll
-    for (int a = 0; a < NX; ++a) pv[c][a] = (a == ti) ? -1.0 : 0.0;
-  }
-  for (int k = N - 1; k >= 0; --k) {
-    const TmP AB = s.AB + (size_t)k * NX * NZ;
-    const TmP Kk = s.K + (size_t)k * NU * NX;
-    const TmP L = s.Lc + (size_t)k * NU * NU;
-    double ABr[NX * NZ], Kr[NU * NX > 0 ? NU * NX : 1], Lr[NU * NU > 0 ? NU * NU : 1];
-#pragma unroll
-    for (int e = 0; e < NX * NZ; ++e) ABr[e] = AB[e];
-#pragma unroll
-    for (int e = 0; e < NU * NX; ++e) Kr[e] = Kk[e];
-#pragma unroll
-    for (int e = 0; e < NU * NU; ++e) Lr[e] = L[e];
-#pragma unroll
-    for (int c = 0; c < NX; ++c) {
-      double fu[NU > 0 ? NU : 1], pn[NX];
-#pragma unroll
-      for (int a = 0; a < NU; ++a) {
-        double v = 0.0;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) v += ABr[i * NZ + NX + a] * pv[c][i];
-        fu[a] = v;
-      }
-#pragma unroll
-      for (int j = 0; j < NX; ++j) {
-        double v = 0.0;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) v += ABr[i * NZ + j] * pv[c][i];
-#pragma unroll
-        for (int a = 0; a < NU; ++a) v += Kr[a * NX + j] * fu[a];
-        pn[j] = v;
-      }
-      double ku[NU > 0 ? NU : 1];
-#pragma unroll
-      for (int a = 0; a < NU; ++a) ku[a] = -fu[a];
-      tm_chol_small_solve(Lr, ku);
-      for (int a = lane; a < NU; a += TM_NL) s.kkm[((size_t)c * N + k) * NU + a] = ku[a];
-#pragma unroll
-      for (int j = 0; j < NX; ++j) pv[c][j] = pn[j];
-    }
-  }
-  TM_SYNC();
-  double z[NX][NZ];
-#pragma unroll
-  for (int c = 0; c < NX; ++c)
-#pragma unroll
-    for (int b = 0; b < NZ; ++b) z[c][b] = 0.0;
-  for (int k = 0; k < N; ++k) {
-    const TmP AB = s.AB + (size_t)k * NX * NZ;
-    const TmP Kk = s.K + (size_t)k * NU * NX;
-    double ABr[NX * NZ], Kr[NU * NX > 0 ? NU * NX : 1];
-#pragma unroll
-    for (int e = 0; e < NX * NZ; ++e) ABr[e] = AB[e];
-#pragma unroll
-    for (int e = 0; e < NU * NX; ++e) Kr[e] = Kk[e];
-#pragma unroll
-    for (int c = 0; c < NX; ++c) {
-#pragma unroll
-      for (int a = 0; a < NU; ++a) {
-        double v = s.kkm[((size_t)c * N + k) * NU + a];
-#pragma unroll
-        for (int j = 0; j < NX; ++j) v += Kr[a * NX + j] * z[c][j];
-        z[c][NX + a] = v;
-      }
-    }
-    for (int i = lane; i < nh; i += TM_NL) {
-      const double* Ci = P.C + (size_t)i * NZ;
-#pragma unroll
-      for (int c = 0; c < NX; ++c) {
-        double t = 0.0;
-#pragma unroll
-        for (int b = 0; b < NZ; ++b) t += Ci[b] * z[c][b];
-        if (c < nxt) Mc[(size_t)c * E + k * nh + i] = t;
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < NX; ++c) {
-      double xn[NX];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        double v = 0.0;
-#pragma unroll
-        for (int b = 0; b < NZ; ++b) v += ABr[i * NZ + b] * z[c][b];
-        xn[i] = v;
-      }
-#pragma unroll
-      for (int i = 0; i < NX; ++i) z[c][i] = xn[i];
-    }
-  }
-  for (int t = lane; t < nxt; t += TM_NL) {
-    const int ti = P.term_idx[t];
-#pragma unroll
-    for (int c = 0; c < NX; ++c) {
-      double v = 0.0;
-#pragma unroll
-      for (int a = 0; a < NX; ++a) if (a == ti) v = z[c][a];
-      if (c < nxt) Mc[(size_t)c * E + NI + t] = v;
-    }
-  }
-  TM_SYNC();
-}
-
-// constraint rows by unified id e: e < N*nh is inequality row (k = e / nh, i = e % nh), e >= N*nh terminal row
-TM_HD double tm_erow_dot(const TmProb& P, int e, TmP v) {
-  const int NI = P.N * P.nh;
-  if (e >= NI) return v[P.N * NZ + P.term_idx[e - NI]];
-  const int k = e / P.nh, i = e % P.nh;
-  double t = 0.0;
-  const double* Ci = P.C + (size_t)i * NZ;
-  const TmP vk = v + k * NZ;
-#pragma unroll
-  for (int b = 0; b < NZ; ++b) t += Ci[b] * vk[b];
-  return t;
-}
-// rhs += coef * n_e   (single lane)
-TM_HD void tm_erow_axpy(const TmProb& P, int e, double coef, TmP rhs) {
-  const int NI = P.N * P.nh;
-  if (e >= NI) { rhs[P.N * NZ + P.term_idx[e - NI]] += coef; return; }
-  const int k = e / P.nh, i = e % P.nh;
-  const double* Ci = P.C + (size_t)i * NZ;
-#pragma unroll
-  for (int b = 0; b < NZ; ++b) rhs[k * NZ + b] += coef * Ci[b];
-}
-
-// rebuild the Cholesky factor Lf of S_ij = acts_i * Mc[j][acte_i] (i, j < m) after a deletion (single lane)
-TM_HD int tm_schur_refactor(TmQpWs& s, int m, int M, int E) {
-  for (int i = 0; i < m; ++i)
-    for (int j = 0; j <= i; ++j) s.Lf[i * M + j] = s.acts[i] * s.Mc[(size_t)j * E + (int)s.acte[i]];
-  for (int c = 0; c < m; ++c) {
-    double dg = s.Lf[c * M + c];
-    for (int l = 0; l < c; ++l) dg -= s.Lf[c * M + l] * s.Lf[c * M + l];
-    if (!(dg > 0.0)) return 0;
-    const double ld = sqrt(dg);
-    s.Lf[c * M + c] = ld;
-    for (int i = c + 1; i < m; ++i) {
-      double v = s.Lf[i * M + c];
-      for (int l = 0; l < c; ++l) v -= s.Lf[i * M + l] * s.Lf[c * M + l];
-      s.Lf[i * M + c] = v / ld;
-    }
-  }
-  return 1;
-}
-
-// returns: 0 ok, 2 infeasible / working-set overflow / numerical breakdown, 3 base factorisation not PD
-// al_mask: rows (k*nh+i) whose squared slack  gamma/2 (C_i d + h_i)^2  is added to the base problem.  The term and its
-// gradient vanish wherever the row is active at the QP solution, so the solution is unchanged iff every masked row ends
-// up in the working set; rows that do not are reported in al_bad (caller removes them and re-solves).  This makes the
-// base factorisation positive definite on the null space of (dynamics + warm-start active rows) -- the space on which
-// the reference tests and regularises its reduced Hessian (sqp_method.py:335-347) -- instead of dynamics only.
-// Perturbed solve used to tabulate the solution map of the first QP after reset() (tm_qp0_*, below): the equality-
-// constrained part of the QP (dynamics, x_0, terminal rows; inequality rows ignored) is solved for modified data and
-// the result goes to (dout, lout) instead of the instance's D / LAMQ.
-struct TmQpPert {
-  int homog;      // 1: zero all offsets (gradient r, dynamics defect b, terminal residual): pure linear response; the x_0 offset is always zeroed
-  int e0_unit;    // >= 0: x_0 offset = unit vector e0_unit
-  int row;        // >= 0: gradient -= n_row (response to a unit multiplier on inequality row `row` = k*nh + i)
-  double *dout, *lout;
-};
-
-TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& s, int use_exact,
-                       const unsigned* al_mask, unsigned* al_bad, const TmQpPert* pert = nullptr) {
-  const int N = P.N, nh = P.nh, nxt = P.nxt, M = P.maxact;
-  const int lane = TM_LANE;
-  const double* w = S.W + inst * P.n_w;
-  const double* lin = S.LIN + inst * P.N * (int64_t)TM_LSZ;
-  // ---- A. stage data ------------------------------------------------------------------------------------------
-  for (int e = lane; e < N * NX * NZ; e += TM_NL) { int k = e / (NX * NZ), o = e % (NX * NZ); s.AB[e] = lin[(size_t)k * TM_LSZ + NX + o]; }
-  for (int e = lane; e < N * NX; e += TM_NL) { int k = e / NX, a = e % NX; s.b[e] = lin[(size_t)k * TM_LSZ + a] - w[(k + 1) * NZ + a]; }
-  if (P.economic) {
-    // economic stage cost: Q_k = d2l/dz2 (+ lam' d2F), r_k = dl/dz at the iterate
-    for (int k = lane; k < N; k += TM_NL) {
-      double z[NZ], gl[NZ], Hl[NZ * NZ];
-#pragma unroll
-      for (int b = 0; b < NZ; ++b) z[b] = w[k * NZ + b];
-      tmpc_cost_grad(z, z + NX, gl);
-      tmpc_cost_hess(z, z + NX, Hl);
-      for (int i = 0; i < NZ; ++i) {
-        for (int j = 0; j < NZ; ++j) {
-          double v = 0.5 * (Hl[i * NZ + j] + Hl[j * NZ + i]);
-          if (use_exact) v += lin[(size_t)k * TM_LSZ + NX + NX * NZ + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
-          s.Q[(size_t)k * NZ * NZ + i * NZ + j] = v;
-        }
-        s.r[k * NZ + i] = gl[i];
-      }
-    }
-  } else {
-    for (int e = lane; e < N * NZ * NZ; e += TM_NL) {
-      int k = e / (NZ * NZ), o = e % (NZ * NZ), i = o / NZ, j = o % NZ;
-      int ph = (S.phase + k) % P.p;
-      double v = P.H[(size_t)ph * NZ * NZ + o];
-      if (use_exact) v += lin[(size_t)k * TM_LSZ + NX + NX * NZ + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
-      s.Q[e] = v;
-    }
-    for (int e = lane; e < N * NZ; e += TM_NL) {
-      int k = e / NZ, i = e % NZ;
-      int ph = (S.phase + k) % P.p;
-      const double* Hk = P.H + (size_t)ph * NZ * NZ + (size_t)i * NZ;
-      const double* wr = P.wref + (size_t)ph * NZ;
-      double v = P.q[(size_t)ph * NZ + i];
-#pragma unroll
-      for (int j = 0; j < NZ; ++j) v += Hk[j] * (w[k * NZ + j] - wr[j]);
-      s.r[e] = v;
-    }
-  }
-  for (int a = lane; a < NZ; a += TM_NL) s.r[N * NZ + a] = 0.0;
-  for (int e = lane; e < N * nh; e += TM_NL) {
-    int k = e / nh, i = e % nh;
-    double v = P.c[i];
-#pragma unroll
-    for (int j = 0; j < NZ; ++j) v += P.C[(size_t)i * NZ + j] * w[k * NZ + j];
-    s.hv[e] = v;
-  }
-  TmP e0 = s.pv + 2 * NX;
-  for (int a = lane; a < NX; a += TM_NL) e0[a] = S.X0[inst * NX + a] - w[a];
-  {
-    const double* xrN = P.wref + (size_t)((S.phase + N) % P.p) * NZ;
-    for (int t = lane; t < nxt; t += TM_NL) s.tr[t] = w[N * NZ + P.term_idx[t]] - xrN[P.term_idx[t]];
-  }
-  TM_SYNC();
-  if (pert) {
-    if (pert->homog) {
-      for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.r[e] = 0.0;
-      for (int e = lane; e < N * NX; e += TM_NL) s.b[e] = 0.0;
-      for (int t = lane; t < nxt; t += TM_NL) s.tr[t] = 0.0;
-    }
-    for (int a = lane; a < NX; a += TM_NL) e0[a] = 0.0;     // the x_0 offset always enters through the table
-    TM_SYNC();
-    if (pert->e0_unit >= 0) for (int a = lane; a < NX; a += TM_NL) e0[a] = (a == pert->e0_unit) ? 1.0 : 0.0;
-    if (pert->row >= 0) {
-      const int k = pert->row / nh, i = pert->row % nh;
-      for (int b2 = lane; b2 < NZ; b2 += TM_NL) s.r[k * NZ + b2] -= P.C[(size_t)i * NZ + b2];
-    }
-    TM_SYNC();
-  }
-  if (al_mask) {
-    // gamma relative to the largest Hessian diagonal entry of the horizon
-    double qmax = 0.0;
-    for (int e = lane; e < N * NZ; e += TM_NL) { int k = e / NZ, i = e % NZ; qmax = fmax(qmax, fabs(s.Q[(size_t)k * NZ * NZ + i * NZ + i])); }
-    qmax = tm_wmax(qmax);
-    const double gam = P.al_gamma * fmax(qmax, 1e-300);
-    for (int k = lane; k < N; k += TM_NL) {
-      for (int i = 0; i < nh; ++i) {
-        const int e = k * nh + i;
-        if (!((al_mask[e >> 5] >> (e & 31)) & 1u)) continue;
-        const double* Ci = P.C + (size_t)i * NZ;
-        double cc = 0.0;
-#pragma unroll
-        for (int b = 0; b < NZ; ++b) cc += Ci[b] * Ci[b];
-        const double g = gam / cc;
-#pragma unroll
-        for (int a = 0; a < NZ; ++a) {
-#pragma unroll
-          for (int b = 0; b < NZ; ++b) s.Q[(size_t)k * NZ * NZ + a * NZ + b] += g * Ci[a] * Ci[b];
-          s.r[k * NZ + a] += g * s.hv[e] * Ci[a];
-        }
-      }
-    }
-    TM_SYNC();
-  }
-  // ---- B. Riccati factorisation + main solve (offsets b_k, e0, terminal penalty) -------------------------------
-  TmP Pn = s.P0;   // P_{k+1}
-  TmP Pk = s.P1;
-  TmP pv0 = s.pv;
-  TmP pv1 = s.pv + NX;
-  for (int e = lane; e < NX * NX; e += TM_NL) {
-    int i = e / NX, j = e % NX;
-    double v = 0.0;
-    for (int t = 0; t < nxt; ++t) if (P.term_idx[t] == i && i == j) v += P.rho;
-    Pn[e] = v;
-  }
-  for (int a = lane; a < NX; a += TM_NL) {
-    double v = 0.0;
-    for (int t = 0; t < nxt; ++t) if (P.term_idx[t] == a) v += P.rho * s.tr[t];
-    pv0[a] = v;
-  }
-  TM_SYNC();
-  int fail = 0;
-  for (int k = N - 1; k >= 0; --k) {
-    const TmP AB = s.AB + (size_t)k * NX * NZ;
-    const TmP Qk = s.Q + (size_t)k * NZ * NZ;
-    for (int e = lane; e < NX * NZ; e += TM_NL) {
-      int i = e / NZ, c = e % NZ;
-      double v = 0.0;
-#pragma unroll
-      for (int l = 0; l < NX; ++l) v += Pn[i * NX + l] * AB[l * NZ + c];
-      s.PAB[e] = v;
-    }
-    TM_SYNC();
-    for (int e = lane; e < NZ * NZ; e += TM_NL) {
-      int a = e / NZ, c = e % NZ;
-      double v = Qk[e];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) v += AB[i * NZ + a] * s.PAB[i * NZ + c];
-      s.F[e] = v;
-    }
-    TM_SYNC();
-    double Fuu[NU * NU], L[NU * NU];
-#pragma unroll
-    for (int a = 0; a < NU; ++a)
-#pragma unroll
-      for (int c = 0; c < NU; ++c) Fuu[a * NU + c] = 0.5 * (s.F[(NX + a) * NZ + NX + c] + s.F[(NX + c) * NZ + NX + a]);
-    if (!tm_chol_small(Fuu, L, P.reg_tol)) { fail = 1; break; }
-    for (int e = lane; e < NU * NU; e += TM_NL) s.Lc[(size_t)k * NU * NU + e] = L[e];
-    // K = -Fuu^-1 Fux : lane j owns column j
-    for (int j = lane; j < NX; j += TM_NL) {
-      double col[NU];
-#pragma unroll
-      for (int a = 0; a < NU; ++a) col[a] = -0.5 * (s.F[(NX + a) * NZ + j] + s.F[j * NZ + NX + a]);
-      tm_chol_small_solve(L, col);
-#pragma unroll
-      for (int a = 0; a < NU; ++a) s.K[(size_t)k * NU * NX + a * NX + j] = col[a];
-    }
-    TM_SYNC();
-    const TmP Kk = s.K + (size_t)k * NU * NX;
-    // P_k = Fxx + sym(Fux' K)
-    for (int e = lane; e < NX * NX; e += TM_NL) {
-      int i = e / NX, j = e % NX;
-      double v = 0.5 * (s.F[i * NZ + j] + s.F[j * NZ + i]);
-#pragma unroll
-      for (int a = 0; a < NU; ++a) {
-        const double fai = 0.5 * (s.F[(NX + a) * NZ + i] + s.F[i * NZ + NX + a]);
-        const double faj = 0.5 * (s.F[(NX + a) * NZ + j] + s.F[j * NZ + NX + a]);
-        v += 0.5 * (fai * Kk[a * NX + j] + faj * Kk[a * NX + i]);
-      }
-      Pk[e] = v;
-    }
-    // main right-hand side: v = p_{k+1} + P_{k+1} b_k
-    {
-      double vv[NX];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        double t = pv0[i];
-#pragma unroll
-        for (int l = 0; l < NX; ++l) t += Pn[i * NX + l] * s.b[k * NX + l];
-        vv[i] = t;
-      }
-      double fu[NU];
-#pragma unroll
-      for (int a = 0; a < NU; ++a) {
-        double t = s.r[k * NZ + NX + a];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) t += AB[i * NZ + NX + a] * vv[i];
-        fu[a] = t;
-      }
-      for (int j = lane; j < NX; j += TM_NL) {
-        double t = s.r[k * NZ + j];
-#pragma unroll
-        for (int i = 0; i < NX; ++i) t += AB[i * NZ + j] * vv[i];
-#pragma unroll
-        for (int a = 0; a < NU; ++a) t += Kk[a * NX + j] * fu[a];
-        pv1[j] = t;
-      }
-      double ku[NU];
-#pragma unroll
-      for (int a = 0; a < NU; ++a) ku[a] = -fu[a];
-      tm_chol_small_solve(L, ku);
-      for (int a = lane; a < NU; a += TM_NL) s.kk[k * NU + a] = ku[a];
-    }
-    TM_SYNC();
-    { TmP t = Pn; Pn = Pk; Pk = t; }
-    { TmP t = pv0; pv0 = pv1; pv1 = t; }
-  }
-  if (fail) return 3;
-  // forward sweep of the main solve
-  for (int a = lane; a < NX; a += TM_NL) s.d[a] = e0[a];
-  TM_SYNC();
-  for (int k = 0; k < N; ++k) {
-    const TmP AB = s.AB + (size_t)k * NX * NZ;
-    const TmP Kk = s.K + (size_t)k * NU * NX;
-    const TmP dx = s.d + k * NZ;
-    double du[NU];
-#pragma unroll
-    for (int a = 0; a < NU; ++a) {
-      double v = s.kk[k * NU + a];
-#pragma unroll
-      for (int j = 0; j < NX; ++j) v += Kk[a * NX + j] * dx[j];
-      du[a] = v;
-    }
-    for (int a = lane; a < NU; a += TM_NL) s.d[k * NZ + NX + a] = du[a];
-    for (int i = lane; i < NX; i += TM_NL) {
-      double v = s.b[k * NX + i];
-#pragma unroll
-      for (int j = 0; j < NX; ++j) v += AB[i * NZ + j] * dx[j];
-#pragma unroll
-      for (int a = 0; a < NU; ++a) v += AB[i * NZ + NX + a] * du[a];
-      s.d[(k + 1) * NZ + i] = v;
-    }
-    TM_SYNC();
-  }
-  for (int a = lane; a < NU; a += TM_NL) s.d[N * NZ + NX + a] = 0.0;
-  TM_SYNC();
-  // ---- C. Goldfarb-Idnani dual active set, carried in the dual space ----------------------------------------------
-  // The primal iterate is never updated inside the loop: d = d_base + sum_j nu_j G n_j is recovered by ONE solve at
-  // the end.  Per added constraint: one (partial) Riccati solve y = G n_q, its dual-Hessian column Mc_q[e] = n_e'y for
-  // every row e, an O(m^2) Cholesky append, and an O(E m) update of all row values sl[e].
-  const int NI = N * nh, E = NI + nxt;
-  for (int e = lane; e < E; e += TM_NL) s.sl[e] = (e < NI ? s.hv[e] : s.tr[e - NI]) + tm_erow_dot(P, e, s.d);
-  TM_SYNC();
-  int m = 0, ret = 0;
-  int n_gi = 0, n_ricc = 0;
-  if (nxt > 0) {
-    // the terminal equality rows enter together: their columns from one multi-right-hand-side sweep, multipliers from
-    // the nxt x nxt Schur complement (the state the one-at-a-time iteration would reach; equality multipliers are
-    // sign-free and never dropped)
-    tm_ricc_cols_term(P, s, s.Mc, E);
-    n_ricc += 1;
-    if (lane == 0) {
-      for (int t = 0; t < nxt; ++t) { s.acte[t] = (double)(NI + t); s.acts[t] = 1.0; }
-      double ok = (double)tm_schur_refactor(s, nxt, M, E);
-      if (ok != 0.0) {
-        for (int i = 0; i < nxt; ++i) {          // L L' nu = -sl_term
-          double v = -s.sl[NI + i];
-          for (int l = 0; l < i; ++l) v -= s.Lf[i * M + l] * s.nu[l];
-          s.nu[i] = v / s.Lf[i * M + i];
-        }
-        for (int i = nxt - 1; i >= 0; --i) {
-          double v = s.nu[i];
-          for (int l = i + 1; l < nxt; ++l) v -= s.Lf[l * M + i] * s.nu[l];
-          s.nu[i] = v / s.Lf[i * M + i];
-        }
-      }
-      s.sc[1] = ok;
-    }
-    TM_SYNC();
-    if (s.sc[1] == 0.0) ret = 2;
-    else {
-      for (int e = lane; e < E; e += TM_NL) {
-        double acc = 0.0;
-        for (int t = 0; t < nxt; ++t) acc += s.nu[t] * s.Mc[(size_t)t * E + e];
-        s.sl[e] += acc;
-      }
-      m = nxt;
-      TM_SYNC();
-    }
-  }
-  const int maxit = pert ? 0 : 4 * E + 8;
-  for (int it = 0; it < maxit && !ret; ++it) {
-    int qe;
-    double qs = 1.0, sval;
-    {
-      double best = TM_INF;
-      int bid = 0x7fffffff;
-      for (int e = lane; e < NI; e += TM_NL) {
-        const int k = e / nh, i = e % nh;
-        if (k == 0 && P.relax0[i]) continue;
-        const double v = s.sl[e] / fmax(1.0, fabs(P.c[i]));
-        if (v < best) { best = v; bid = e; }
-      }
-      tm_wargmin(best, bid);
-      if (!(best < -1e-10)) break;            // primal feasible: optimal
-      int dup = 0;                            // a working-set row can only show up here through round-off
-      for (int j2 = 0; j2 < m; ++j2) if ((int)s.acte[j2] == bid) dup = 1;
-      if (dup) break;
-      qe = bid;
-      sval = s.sl[qe];
-    }
-    if (m >= M) { ret = 2; break; }
-    TmP mq = s.Mc + (size_t)m * E;            // candidate column, becomes member m when added
-    tm_ricc_col(P, s, qe, qs, mq);
-    ++n_gi; ++n_ricc;
-    const double yq = qs * mq[qe];
-    double nq = 0.0;
-    int added = 0;
-    for (int inner = 0; inner < M + 2; ++inner) {
-      // l = L^-1 S_Aq (kept in cA), zn = yq - l'l, r = L^-T l (rv)
-      if (lane == 0) {
-        double ll = 0.0;
-        for (int i = 0; i < m; ++i) {
-          double v = s.acts[i] * mq[(int)s.acte[i]];
-          for (int l = 0; l < i; ++l) v -= s.Lf[i * M + l] * s.cA[l];
-          v /= s.Lf[i * M + i];
-          s.cA[i] = v;
-          ll += v * v;
-        }
-        for (int i = m - 1; i >= 0; --i) {
-          double v = s.cA[i];
-          for (int l = i + 1; l < m; ++l) v -= s.Lf[l * M + i] * s.rv[l];
-          s.rv[i] = v / s.Lf[i * M + i];
-        }
-        s.sc[0] = ll;
-      }
-      TM_SYNC();
-      const double zn = yq - s.sc[0];
-      double t1 = TM_INF;
-      int jd = -1;
-      for (int j2 = 0; j2 < m; ++j2) {
-        if ((int)s.acte[j2] >= NI) continue;           // equality rows are never dropped
-        const double rj = s.rv[j2];
-        if (rj > 1e-14) { const double tj = s.nu[j2] / rj; if (tj < t1) { t1 = tj; jd = j2; } }
-      }
-      const int dependent = !(zn > 1e-11 * fmax(yq, 1e-300));
-      double t;
-      int do_add = 0;
-      if (dependent) {
-        if (jd < 0) { ret = 2; break; }
-        t = t1;
-      } else {
-        const double t2 = -sval / zn;
-        if (t2 <= t1) { t = t2; do_add = 1; } else t = t1;
-        for (int e = lane; e < E; e += TM_NL) {
-          double acc = mq[e];
-          for (int j2 = 0; j2 < m; ++j2) acc -= s.rv[j2] * s.Mc[(size_t)j2 * E + e];
-          s.sl[e] += t * acc;
-        }
-        sval += t * zn;
-      }
-      TM_SYNC();
-      for (int j2 = lane; j2 < m; j2 += TM_NL) s.nu[j2] -= t * s.rv[j2];
-      nq += t;
-      TM_SYNC();
-      if (do_add) {
-        if (lane == 0) {
-          for (int l = 0; l < m; ++l) s.Lf[m * M + l] = s.cA[l];
-          s.Lf[m * M + m] = sqrt(zn);
-          s.acte[m] = (double)qe; s.acts[m] = qs; s.nu[m] = nq;
-        }
-        TM_SYNC();
-        ++m;
-        added = 1;
-        break;
-      }
-      // drop member jd: shift members jd+1..m-1 and the candidate column down by one slot, rebuild the factor
-      for (int a = jd; a < m; ++a) {
-        for (int e = lane; e < E; e += TM_NL) s.Mc[(size_t)a * E + e] = s.Mc[(size_t)(a + 1) * E + e];
-        TM_SYNC();
-      }
-      if (lane == 0) {
-        for (int a = jd; a < m - 1; ++a) { s.acte[a] = s.acte[a + 1]; s.acts[a] = s.acts[a + 1]; s.nu[a] = s.nu[a + 1]; }
-      }
-      --m;
-      TM_SYNC();
-      mq = s.Mc + (size_t)m * E;
-      if (lane == 0) s.sc[1] = (double)tm_schur_refactor(s, m, M, E);
-      TM_SYNC();
-      if (s.sc[1] == 0.0) { ret = 2; break; }
-    }
-    if (ret) break;
-    if (!added) { ret = 2; break; }
-    if (it == maxit - 1) ret = 2;
-  }
-  if (!ret) {
-    // primal recovery: d = d_base + G N_A' nu  (one full solve)
-    for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.rhs[e] = 0.0;
-    TM_SYNC();
-    int kfrom = -1;
-    if (lane == 0) for (int j2 = 0; j2 < m; ++j2) tm_erow_axpy(P, (int)s.acte[j2], -s.acts[j2] * s.nu[j2], s.rhs);
-    for (int j2 = 0; j2 < m; ++j2) { const int e = (int)s.acte[j2]; const int k = e < NI ? e / nh : N; if (k > kfrom) kfrom = k; }
-    TM_SYNC();
-    if (m > 0) {
-      tm_ricc_solve(P, s, s.rhs, s.y, kfrom);
-      ++n_ricc;
-      for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.d[e] += s.y[e];
-      TM_SYNC();
-    }
-  }
-  if (lane == 0 && !pert) {
-    S.qpwork[inst] = n_gi;
-#ifdef __CUDA_ARCH__
-    atomicAdd(S.counters + 5, 1ull); atomicAdd(S.counters + 6, (unsigned long long)n_gi); atomicAdd(S.counters + 7, (unsigned long long)n_ricc);
-#else
-    S.counters[5] += 1; S.counters[6] += n_gi; S.counters[7] += n_ricc;
-#endif
-  }
-  if (ret) return ret;
-  if (al_mask) {
-    int nbad = 0;
-    for (int wd = 0; wd < TM_ALW; ++wd) al_bad[wd] = 0u;
-    for (int e = 0; e < NI && e < 32 * TM_ALW; ++e) {
-      if (!((al_mask[e >> 5] >> (e & 31)) & 1u)) continue;
-      int found = 0;
-      for (int j2 = 0; j2 < m; ++j2) if ((int)s.acte[j2] == e) found = 1;
-      if (!found) { al_bad[e >> 5] |= (1u << (e & 31)); ++nbad; }
-    }
-    if (nbad) return 5;
-  }
-  // ---- D. outputs: step and multipliers (CasADi sign: H d + g + J' lam = 0) ------------------------------------
-  double* dout = pert ? pert->dout : S.D + inst * P.n_w;
-  double* lq = pert ? pert->lout : S.LAMQ + inst * P.n_g;
-  for (int e = lane; e < P.n_w; e += TM_NL) dout[e] = s.d[e];
-  for (int e = lane; e < P.n_g; e += TM_NL) lq[e] = 0.0;
-  TM_SYNC();
-  if (lane == 0) {
-    for (int j2 = 0; j2 < m; ++j2) {
-      const int e = (int)s.acte[j2];
-      if (e >= NI) lq[tm_gterm(P) + (e - NI)] = -s.acts[j2] * s.nu[j2];
-      else lq[tm_gh(P, e / nh) + e % nh] = -s.nu[j2];
-    }
-  }
-  TM_SYNC();
-  // dynamics multipliers by the stationarity recursion (pv0/pv1 reused as lam_{k}, lam_{k-1})
-  pv0 = s.pv; pv1 = s.pv + NX;
-  for (int a = lane; a < NX; a += TM_NL) {
-    double v = 0.0;
-    for (int t = 0; t < nxt; ++t) if (P.term_idx[t] == a) v += lq[tm_gterm(P) + t];
-    pv0[a] = v;
-  }
-  TM_SYNC();
-  for (int k = N - 1; k >= 0; --k) {
-    const TmP AB = s.AB + (size_t)k * NX * NZ;
-    const TmP Qk = s.Q + (size_t)k * NZ * NZ;
-    for (int a = lane; a < NX; a += TM_NL) lq[tm_gdyn(P, k) + a] = pv0[a];
-    for (int j = lane; j < NX; j += TM_NL) {
-      double v = s.r[k * NZ + j];
-#pragma unroll
-      for (int c = 0; c < NZ; ++c) v += 0.5 * (Qk[j * NZ + c] + Qk[c * NZ + j]) * s.d[k * NZ + c];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) v += AB[i * NZ + j] * pv0[i];
-      for (int i = 0; i < nh; ++i) v += P.C[(size_t)i * NZ + j] * lq[tm_gh(P, k) + i];
-      pv1[j] = v;
-    }
-    TM_SYNC();
-    { TmP t = pv0; pv0 = pv1; pv1 = t; }
-  }
-  for (int a = lane; a < NX; a += TM_NL) lq[a] = -pv0[a];
-  TM_SYNC();
-  return 0;
-}
+#include "tmpc_qp.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
 // objective and infeasibility of a point w_t = W + alpha*D.  xf_from_lin: take F(x_k,u_k) from LIN (valid for the
@@ -1892,9 +993,25 @@ TM_HD void tm_post(const TmProb& P, const TmState& S, int64_t inst) {
   for (int e = lane; e < P.n_w; e += TM_NL) w[e] += alpha * d[e];        // :174
   for (int e = lane; e < P.n_g; e += TM_NL) lam[e] = lq[e];              // :175 full dual step
   if (lane == 0) {
-    S.FILT[(inst * P.filter_cap + nf) * 2 + 0] = f;                       // :323
-    S.FILT[(inst * P.filter_cap + nf) * 2 + 1] = v;
-    S.nfilt[inst] = nf + 1;
+    // The reference's filter grows by one row per iteration (:323) and is only ever asked "do more than one of the
+    // stored rows dominate the trial point" (:305-311).  A stored row that is itself weakly dominated by two other
+    // stored rows can never change that answer (whenever it counts, both of them count as well), so such rows are
+    // dropped and the filter stays small however many iterations max_iter allows.  The newest row is kept: its
+    // infeasibility is the one the convergence test reads (:271,276).
+    double* Fw = S.FILT + inst * P.filter_cap * 2;
+    int n = nf;
+    for (int e = 0; e < n;) {
+      int dom = 0;
+      for (int o = 0; o < n; ++o) dom += (o != e && Fw[2 * o] <= Fw[2 * e] && Fw[2 * o + 1] <= Fw[2 * e + 1]) ? 1 : 0;
+      dom += (f <= Fw[2 * e] && v <= Fw[2 * e + 1]) ? 1 : 0;
+      if (dom >= 2) {
+        for (int o = e; o < n - 1; ++o) { Fw[2 * o] = Fw[2 * o + 2]; Fw[2 * o + 1] = Fw[2 * o + 3]; }
+        --n;
+      } else ++e;
+    }
+    Fw[2 * n + 0] = f;                                                    // :323
+    Fw[2 * n + 1] = v;
+    S.nfilt[inst] = n + 1;
     S.iter[inst] += 1;
     if (relin) S.flags[inst] |= 2;
 #ifdef __CUDA_ARCH__
@@ -2086,8 +1203,11 @@ TM_HD void tm_qp0_build_row(const TmProb& P, const TmState& S, int64_t inst, TmQ
   pt.row = t > NX ? t - 1 - NX : -1;
   pt.dout = T.TAB + (size_t)t * T.n_out;
   pt.lout = pt.dout + P.n_w;
-  unsigned bad[TM_ALW];
-  const int ret = tm_qp_solve(P, S, inst, ws, P.hessian_exact, nullptr, bad, &pt);
+  unsigned none[TM_ALW], nxt[TM_ALW];
+  for (int wd = 0; wd < TM_ALW; ++wd) none[wd] = 0u;
+  int nwrong = 0, ngi = 0;
+  tm_qp_setup(P, S, inst, ws, P.hessian_exact);
+  const int ret = tm_qp_solve(P, S, inst, ws, none, nxt, nwrong, ngi, &pt);
   if (TM_LANE == 0) {
     if (ret != 0) {
 #ifdef __CUDA_ARCH__
@@ -2145,57 +1265,98 @@ TM_HD void tm_qp0_finish(const TmProb& P, const TmState& S, int64_t inst, int re
   }
 }
 
-// One QP attempt with the configured Hessian.  Exact mode: (1) augmented-Lagrangian convexification on the rows that
-// are active in the current multipliers (the reference's reduced space); if some of those rows turn out inactive they
-// are removed from the mask and the instance is queued for a re-solve; (2) if the base factorisation is still not
-// positive definite: re-solve with the Gauss-Newton Hessian, flagged (the reference would eigen-clip its reduced
-// Hessian there, sqp_method.py:345-376).  Re-solves run in a later launch over the compacted retry list, so that the
-// lanes of a warp stay in step (thread-per-instance kernel).
+// The QP of one SQP iteration for one instance.  Base rows = the inequality rows active in the current multipliers
+// (the reference's reduced space, sqp_method.py:338-341,417-423).  Outcomes of the base factorisation:
+//   positive definite                      -> solve; base rows that come back with a wrong-signed multiplier are released
+//                                             (and the rows the dual active set added are held) and the QP is re-solved
+//   not positive definite, exact Hessian   -> the reference eigen-clips its reduced Hessian here (sqp_method.py:345-376);
+//                                             this solver re-solves with the Gauss-Newton Hessian, instance flagged
+//   base rows inconsistent / infeasible    -> re-solve from the empty working set
+#ifndef TM_MAX_ATTEMPTS
+#define TM_MAX_ATTEMPTS 6
+#endif
 TM_HD void tm_qp(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& ws) {
-  unsigned mask[TM_ALW], bad[TM_ALW];
-  int nmask = 0;
-  const int mode = S.qpmode[inst];
-  const int use_exact = P.hessian_exact && mode < 100;
+  unsigned mask[TM_ALW], next[TM_ALW];
+  const int NI = P.N * P.nh;
+  int use_exact = P.hessian_exact;
+  int flag = 0, work = 0, ret = 0, emptied = 0, attempts = 0;
   for (int wd = 0; wd < TM_ALW; ++wd) mask[wd] = 0u;
-  if (use_exact && P.al_gamma > 0.0) {
-    if (mode == 0) {
-      const double* lam = S.LAM + inst * P.n_g;
-      for (int e = 0; e < P.N * P.nh && e < 32 * TM_ALW; ++e) {
-        const int k = e / P.nh, i = e % P.nh;
-        if (k == 0 && P.relax0[i]) continue;
-        if (lam[tm_gh(P, k) + i] != 0.0) { mask[e >> 5] |= (1u << (e & 31)); ++nmask; }
+  {
+    const double* lam = S.LAM + inst * P.n_g;
+    for (int e = 0; e < NI; ++e) {
+      const int k = e / P.nh, i = e % P.nh;
+      if (k == 0 && P.relax0[i]) continue;
+      if (lam[tm_gh(P, k) + i] != 0.0) tm_mask_set(mask, e);
+    }
+  }
+  tm_qp_setup(P, S, inst, ws, use_exact);
+  for (int guard = 0; guard < 4 * TM_MAX_ATTEMPTS; ++guard) {
+    int nwrong = 0, ngi = 0;
+    ret = tm_qp_solve(P, S, inst, ws, mask, next, nwrong, ngi);
+    work += 1 + ngi;
+    int hr = ret == 0 ? (nwrong ? 3 : 0) : (ret == 3 ? 2 : 1);
+    if (TM_LANE == 0) {   // attempt histogram: [8 + 4*(0 exact first | 1 exact re-solve | 2 Gauss-Newton) + (0 ok | 1 infeasible | 2 not PD | 3 wrong-signed base rows)]
+      const int hm = use_exact ? (guard == 0 ? 0 : 1) : 2;
+#ifdef __CUDA_ARCH__
+      atomicAdd(S.counters + 8 + 4 * hm + hr, 1ull);
+#else
+      S.counters[8 + 4 * hm + hr] += 1;
+#endif
+    }
+#if defined(TM_DEBUG_QP) && !defined(__CUDA_ARCH__)
+    if (ret == 0) {   // stationarity and feasibility residuals of the returned (d, lam)
+      const double* lq = S.LAMQ + inst * P.n_g;
+      const TmP d = ws.d;
+      double rs = 0.0, rf = 0.0;
+      for (int k = 0; k < P.N; ++k) {
+        for (int c = 0; c < NZ; ++c) {
+          double v = ws.r[k * NZ + c];
+          for (int e = 0; e < NZ; ++e) v += 0.5 * (ws.Q[(size_t)k * NZ * NZ + c * NZ + e] + ws.Q[(size_t)k * NZ * NZ + e * NZ + c]) * d[k * NZ + e];
+          for (int i = 0; i < NX; ++i) v += ws.AB[(size_t)k * NX * NZ + i * NZ + c] * lq[tm_gdyn(P, k) + i];
+          for (int i = 0; i < P.nh; ++i) v += P.C[(size_t)i * NZ + c] * lq[tm_gh(P, k) + i];
+          if (c < NX) v += (k == 0) ? lq[c] : -lq[tm_gdyn(P, k - 1) + c];
+          rs = fmax(rs, fabs(v));
+        }
+        for (int i = 0; i < NX; ++i) {
+          double v = ws.b[k * NX + i] - d[(k + 1) * NZ + i];
+          for (int c = 0; c < NZ; ++c) v += ws.AB[(size_t)k * NX * NZ + i * NZ + c] * d[k * NZ + c];
+          rf = fmax(rf, fabs(v));
+        }
       }
-    } else {
-      for (int wd = 0; wd < TM_ALW; ++wd) { mask[wd] = S.almask[inst * TM_ALW + wd]; nmask += (mask[wd] != 0u); }
+      for (int a = 0; a < NX; ++a) {
+        double v = -lq[tm_gdyn(P, P.N - 1) + a];
+        for (int t = 0; t < P.nxt; ++t) if (P.term_idx[t] == a) v += lq[tm_gterm(P) + t];
+        rs = fmax(rs, fabs(v));
+      }
+      for (int t = 0; t < P.nxt; ++t) rf = fmax(rf, fabs(ws.tr[t] + d[P.N * NZ + P.term_idx[t]]));
+      fprintf(stderr, "[qp] inst %lld guard %d exact %d nwrong %d ngi %d: stationarity %.2e feasibility %.2e\n", (long long)inst, guard, use_exact, nwrong, ngi, rs, rf);
     }
-  }
-  int ret = tm_qp_solve(P, S, inst, ws, use_exact, nmask ? mask : nullptr, bad);
-  if (TM_LANE == 0) {   // attempt histogram: [8 + 4*(0 fresh | 1 mask retry | 2 Gauss-Newton) + (0 ok | 1 infeasible | 2 not PD | 3 mask rows inactive)]
-    const int hm = mode == 0 ? 0 : (mode < 100 ? 1 : 2), hr = ret == 0 ? 0 : (ret == 2 ? 1 : (ret == 3 ? 2 : 3));
-#ifdef __CUDA_ARCH__
-    atomicAdd(S.counters + 8 + 4 * hm + hr, 1ull);
-#else
-    S.counters[8 + 4 * hm + hr] += 1;
 #endif
+    if (ret == 0 && nwrong == 0) break;
+    int any = 0;
+    for (int wd = 0; wd < TM_ALW; ++wd) any |= (mask[wd] != 0u);
+    if (ret == 0) {                                  // wrong-signed base rows
+      ++attempts;
+      if (attempts < TM_MAX_ATTEMPTS) { for (int wd = 0; wd < TM_ALW; ++wd) mask[wd] = next[wd]; continue; }
+      ret = 3;                                       // cycling: treat like a failed factorisation
+    }
+    if (ret == 3 && use_exact) {
+      use_exact = 0; flag |= (guard == 0 ? 1 : 4); attempts = 0;
+      tm_qp_setup(P, S, inst, ws, 0);
+      continue;
+    }
+    if ((ret == 2 || ret == 6 || ret == 3) && any && !emptied) {
+      emptied = 1; attempts = 0;
+      for (int wd = 0; wd < TM_ALW; ++wd) mask[wd] = 0u;
+      continue;
+    }
+    break;
   }
-  int next_mode = 0;
-  if (ret == 5) next_mode = (mode + 1 >= 4) ? 100 : mode + 1;
-  else if (ret == 3 && use_exact) next_mode = 100;
   if (TM_LANE == 0) {
-    if (next_mode) {
-      for (int wd = 0; wd < TM_ALW; ++wd) S.almask[inst * TM_ALW + wd] = (ret == 5) ? (mask[wd] & ~bad[wd]) : 0u;
-      S.qpmode[inst] = next_mode;
-      if (next_mode == 100) S.flags[inst] |= 1;
-#ifdef __CUDA_ARCH__
-      const int pos = atomicAdd(S.cnt_retry, 1);
-#else
-      const int pos = (*S.cnt_retry)++;
-#endif
-      S.list_retry[pos] = (int)inst;
-    } else {
-      S.qpmode[inst] = 0;
-      S.qpstat[inst] = ret;
-    }
+    S.qpmode[inst] = 0;
+    S.qpstat[inst] = ret == 0 ? 0 : (ret == 3 ? 3 : (ret == 7 ? 5 : 2));
+    S.qpwork[inst] = work;
+    if (flag) S.flags[inst] |= flag;
   }
   TM_SYNC();
 }

@@ -1,0 +1,1098 @@
+// tmpc_qp.cuh -- K3/K4: the QP of one SQP iteration (included by tmpc_core.cuh).
+//
+// Replaces in the reference:  __regularize_hessian's positive-definiteness test (tunempc/sqp_method.py:335-347),
+// __active_constraints_jacobian (:405-425) and the conic('qpoases') solve (:158-168).
+//
+// Method.  The reference tests (and, if needed, clips) its Hessian on the null space of
+//        [ equality rows ; inequality rows with a non-zero multiplier ]                    (sqp_method.py:338-341)
+// and the benchmark problems need exactly that space: with the exact Lagrangian Hessian the stage blocks are
+// indefinite and the reduced Hessian is positive definite only once the rows active in the multipliers are held
+// (measured on the CSTR sweep: min eig 1e-3 on that space, -1 on the null space of the equalities alone).  So the
+// BASE problem of this solver is the equality-constrained QP on exactly that space:
+//     min 1/2 d'Hd + r'd   s.t.  d_x0 = e0,  dynamics,  terminal rows T d_N + t = 0,  rows in A as equalities,
+// factorised by a Riccati recursion with CONSTRAINT-TO-GO: going backwards, stage k holds a cost-to-go (P, p) and a
+// set of linear constraints Gc x + gc = 0 on x_k inherited from later stages; together with the stage's own active
+// rows they are eliminated against the stage inputs by Gauss-Jordan with full pivoting (u = Ku x + ku + Zu v), rows
+// without an input pivot become the constraint-to-go of stage k-1, and the Cholesky factor of the projected block
+// Zu'(R + B'PB)Zu is the positive-definiteness test: all pivots > reg_tol  <=>  the reduced Hessian on the
+// reference's space is positive definite (block elimination of that matrix).  No penalty parameter anywhere.
+// Every other inequality row enters a Goldfarb-Idnani dual active-set iteration carried in a small Schur complement
+// over the base inverse (one Riccati sweep per added row).  Multipliers of the base rows come from a forward sweep
+// over the stage-wise stationarity conditions; base rows whose multiplier has the wrong sign are released and the
+// QP re-solved.  Exact active-set solution: inactive multipliers are exact zeros (sqp_method.py:421 relies on it).
+#pragma once
+
+#define NV NU               /* free variables of a stage block (inputs; + slacks in the slack formulation) */
+#define TM_ES (NZ + 2)      /* row stride of the elimination scratch: coefficients | offset | state */
+
+struct TmQpWs {
+  TmP AB, Q, r, b, hv;                    // stage data: [A B] nx*nz | Hessian nz*nz | gradient | dynamics defect | row values
+  TmP K, Wm, kkm;                         // per stage: feedback nv*nx, projected inverse Zu (Zu'Fuu Zu)^-1 Zu' nv*nv, main feed-forward
+  TmP Pk, pm, py;                         // cost-to-go Hessian (N+1)*nx*nx, gradient of the main solve / of the correction solve
+  TmP Gc, gc, ncs;                        // constraint-to-go rows (N+1)*nx*nx, offsets (N+1)*nx, row counts (N+1)
+  TmP kk, d, y, rhs;                      // feed-forward of the current sweep; step, correction, right-hand side
+  TmP sl, Mc, Lf, cA, rv, nu, acts, acte, sc;   // dual active set: row values, dual-Hessian columns, Schur factor, members
+  TmP Ew, F, f, PAB, pv, tr, lh;          // scratch: elimination rows, stage KKT block, vectors; terminal residual; row multipliers
+};
+
+TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
+  const size_t NI = (size_t)N * nh + nxt + 1;        // row universe of the dual active set: inequality rows, then terminal rows
+  size_t n = 0;
+  n += (size_t)N * NX * NZ + (size_t)N * NZ * NZ + (size_t)(N + 1) * NZ + (size_t)N * NX + NI;        // AB Q r b hv
+  n += (size_t)N * NV * NX + (size_t)N * NV * NV + (size_t)N * NV;                                     // K Wm kkm
+  n += (size_t)(N + 1) * NX * NX + 2 * (size_t)(N + 1) * NX;                                           // Pk pm py
+  n += (size_t)(N + 1) * NX * NX + (size_t)(N + 1) * NX + (size_t)(N + 1);                             // Gc gc ncs
+  n += (size_t)N * NV + 3 * (size_t)(N + 1) * NZ;                                                      // kk d y rhs
+  n += NI + (size_t)(M + 1) * NI + (size_t)M * M + 5 * (size_t)M + 8;                                  // sl Mc Lf cA rv nu acts acte sc
+  n += (size_t)(NX + nh) * TM_ES + NZ * NZ + NZ + NX * NZ + 4 * NX + (nxt > 0 ? nxt : 1) + NI;         // Ew F f PAB pv tr lh
+  return n;
+}
+
+TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s) {
+  const size_t NI = (size_t)N * nh + nxt + 1;
+  size_t o = 0;
+#define TM_CARVE(member, n) s.member = tm_mkp(base, o); o += (size_t)(n)
+  TM_CARVE(AB, (size_t)N * NX * NZ);
+  TM_CARVE(Q, (size_t)N * NZ * NZ);
+  TM_CARVE(r, (size_t)(N + 1) * NZ);
+  TM_CARVE(b, (size_t)N * NX);
+  TM_CARVE(hv, NI);
+  TM_CARVE(K, (size_t)N * NV * NX);
+  TM_CARVE(Wm, (size_t)N * NV * NV);
+  TM_CARVE(kkm, (size_t)N * NV);
+  TM_CARVE(Pk, (size_t)(N + 1) * NX * NX);
+  TM_CARVE(pm, (size_t)(N + 1) * NX);
+  TM_CARVE(py, (size_t)(N + 1) * NX);
+  TM_CARVE(Gc, (size_t)(N + 1) * NX * NX);
+  TM_CARVE(gc, (size_t)(N + 1) * NX);
+  TM_CARVE(ncs, (size_t)(N + 1));
+  TM_CARVE(kk, (size_t)N * NV);
+  TM_CARVE(d, (size_t)(N + 1) * NZ);
+  TM_CARVE(y, (size_t)(N + 1) * NZ);
+  TM_CARVE(rhs, (size_t)(N + 1) * NZ);
+  TM_CARVE(sl, NI);
+  TM_CARVE(Mc, (size_t)(M + 1) * NI);
+  TM_CARVE(Lf, (size_t)M * M);
+  TM_CARVE(cA, M);
+  TM_CARVE(rv, M);
+  TM_CARVE(nu, M);
+  TM_CARVE(acts, M);
+  TM_CARVE(acte, M);
+  TM_CARVE(sc, 8);
+  TM_CARVE(Ew, (size_t)(NX + nh) * TM_ES);
+  TM_CARVE(F, NZ * NZ);
+  TM_CARVE(f, NZ);
+  TM_CARVE(PAB, NX * NZ);
+  TM_CARVE(pv, 4 * NX);
+  TM_CARVE(tr, (nxt > 0 ? nxt : 1));
+  TM_CARVE(lh, NI);
+#undef TM_CARVE
+}
+
+TM_HD int tm_mask_get(const unsigned* m, int e) { return (m[e >> 5] >> (e & 31)) & 1u; }
+TM_HD void tm_mask_set(unsigned* m, int e) { m[e >> 5] |= (1u << (e & 31)); }
+TM_HD void tm_mask_clr(unsigned* m, int e) { m[e >> 5] &= ~(1u << (e & 31)); }
+
+// ---- one stage of the constrained factorisation (single lane) --------------------------------------------------
+// in:  s.F (nz*nz stage block Q + [A B]'P[A B]), s.f (gradient r + [A B]'(P b + p)), nr candidate rows in s.Ew
+//      ([coefficients nz | offset | state]: constraint-to-go of stage k+1 pulled back through the dynamics, then the
+//      stage's own active rows)
+// out: K, Wm, kkm of stage k; constraint-to-go (Gc, gc, ncs) of stage k; s.f <- f + F[:,u] ku
+// returns 0 ok, 3 projected block not positive definite, 6 rows inconsistent
+TM_HD int tm_stage_factor(const TmProb& P, TmQpWs& s, int k, int nr) {
+  const TmP E = s.Ew;
+  const double tolp = 1e-9, tolc = 1e-7;
+  int colrow[NV > 0 ? NV : 1];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) colrow[j] = -1;
+  // normalise rows (max-abs 1); zero rows are dropped or flagged inconsistent
+  for (int i = 0; i < nr; ++i) {
+    double mx = 0.0;
+    for (int c = 0; c < NZ; ++c) mx = fmax(mx, fabs(E[i * TM_ES + c]));
+    if (!(mx > 1e-300)) {
+      if (fabs(E[i * TM_ES + NZ]) > tolc) return 6;
+      E[i * TM_ES + NZ + 1] = 3.0;
+      continue;
+    }
+    const double inv = 1.0 / mx;
+    for (int c = 0; c <= NZ; ++c) E[i * TM_ES + c] *= inv;
+    E[i * TM_ES + NZ + 1] = 0.0;
+  }
+  // Gauss-Jordan on the input columns, full pivoting
+  for (int step = 0; step < NV; ++step) {
+    double best = 0.0;
+    int bi = -1, bj = -1;
+    for (int i = 0; i < nr; ++i) {
+      if (E[i * TM_ES + NZ + 1] != 0.0) continue;
+      for (int j = 0; j < NV; ++j) {
+        if (colrow[j] >= 0) continue;
+        const double v = fabs(E[i * TM_ES + NX + j]);
+        if (v > best) { best = v; bi = i; bj = j; }
+      }
+    }
+    if (!(best > tolp)) break;
+    const double ip = 1.0 / E[bi * TM_ES + NX + bj];
+    for (int c = 0; c <= NZ; ++c) E[bi * TM_ES + c] *= ip;
+    E[bi * TM_ES + NX + bj] = 1.0;
+    for (int i = 0; i < nr; ++i) {
+      if (i == bi || E[i * TM_ES + NZ + 1] >= 2.0) continue;
+      const double fc = E[i * TM_ES + NX + bj];
+      if (fc == 0.0) continue;
+      for (int c = 0; c <= NZ; ++c) E[i * TM_ES + c] -= fc * E[bi * TM_ES + c];
+      E[i * TM_ES + NX + bj] = 0.0;
+    }
+    colrow[bj] = bi;
+    E[bi * TM_ES + NZ + 1] = 1.0;
+  }
+  // rows without an input pivot constrain x_k alone: reduce them to independent rows = constraint-to-go of this stage
+  int nck = 0;
+  {
+    int xrow[NX], xcol[NX];
+    for (int step = 0; step < NX; ++step) {
+      double best = 0.0;
+      int bi = -1, bj = -1;
+      for (int i = 0; i < nr; ++i) {
+        if (E[i * TM_ES + NZ + 1] != 0.0) continue;
+        for (int j = 0; j < NX; ++j) {
+          int used = 0;
+          for (int q = 0; q < nck; ++q) used |= (xcol[q] == j);
+          if (used) continue;
+          const double v = fabs(E[i * TM_ES + j]);
+          if (v > best) { best = v; bi = i; bj = j; }
+        }
+      }
+      if (!(best > tolp)) break;
+      const double ip = 1.0 / E[bi * TM_ES + bj];
+      for (int c = 0; c < NX; ++c) E[bi * TM_ES + c] *= ip;
+      E[bi * TM_ES + NZ] *= ip;
+      E[bi * TM_ES + bj] = 1.0;
+      for (int i = 0; i < nr; ++i) {
+        const double stt = E[i * TM_ES + NZ + 1];
+        if (i == bi || stt == 1.0 || stt == 3.0) continue;
+        const double fc = E[i * TM_ES + bj];
+        if (fc == 0.0) continue;
+        for (int c = 0; c < NX; ++c) E[i * TM_ES + c] -= fc * E[bi * TM_ES + c];
+        E[i * TM_ES + NZ] -= fc * E[bi * TM_ES + NZ];
+        E[i * TM_ES + bj] = 0.0;
+      }
+      E[bi * TM_ES + NZ + 1] = 2.0;
+      xrow[nck] = bi; xcol[nck] = bj;
+      ++nck;
+    }
+    for (int i = 0; i < nr; ++i)
+      if (E[i * TM_ES + NZ + 1] == 0.0) {            // numerically zero row: redundant if its offset vanishes too
+        if (fabs(E[i * TM_ES + NZ]) > tolc) return 6;
+        E[i * TM_ES + NZ + 1] = 3.0;
+      }
+    const TmP Gk = s.Gc + (size_t)k * NX * NX;
+    for (int q = 0; q < nck; ++q) {
+      for (int c = 0; c < NX; ++c) Gk[q * NX + c] = E[xrow[q] * TM_ES + c];
+      s.gc[k * NX + q] = E[xrow[q] * TM_ES + NZ];
+    }
+    s.ncs[k] = (double)nck;
+  }
+  // u = Ku x + ku + Zu v
+  double Ku[(NV > 0 ? NV : 1) * NX], ku[NV > 0 ? NV : 1], Zu[(NV > 0 ? NV : 1) * (NV > 0 ? NV : 1)];
+  int fl[NV > 0 ? NV : 1], nf = 0;
+  for (int j = 0; j < NV; ++j) if (colrow[j] < 0) fl[nf++] = j;
+  for (int j = 0; j < NV; ++j) {
+    const int ri = colrow[j];
+    for (int c = 0; c < NX; ++c) Ku[j * NX + c] = ri >= 0 ? -E[ri * TM_ES + c] : 0.0;
+    ku[j] = ri >= 0 ? -E[ri * TM_ES + NZ] : 0.0;
+    for (int c = 0; c < nf; ++c) Zu[j * NV + c] = ri >= 0 ? -E[ri * TM_ES + NX + fl[c]] : (fl[c] == j ? 1.0 : 0.0);
+  }
+  const TmP F = s.F;
+  // projected block Rt = Zu' Fuu Zu and its Cholesky factor (lower, in place)
+  double Rt[(NV > 0 ? NV : 1) * (NV > 0 ? NV : 1)], FZ[(NV > 0 ? NV : 1) * (NV > 0 ? NV : 1)];
+  for (int a = 0; a < NV; ++a)
+    for (int c = 0; c < nf; ++c) {
+      double v = 0.0;
+      for (int b2 = 0; b2 < NV; ++b2) v += 0.5 * (F[(NX + a) * NZ + NX + b2] + F[(NX + b2) * NZ + NX + a]) * Zu[b2 * NV + c];
+      FZ[a * NV + c] = v;
+    }
+  for (int c = 0; c < nf; ++c)
+    for (int e = 0; e <= c; ++e) {
+      double v = 0.0;
+      for (int a = 0; a < NV; ++a) v += Zu[a * NV + c] * FZ[a * NV + e];
+      Rt[c * NV + e] = v;
+    }
+  for (int c = 0; c < nf; ++c) {
+    double dg = Rt[c * NV + c];
+    for (int l = 0; l < c; ++l) dg -= Rt[c * NV + l] * Rt[c * NV + l];
+    if (!(dg > P.reg_tol)) {
+#if defined(TM_DEBUG_QP) && !defined(__CUDA_ARCH__)
+      fprintf(stderr, "[qp] stage %d not PD: pivot %d = %.3e (nf %d, nr %d, nck %d)\n", k, c, dg, nf, nr, nck);
+#endif
+      return 3;
+    }
+    const double ld = sqrt(dg);
+    Rt[c * NV + c] = ld;
+    for (int i = c + 1; i < nf; ++i) {
+      double v = Rt[i * NV + c];
+      for (int l = 0; l < c; ++l) v -= Rt[i * NV + l] * Rt[c * NV + l];
+      Rt[i * NV + c] = v / ld;
+    }
+  }
+  // Y = L^-1 Zu' (nf x nv);  Wm = Y'Y
+  double Y[(NV > 0 ? NV : 1) * (NV > 0 ? NV : 1)];
+  for (int a = 0; a < NV; ++a)
+    for (int c = 0; c < nf; ++c) {
+      double v = Zu[a * NV + c];
+      for (int l = 0; l < c; ++l) v -= Rt[c * NV + l] * Y[l * NV + a];
+      Y[c * NV + a] = v / Rt[c * NV + c];
+    }
+  const TmP Wk = s.Wm + (size_t)k * NV * NV;
+  for (int a = 0; a < NV; ++a)
+    for (int b2 = 0; b2 < NV; ++b2) {
+      double v = 0.0;
+      for (int c = 0; c < nf; ++c) v += Y[c * NV + a] * Y[c * NV + b2];
+      Wk[a * NV + b2] = v;
+    }
+  // K = Ku - Wm (Fux + Fuu Ku)
+  const TmP Kk = s.K + (size_t)k * NV * NX;
+  for (int j = 0; j < NX; ++j) {
+    double t[NV > 0 ? NV : 1];
+    for (int a = 0; a < NV; ++a) {
+      double v = 0.5 * (F[(NX + a) * NZ + j] + F[j * NZ + NX + a]);
+      for (int b2 = 0; b2 < NV; ++b2) v += 0.5 * (F[(NX + a) * NZ + NX + b2] + F[(NX + b2) * NZ + NX + a]) * Ku[b2 * NX + j];
+      t[a] = v;
+    }
+    for (int a = 0; a < NV; ++a) {
+      double v = Ku[a * NX + j];
+      for (int b2 = 0; b2 < NV; ++b2) v -= Wk[a * NV + b2] * t[b2];
+      Kk[a * NX + j] = v;
+    }
+  }
+  // main solve: ftil = f + F[:,u] ku ;  kk = ku - Wm ftil_u
+  for (int c = 0; c < NZ; ++c) {
+    double v = s.f[c];
+    for (int b2 = 0; b2 < NV; ++b2) v += 0.5 * (F[c * NZ + NX + b2] + F[(NX + b2) * NZ + c]) * ku[b2];
+    s.f[c] = v;
+  }
+  for (int a = 0; a < NV; ++a) {
+    double v = ku[a];
+    for (int b2 = 0; b2 < NV; ++b2) v -= Wk[a * NV + b2] * s.f[NX + b2];
+    s.kkm[k * NV + a] = v;
+  }
+  return 0;
+}
+
+// ---- base factorisation + main solve ----------------------------------------------------------------------------
+// amask: inequality rows (k*nh + i) held as equalities.  Fills K, Wm, Pk, pm, Gc, gc, ncs and the step s.d of the base
+// problem.  returns 0 ok, 3 not positive definite on the null space of the base rows, 6 base rows inconsistent.
+TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const TmP e0, double rho) {
+  const int N = P.N, nh = P.nh, nxt = P.nxt;
+  const int lane = TM_LANE;
+#ifdef TM_TERM_ELIM
+  // validation mode: terminal rows eliminated like base rows (exact null space; ill-conditioned when the inputs couple weakly)
+  for (int e = lane; e < NX * NX; e += TM_NL) s.Pk[(size_t)N * NX * NX + e] = 0.0;
+  for (int a = lane; a < NX; a += TM_NL) s.pm[N * NX + a] = 0.0;
+  for (int e = lane; e < nxt * NX; e += TM_NL) s.Gc[(size_t)N * NX * NX + e] = (P.term_idx[e / NX] == e % NX) ? 1.0 : 0.0;
+  for (int t = lane; t < nxt; t += TM_NL) s.gc[N * NX + t] = s.tr[t];
+  if (lane == 0) s.ncs[N] = (double)nxt;
+#else
+  // terminal rows live in the dual active set (always-active equality members of the Schur complement); the base carries
+  // their augmented-Lagrangian term rho/2 |T d_N + t|^2, which vanishes -- value and gradient -- at the QP solution
+  for (int e = lane; e < NX * NX; e += TM_NL) {
+    const int i = e / NX, j = e % NX;
+    double v = 0.0;
+    for (int t = 0; t < nxt; ++t) if (P.term_idx[t] == i && i == j) v += rho;
+    s.Pk[(size_t)N * NX * NX + e] = v;
+  }
+  for (int a = lane; a < NX; a += TM_NL) {
+    double v = 0.0;
+    for (int t = 0; t < nxt; ++t) if (P.term_idx[t] == a) v += rho * s.tr[t];
+    s.pm[N * NX + a] = v;
+  }
+  if (lane == 0) s.ncs[N] = 0.0;
+#endif
+  TM_SYNC();
+  for (int k = N - 1; k >= 0; --k) {
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Qk = s.Q + (size_t)k * NZ * NZ;
+    const TmP Pn = s.Pk + (size_t)(k + 1) * NX * NX;
+    const TmP Gn = s.Gc + (size_t)(k + 1) * NX * NX;
+    const int ncn = (int)s.ncs[k + 1];
+    for (int e = lane; e < NX * NZ; e += TM_NL) {
+      const int i = e / NZ, c = e % NZ;
+      double v = 0.0;
+#pragma unroll
+      for (int l = 0; l < NX; ++l) v += Pn[i * NX + l] * AB[l * NZ + c];
+      s.PAB[e] = v;
+    }
+    for (int i = lane; i < NX; i += TM_NL) {           // vv = P b + p
+      double v = s.pm[(k + 1) * NX + i];
+#pragma unroll
+      for (int l = 0; l < NX; ++l) v += Pn[i * NX + l] * s.b[k * NX + l];
+      s.pv[i] = v;
+    }
+    // candidate rows: constraint-to-go of stage k+1 through the dynamics, then the stage's own base rows
+    for (int e = lane; e < ncn * (NZ + 1); e += TM_NL) {
+      const int i = e / (NZ + 1), c = e % (NZ + 1);
+      double v = (c == NZ) ? s.gc[(k + 1) * NX + i] : 0.0;
+#pragma unroll
+      for (int l = 0; l < NX; ++l) v += Gn[i * NX + l] * (c == NZ ? s.b[k * NX + l] : AB[l * NZ + c]);
+      s.Ew[i * TM_ES + c] = v;
+    }
+    int nr = ncn;
+    for (int i = 0; i < nh; ++i) {
+      if (!tm_mask_get(amask, k * nh + i)) continue;
+      for (int c = lane; c <= NZ; c += TM_NL) s.Ew[nr * TM_ES + c] = (c == NZ) ? s.hv[k * nh + i] : P.C[(size_t)i * NZ + c];
+      ++nr;
+    }
+    TM_SYNC();
+    for (int e = lane; e < NZ * NZ; e += TM_NL) {
+      const int a = e / NZ, c = e % NZ;
+      double v = Qk[e];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + a] * s.PAB[i * NZ + c];
+      s.F[e] = v;
+    }
+    for (int c = lane; c < NZ; c += TM_NL) {
+      double v = s.r[k * NZ + c];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + c] * s.pv[i];
+      s.f[c] = v;
+    }
+    TM_SYNC();
+    if (lane == 0) s.sc[2] = (double)tm_stage_factor(P, s, k, nr);
+    TM_SYNC();
+    if (s.sc[2] != 0.0) return (int)s.sc[2];
+    // P_k = [I;K]' F [I;K] (symmetrised), p_k = ftil_x + K' ftil_u
+    const TmP Kk = s.K + (size_t)k * NV * NX;
+    for (int e = lane; e < NX * NZ; e += TM_NL) {      // X = F_x. + K' F_u.
+      const int i = e / NZ, c = e % NZ;
+      double v = 0.5 * (s.F[i * NZ + c] + s.F[c * NZ + i]);
+#pragma unroll
+      for (int a = 0; a < NV; ++a) v += Kk[a * NX + i] * 0.5 * (s.F[(NX + a) * NZ + c] + s.F[c * NZ + NX + a]);
+      s.PAB[e] = v;
+    }
+    TM_SYNC();
+    const TmP Pc = s.Pk + (size_t)k * NX * NX;
+    for (int e = lane; e < NX * NX; e += TM_NL) {
+      const int i = e / NX, j = e % NX;
+      double vij = s.PAB[i * NZ + j], vji = s.PAB[j * NZ + i];
+#pragma unroll
+      for (int a = 0; a < NV; ++a) { vij += s.PAB[i * NZ + NX + a] * Kk[a * NX + j]; vji += s.PAB[j * NZ + NX + a] * Kk[a * NX + i]; }
+      Pc[e] = 0.5 * (vij + vji);
+    }
+    for (int i = lane; i < NX; i += TM_NL) {
+      double v = s.f[i];
+#pragma unroll
+      for (int a = 0; a < NV; ++a) v += Kk[a * NX + i] * s.f[NX + a];
+      s.pm[k * NX + i] = v;
+    }
+    TM_SYNC();
+  }
+  // the constraint-to-go that reaches stage 0 must hold at the fixed x_0
+  {
+    const int nc0 = (int)s.ncs[0];
+    int bad = 0;
+    for (int i = 0; i < nc0; ++i) {
+      double v = s.gc[i];
+#pragma unroll
+      for (int c = 0; c < NX; ++c) v += s.Gc[i * NX + c] * e0[c];
+      if (fabs(v) > 1e-7) bad = 1;
+    }
+    if (bad) return 6;
+  }
+  // forward sweep of the main solve
+  for (int a = lane; a < NX; a += TM_NL) s.d[a] = e0[a];
+  TM_SYNC();
+  for (int k = 0; k < N; ++k) {
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NV * NX;
+    const TmP dx = s.d + k * NZ;
+    double du[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) {
+      double v = s.kkm[k * NV + a];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) v += Kk[a * NX + j] * dx[j];
+      du[a] = v;
+    }
+    for (int a = lane; a < NV; a += TM_NL) s.d[k * NZ + NX + a] = du[a];
+    for (int i = lane; i < NX; i += TM_NL) {
+      double v = s.b[k * NX + i];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) v += AB[i * NZ + j] * dx[j];
+#pragma unroll
+      for (int a = 0; a < NV; ++a) v += AB[i * NZ + NX + a] * du[a];
+      s.d[(k + 1) * NZ + i] = v;
+    }
+    TM_SYNC();
+  }
+  for (int a = lane; a < NV; a += TM_NL) s.d[N * NZ + NX + a] = 0.0;
+  TM_SYNC();
+  return 0;
+}
+
+// homogeneous base solve:  out = argmin 1/2 d'Hd + rhs'd  over the null space of the base rows ( = -G rhs ).
+// kfrom: last stage with a non-zero right-hand side.  The cost-to-go gradients go to s.py (multiplier recovery).
+TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, TmP rhs, TmP out, int kfrom) {
+  const int N = P.N;
+  const int lane = TM_LANE;
+  const int kb = (kfrom >= N) ? N - 1 : kfrom;
+  for (int e = lane; e < (N + 1) * NX; e += TM_NL) s.py[e] = (kfrom >= N && e >= N * NX) ? rhs[N * NZ + (e - N * NX)] : 0.0;
+  TM_SYNC();
+  for (int k = kb; k >= 0; --k) {
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NV * NX;
+    const TmP Wk = s.Wm + (size_t)k * NV * NV;
+    const TmP rk = rhs + k * NZ;
+    double pvr[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) pvr[i] = s.py[(k + 1) * NX + i];
+    double fu[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) {
+      double v = rk[NX + a];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + NX + a] * pvr[i];
+      fu[a] = v;
+    }
+    for (int j = lane; j < NX; j += TM_NL) {
+      double v = rk[j];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + j] * pvr[i];
+#pragma unroll
+      for (int a = 0; a < NV; ++a) v += Kk[a * NX + j] * fu[a];
+      s.py[k * NX + j] = v;
+    }
+    for (int a = lane; a < NV; a += TM_NL) {
+      double v = 0.0;
+#pragma unroll
+      for (int b2 = 0; b2 < NV; ++b2) v -= Wk[a * NV + b2] * fu[b2];
+      s.kk[k * NV + a] = v;
+    }
+    TM_SYNC();
+  }
+  for (int a = lane; a < NX; a += TM_NL) out[a] = 0.0;
+  TM_SYNC();
+  for (int k = 0; k < N; ++k) {
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NV * NX;
+    const TmP dx = out + k * NZ;
+    double dxr[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) dxr[j] = dx[j];
+    double du[NV > 0 ? NV : 1];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) {
+      double v = (k <= kb) ? s.kk[k * NV + a] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) v += Kk[a * NX + j] * dxr[j];
+      du[a] = v;
+    }
+    for (int a = lane; a < NV; a += TM_NL) out[k * NZ + NX + a] = du[a];
+    for (int i = lane; i < NX; i += TM_NL) {
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) v += AB[i * NZ + j] * dxr[j];
+#pragma unroll
+      for (int a = 0; a < NV; ++a) v += AB[i * NZ + NX + a] * du[a];
+      out[(k + 1) * NZ + i] = v;
+    }
+    TM_SYNC();
+  }
+  for (int a = lane; a < NV; a += TM_NL) out[N * NZ + NX + a] = 0.0;
+  TM_SYNC();
+}
+
+// Dual-Hessian column of inequality row qe:  y = G n_qe is swept stage by stage and never stored; mq[e] = n_e' y for
+// every inequality row e.  The NX-wide recursions are carried in registers by every lane (no synchronisation inside).
+TM_HD void tm_ricc_col(const TmProb& P, TmQpWs& s, int qe, TmP mq) {
+  const int N = P.N, nh = P.nh, NI = N * nh;
+  const int lane = TM_LANE;
+  double pv[NX], rz[NZ];
+#pragma unroll
+  for (int a = 0; a < NX; ++a) pv[a] = 0.0;
+#pragma unroll
+  for (int b = 0; b < NZ; ++b) rz[b] = 0.0;
+  int kb;
+  if (qe >= NI) {
+    const int ti = P.term_idx[qe - NI];
+#pragma unroll
+    for (int a = 0; a < NX; ++a) if (a == ti) pv[a] = -1.0;
+    kb = N - 1;
+  } else {
+    kb = qe / nh;
+    const double* Ci = P.C + (size_t)(qe % nh) * NZ;
+#pragma unroll
+    for (int b = 0; b < NZ; ++b) rz[b] = -Ci[b];
+  }
+  for (int k = kb; k >= 0; --k) {
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NV * NX;
+    const TmP Wk = s.Wm + (size_t)k * NV * NV;
+    double fu[NV > 0 ? NV : 1], pn[NX];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) {
+      double v = (k == kb) ? rz[NX + a] : 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + NX + a] * pv[i];
+      fu[a] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      double v = (k == kb) ? rz[j] : 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + j] * pv[i];
+#pragma unroll
+      for (int a = 0; a < NV; ++a) v += Kk[a * NX + j] * fu[a];
+      pn[j] = v;
+    }
+    for (int a = lane; a < NV; a += TM_NL) {
+      double v = 0.0;
+#pragma unroll
+      for (int b2 = 0; b2 < NV; ++b2) v -= Wk[a * NV + b2] * fu[b2];
+      s.kk[k * NV + a] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < NX; ++j) pv[j] = pn[j];
+  }
+  TM_SYNC();
+  double z[NZ];
+#pragma unroll
+  for (int b = 0; b < NZ; ++b) z[b] = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP Kk = s.K + (size_t)k * NV * NX;
+#pragma unroll
+    for (int a = 0; a < NV; ++a) {
+      double v = (k <= kb) ? s.kk[k * NV + a] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j) v += Kk[a * NX + j] * z[j];
+      z[NX + a] = v;
+    }
+    for (int i = lane; i < nh; i += TM_NL) {
+      const double* Ci = P.C + (size_t)i * NZ;
+      double t = 0.0;
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) t += Ci[b] * z[b];
+      mq[k * nh + i] = t;
+    }
+    double xn[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double v = 0.0;
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) v += AB[i * NZ + b] * z[b];
+      xn[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) z[i] = xn[i];
+  }
+  for (int t = lane; t < P.nxt; t += TM_NL) {
+    const int ti = P.term_idx[t];
+    double v = 0.0;
+#pragma unroll
+    for (int a = 0; a < NX; ++a) if (a == ti) v = z[a];
+    mq[NI + t] = v;
+  }
+  TM_SYNC();
+}
+
+TM_HD double tm_erow_dot(const TmProb& P, int e, TmP v) {       // n_e' v: e < N*nh inequality row k*nh + i, else terminal row
+  if (e >= P.N * P.nh) return v[P.N * NZ + P.term_idx[e - P.N * P.nh]];
+  const int k = e / P.nh, i = e % P.nh;
+  double t = 0.0;
+  const double* Ci = P.C + (size_t)i * NZ;
+  const TmP vk = v + k * NZ;
+#pragma unroll
+  for (int b = 0; b < NZ; ++b) t += Ci[b] * vk[b];
+  return t;
+}
+
+// rebuild the Cholesky factor Lf of S_ij = Mc[j][acte_i] (i, j < m) after a deletion (single lane)
+TM_HD int tm_schur_refactor(TmQpWs& s, int m, int M, int E) {
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j <= i; ++j) s.Lf[i * M + j] = s.Mc[(size_t)j * E + (int)s.acte[i]];
+  for (int c = 0; c < m; ++c) {
+    double dg = s.Lf[c * M + c];
+    for (int l = 0; l < c; ++l) dg -= s.Lf[c * M + l] * s.Lf[c * M + l];
+    if (!(dg > 0.0)) return 0;
+    const double ld = sqrt(dg);
+    s.Lf[c * M + c] = ld;
+    for (int i = c + 1; i < m; ++i) {
+      double v = s.Lf[i * M + c];
+      for (int l = 0; l < c; ++l) v -= s.Lf[i * M + l] * s.Lf[c * M + l];
+      s.Lf[i * M + c] = v / ld;
+    }
+  }
+  return 1;
+}
+
+// ---- Goldfarb-Idnani dual active set over the factorised base ---------------------------------------------------
+// Row universe e: e < N*nh inequality row (k = e / nh, i = e % nh), e >= N*nh terminal row.  The terminal rows enter
+// first as equality members (full step, sign-free multiplier, never dropped); then the rows outside the base mask that
+// are violated enter one at a time.  The primal iterate is never updated inside the loop (one correction solve at the
+// end).  returns 0 ok, 2 infeasible, 7 working-set overflow.
+TM_HD int tm_qp_gi(const TmProb& P, TmQpWs& s, const unsigned* amask, int& m_out, int& n_gi, int& n_ricc) {
+  const int N = P.N, nh = P.nh, M = P.maxact;
+  const int lane = TM_LANE;
+  const int NI = N * nh;
+#ifdef TM_TERM_ELIM
+  const int neq = 0;
+#else
+  const int neq = P.nxt;
+#endif
+  const int E = NI + P.nxt;
+  for (int e = lane; e < E; e += TM_NL)
+    s.sl[e] = (e < NI) ? (tm_mask_get(amask, e) ? 0.0 : s.hv[e] + tm_erow_dot(P, e, s.d)) : s.tr[e - NI] + tm_erow_dot(P, e, s.d);
+  TM_SYNC();
+  int m = 0, ret = 0, eq_next = 0;
+  const int maxit = 4 * NI + 8 + neq;
+  for (int it = 0; it < maxit && !ret; ++it) {
+    int qe, is_eq = 0;
+    double sval;
+    if (eq_next < neq) {
+      qe = NI + eq_next;
+      ++eq_next;
+      is_eq = 1;
+      sval = s.sl[qe];
+    } else {
+      double best = TM_INF;
+      int bid = 0x7fffffff;
+      for (int e = lane; e < NI; e += TM_NL) {
+        const int k = e / nh, i = e % nh;
+        if ((k == 0 && P.relax0[i]) || tm_mask_get(amask, e)) continue;
+        const double v = s.sl[e] / fmax(1.0, fabs(P.c[i]));
+        if (v < best) { best = v; bid = e; }
+      }
+      tm_wargmin(best, bid);
+      if (!(best < -1e-10)) break;            // primal feasible: optimal
+      int dup = 0;                            // a working-set row can only show up here through round-off
+      for (int j2 = 0; j2 < m; ++j2) if ((int)s.acte[j2] == bid) dup = 1;
+      if (dup) break;
+      qe = bid;
+      sval = s.sl[qe];
+    }
+    if (m >= M) { ret = 7; break; }
+    TmP mq = s.Mc + (size_t)m * E;            // candidate column, becomes member m when added
+    tm_ricc_col(P, s, qe, mq);
+    if (!is_eq) ++n_gi;
+    ++n_ricc;
+    const double yq = mq[qe];
+    double nq = 0.0;
+    int added = 0;
+    for (int inner = 0; inner < M + 2; ++inner) {
+      if (lane == 0) {                        // l = L^-1 S_Aq (cA), r = L^-T l (rv)
+        double ll = 0.0;
+        for (int i = 0; i < m; ++i) {
+          double v = mq[(int)s.acte[i]];
+          for (int l = 0; l < i; ++l) v -= s.Lf[i * M + l] * s.cA[l];
+          v /= s.Lf[i * M + i];
+          s.cA[i] = v;
+          ll += v * v;
+        }
+        for (int i = m - 1; i >= 0; --i) {
+          double v = s.cA[i];
+          for (int l = i + 1; l < m; ++l) v -= s.Lf[l * M + i] * s.rv[l];
+          s.rv[i] = v / s.Lf[i * M + i];
+        }
+        s.sc[0] = ll;
+      }
+      TM_SYNC();
+      const double zn = yq - s.sc[0];
+      double t1 = TM_INF;
+      int jd = -1;
+      for (int j2 = 0; j2 < m; ++j2) {
+        if ((int)s.acte[j2] >= NI) continue;           // equality members are never dropped
+        const double rj = s.rv[j2];
+        if (rj > 1e-14) { const double tj = s.nu[j2] / rj; if (tj < t1) { t1 = tj; jd = j2; } }
+      }
+      const int dependent = !(zn > 1e-11 * fmax(yq, 1e-300));
+      double t;
+      int do_add = 0;
+      if (dependent) {
+        if (is_eq) {                                   // redundant terminal row: skip it if it already holds
+          if (fabs(sval) > 1e-7) ret = 2;
+          added = 2;
+          break;
+        }
+        if (jd < 0) { ret = 2; break; }
+        t = t1;
+      } else {
+        const double t2 = -sval / zn;
+        if (is_eq || t2 <= t1) { t = t2; do_add = 1; } else t = t1;
+        for (int e = lane; e < E; e += TM_NL) {
+          double acc = mq[e];
+          for (int j2 = 0; j2 < m; ++j2) acc -= s.rv[j2] * s.Mc[(size_t)j2 * E + e];
+          s.sl[e] += t * acc;
+        }
+        sval += t * zn;
+      }
+      TM_SYNC();
+      for (int j2 = lane; j2 < m; j2 += TM_NL) s.nu[j2] -= t * s.rv[j2];
+      nq += t;
+      TM_SYNC();
+      if (do_add) {
+        if (lane == 0) {
+          for (int l = 0; l < m; ++l) s.Lf[m * M + l] = s.cA[l];
+          s.Lf[m * M + m] = sqrt(zn);
+          s.acte[m] = (double)qe; s.nu[m] = nq;
+        }
+        TM_SYNC();
+        ++m;
+        added = 1;
+        break;
+      }
+      // drop member jd: shift members jd+1..m-1 and the candidate column down by one slot, rebuild the factor
+      for (int a = jd; a < m; ++a) {
+        for (int e = lane; e < E; e += TM_NL) s.Mc[(size_t)a * E + e] = s.Mc[(size_t)(a + 1) * E + e];
+        TM_SYNC();
+      }
+      if (lane == 0) {
+        for (int a = jd; a < m - 1; ++a) { s.acte[a] = s.acte[a + 1]; s.nu[a] = s.nu[a + 1]; }
+      }
+      --m;
+      TM_SYNC();
+      mq = s.Mc + (size_t)m * E;
+      if (lane == 0) s.sc[1] = (double)tm_schur_refactor(s, m, M, E);
+      TM_SYNC();
+      if (s.sc[1] == 0.0) { ret = 2; break; }
+    }
+    if (ret) break;
+    if (!added) { ret = 2; break; }
+    if (it == maxit - 1) ret = 2;
+  }
+  m_out = m;
+  return ret;
+}
+
+// ---- multipliers of the base rows -------------------------------------------------------------------------------
+// Stage-wise stationarity with the final step d and gradient r' (r plus the dual active-set rows' terms):
+//     Q z_k + r'_k + [A B]' lam_{k+1} + sum_{i in A_k} C_i' mu_i = [lam_k ; 0],   lam_k = P_k x_k + p_k + Gc_k' nu_k
+// solved forwards for (nu_{k+1}, mu) by least squares on the (consistent) nz equations of every stage.  Stages whose
+// neighbours carry no constraint-to-go are independent of each other (lane <-> stage); the others chain through nu.
+// Writes lq (n_g, CasADi sign) completely.  lamh: multipliers of the dual active-set rows, already in lq.
+TM_HD void tm_qp_recover_stage(const TmProb& P, TmQpWs& s, const unsigned* amask, int k, const double* nu_k, double* nu_next,
+                               double* lq) {
+  const int nh = P.nh;
+  const TmP AB = s.AB + (size_t)k * NX * NZ;
+  const TmP Qk = s.Q + (size_t)k * NZ * NZ;
+  const int nck = (int)s.ncs[k], ncn = (int)s.ncs[k + 1];
+  double z[NZ], xn[NX], lin[NX], cst[NX], rh[NZ];
+#pragma unroll
+  for (int c = 0; c < NZ; ++c) z[c] = s.d[k * NZ + c];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) xn[i] = s.d[(k + 1) * NZ + i];
+  for (int i = 0; i < NX; ++i) {                      // lam_k and the cost-to-go part of lam_{k+1}
+    double a = s.pm[k * NX + i] + s.py[k * NX + i], b2 = s.pm[(k + 1) * NX + i] + s.py[(k + 1) * NX + i];
+    for (int l = 0; l < NX; ++l) {
+      a += s.Pk[(size_t)k * NX * NX + i * NX + l] * z[l];
+      b2 += s.Pk[(size_t)(k + 1) * NX * NX + i * NX + l] * xn[l];
+    }
+    for (int q = 0; q < nck; ++q) a += s.Gc[(size_t)k * NX * NX + q * NX + i] * nu_k[q];
+    lin[i] = a; cst[i] = b2;
+  }
+  for (int c = 0; c < NZ; ++c) {                      // rh = [lam_k;0] - (Q z + r') - [A B]' cst
+    double v = (c < NX ? lin[c] : 0.0) - s.rhs[k * NZ + c];
+    for (int e = 0; e < NZ; ++e) v -= 0.5 * (Qk[c * NZ + e] + Qk[e * NZ + c]) * z[e];
+    for (int i = 0; i < NX; ++i) v -= AB[i * NZ + c] * cst[i];
+    rh[c] = v;
+  }
+  // rows: Gc_{k+1} [A B]  |  C_i, i in A_k        (at most NZ independent ones)
+  double Er[NZ * NZ], Gm[NZ * NZ], et[NZ];
+  int rid[NZ];
+  int nr = 0;
+  for (int q = 0; q < ncn && nr < NZ; ++q) {
+    for (int c = 0; c < NZ; ++c) {
+      double v = 0.0;
+      for (int l = 0; l < NX; ++l) v += s.Gc[(size_t)(k + 1) * NX * NX + q * NX + l] * AB[l * NZ + c];
+      Er[nr * NZ + c] = v;
+    }
+    rid[nr++] = -1 - q;
+  }
+  for (int i = 0; i < nh && nr < NZ; ++i) {
+    if (!tm_mask_get(amask, k * nh + i)) continue;
+    for (int c = 0; c < NZ; ++c) Er[nr * NZ + c] = P.C[(size_t)i * NZ + c];
+    rid[nr++] = i;
+  }
+  for (int i = 0; i < nr; ++i) {
+    double v = 0.0;
+    for (int c = 0; c < NZ; ++c) v += Er[i * NZ + c] * rh[c];
+    et[i] = v;
+    for (int j = 0; j <= i; ++j) {
+      double g = 0.0;
+      for (int c = 0; c < NZ; ++c) g += Er[i * NZ + c] * Er[j * NZ + c];
+      Gm[i * NZ + j] = g;
+    }
+  }
+  // Cholesky of E E' with dependent rows skipped (their multiplier is set to zero)
+  int skip[NZ];
+  for (int c = 0; c < nr; ++c) {
+    double dg = Gm[c * NZ + c];
+    const double dg0 = dg;
+    for (int l = 0; l < c; ++l) if (!skip[l]) dg -= Gm[c * NZ + l] * Gm[c * NZ + l];
+    skip[c] = !(dg > 1e-12 * fmax(dg0, 1e-300));
+    if (skip[c]) continue;
+    const double ld = sqrt(dg);
+    Gm[c * NZ + c] = ld;
+    for (int i = c + 1; i < nr; ++i) {
+      double v = Gm[i * NZ + c];
+      for (int l = 0; l < c; ++l) if (!skip[l]) v -= Gm[i * NZ + l] * Gm[c * NZ + l];
+      Gm[i * NZ + c] = v / ld;
+    }
+  }
+  for (int i = 0; i < nr; ++i) {
+    if (skip[i]) { et[i] = 0.0; continue; }
+    double v = et[i];
+    for (int l = 0; l < i; ++l) if (!skip[l]) v -= Gm[i * NZ + l] * et[l];
+    et[i] = v / Gm[i * NZ + i];
+  }
+  for (int i = nr - 1; i >= 0; --i) {
+    if (skip[i]) continue;
+    double v = et[i];
+    for (int l = i + 1; l < nr; ++l) if (!skip[l]) v -= Gm[l * NZ + i] * et[l];
+    et[i] = v / Gm[i * NZ + i];
+  }
+#if defined(TM_DEBUG_QP) && !defined(__CUDA_ARCH__)
+  {
+    double res = 0.0, rmax = 0.0;
+    for (int c = 0; c < NZ; ++c) {
+      double v = rh[c];
+      for (int i = 0; i < nr; ++i) v -= Er[i * NZ + c] * et[i];
+      res = fmax(res, fabs(v)); rmax = fmax(rmax, fabs(rh[c]));
+    }
+    if (res > 1e-9 * fmax(1.0, rmax)) {
+      fprintf(stderr, "[qp] recover stage %d: LS residual %.2e (rhs %.2e, nr %d, ncn %d, nck %d) rh:", k, res, rmax, nr, ncn, nck);
+      for (int c = 0; c < NZ; ++c) fprintf(stderr, " %.2e", rh[c]);
+      fprintf(stderr, " | lin:"); for (int c = 0; c < NX; ++c) fprintf(stderr, " %.2e", lin[c]);
+      fprintf(stderr, " | cst:"); for (int c = 0; c < NX; ++c) fprintf(stderr, " %.2e", cst[c]);
+      { double pn = 0, qn = 0, xnn = 0, yn = 0; for (int e = 0; e < NX * NX; ++e) pn = fmax(pn, fabs(s.Pk[(size_t)(k + 1) * NX * NX + e]));
+        for (int e = 0; e < NX; ++e) { qn = fmax(qn, fabs(s.pm[(k + 1) * NX + e])); yn = fmax(yn, fabs(s.py[(k + 1) * NX + e])); xnn = fmax(xnn, fabs(xn[e])); }
+        fprintf(stderr, " | |P+|=%.2e |pm+|=%.2e |py+|=%.2e |x+|=%.2e", pn, qn, yn, xnn); }
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
+  for (int q = 0; q < NX; ++q) nu_next[q] = 0.0;
+  for (int i = 0; i < nr; ++i) {
+    if (rid[i] < 0) nu_next[-1 - rid[i]] = et[i];
+    else lq[tm_gh(P, k) + rid[i]] = et[i];
+  }
+  for (int i = 0; i < NX; ++i) {                      // lam_{k+1} = multiplier of dynamics row k
+    double v = cst[i];
+    for (int q = 0; q < ncn; ++q) v += s.Gc[(size_t)(k + 1) * NX * NX + q * NX + i] * nu_next[q];
+    lq[tm_gdyn(P, k) + i] = v;
+  }
+  if (k == 0) for (int i = 0; i < NX; ++i) lq[i] = -lin[i];
+}
+
+TM_HD void tm_qp_recover(const TmProb& P, TmQpWs& s, const unsigned* amask, double* lq) {
+  const int N = P.N;
+  const int lane = TM_LANE;
+  int kseq = N;                                       // first stage of the sequential tail
+  for (int k = 0; k <= N; ++k) if ((int)s.ncs[k] > 0) { kseq = k > 0 ? k - 1 : 0; break; }
+  if (kseq > N - 1) kseq = N - 1;
+  double nu0[NX], nu1[NX];
+#pragma unroll
+  for (int q = 0; q < NX; ++q) nu0[q] = 0.0;
+  for (int k = lane; k < kseq; k += TM_NL) tm_qp_recover_stage(P, s, amask, k, nu0, nu1, lq);
+  TM_SYNC();
+  if (lane == 0) {
+    for (int k = kseq; k < N; ++k) {
+      tm_qp_recover_stage(P, s, amask, k, nu0, nu1, lq);
+#pragma unroll
+      for (int q = 0; q < NX; ++q) nu0[q] = nu1[q];
+    }
+#ifdef TM_TERM_ELIM
+    for (int t = 0; t < P.nxt; ++t) lq[tm_gterm(P) + t] = nu0[t];    // Gc_N = the terminal rows themselves
+#endif
+  }
+  TM_SYNC();
+}
+
+// Perturbed solve used to tabulate the solution map of the first QP after reset() (tm_qp0_*, tmpc_core.cuh): the base
+// problem (no dual active set) is solved for modified data and the result goes to (dout, lout).
+struct TmQpPert {
+  int homog;      // 1: zero all offsets (gradient r, dynamics defect b, terminal residual): pure linear response; the x_0 offset is always zeroed
+  int e0_unit;    // >= 0: x_0 offset = unit vector e0_unit
+  int row;        // >= 0: gradient -= n_row (response to a unit multiplier on inequality row `row` = k*nh + i)
+  double *dout, *lout;
+};
+
+// stage data of the QP at the iterate (W, LAM) with the linearisation in LIN
+TM_HD void tm_qp_setup(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& s, int use_exact) {
+  const int N = P.N, nh = P.nh, nxt = P.nxt;
+  const int lane = TM_LANE;
+  const double* w = S.W + inst * P.n_w;
+  const double* lin = S.LIN + inst * P.N * (int64_t)TM_LSZ;
+  for (int e = lane; e < N * NX * NZ; e += TM_NL) { int k = e / (NX * NZ), o = e % (NX * NZ); s.AB[e] = lin[(size_t)k * TM_LSZ + NX + o]; }
+  for (int e = lane; e < N * NX; e += TM_NL) { int k = e / NX, a = e % NX; s.b[e] = lin[(size_t)k * TM_LSZ + a] - w[(k + 1) * NZ + a]; }
+  if (P.economic) {
+    // economic stage cost: Q_k = d2l/dz2 (+ lam' d2F), r_k = dl/dz at the iterate
+    for (int k = lane; k < N; k += TM_NL) {
+      double z[NZ], gl[NZ], Hl[NZ * NZ];
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) z[b] = w[k * NZ + b];
+      tmpc_cost_grad(z, z + NX, gl);
+      tmpc_cost_hess(z, z + NX, Hl);
+      for (int i = 0; i < NZ; ++i) {
+        for (int j = 0; j < NZ; ++j) {
+          double v = 0.5 * (Hl[i * NZ + j] + Hl[j * NZ + i]);
+          if (use_exact) v += lin[(size_t)k * TM_LSZ + NX + NX * NZ + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
+          s.Q[(size_t)k * NZ * NZ + i * NZ + j] = v;
+        }
+        s.r[k * NZ + i] = gl[i];
+      }
+    }
+  } else {
+    for (int e = lane; e < N * NZ * NZ; e += TM_NL) {
+      int k = e / (NZ * NZ), o = e % (NZ * NZ), i = o / NZ, j = o % NZ;
+      int ph = (S.phase + k) % P.p;
+      double v = P.H[(size_t)ph * NZ * NZ + o];
+      if (use_exact) v += lin[(size_t)k * TM_LSZ + NX + NX * NZ + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
+      s.Q[e] = v;
+    }
+    for (int e = lane; e < N * NZ; e += TM_NL) {
+      int k = e / NZ, i = e % NZ;
+      int ph = (S.phase + k) % P.p;
+      const double* Hk = P.H + (size_t)ph * NZ * NZ + (size_t)i * NZ;
+      const double* wr = P.wref + (size_t)ph * NZ;
+      double v = P.q[(size_t)ph * NZ + i];
+#pragma unroll
+      for (int j = 0; j < NZ; ++j) v += Hk[j] * (w[k * NZ + j] - wr[j]);
+      s.r[e] = v;
+    }
+  }
+  for (int a = lane; a < NZ; a += TM_NL) s.r[N * NZ + a] = 0.0;
+  for (int e = lane; e < N * nh; e += TM_NL) {
+    int k = e / nh, i = e % nh;
+    double v = P.c[i];
+#pragma unroll
+    for (int j = 0; j < NZ; ++j) v += P.C[(size_t)i * NZ + j] * w[k * NZ + j];
+    s.hv[e] = v;
+  }
+  TmP e0 = s.pv + 2 * NX;
+  for (int a = lane; a < NX; a += TM_NL) e0[a] = S.X0[inst * NX + a] - w[a];
+  {
+    const double* xrN = P.wref + (size_t)((S.phase + N) % P.p) * NZ;
+    for (int t = lane; t < nxt; t += TM_NL) s.tr[t] = w[N * NZ + P.term_idx[t]] - xrN[P.term_idx[t]];
+  }
+  TM_SYNC();
+}
+
+// One QP with the base rows in amask.  returns 0 ok (step and multipliers in dout / lq, wrong-sign base rows reported
+// in nwrong / amask_next), 2 infeasible, 3 base not positive definite, 6 base rows inconsistent, 7 working-set overflow.
+// amask_next = base rows with a correctly signed multiplier + the rows the dual active set added: the working set a
+// re-solve starts from.
+TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& s, const unsigned* amask,
+                       unsigned* amask_next, int& nwrong, int& n_gi_out, const TmQpPert* pert = nullptr) {
+  const int N = P.N, nh = P.nh, nxt = P.nxt;
+  const int lane = TM_LANE;
+  const int NI = N * nh;
+  TmP e0 = s.pv + 2 * NX;
+  if (pert) {
+    if (pert->homog) {
+      for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.r[e] = 0.0;
+      for (int e = lane; e < N * NX; e += TM_NL) s.b[e] = 0.0;
+      for (int t = lane; t < nxt; t += TM_NL) s.tr[t] = 0.0;
+    }
+    for (int a = lane; a < NX; a += TM_NL) e0[a] = 0.0;     // the x_0 offset always enters through the table
+    TM_SYNC();
+    if (pert->e0_unit >= 0) for (int a = lane; a < NX; a += TM_NL) e0[a] = (a == pert->e0_unit) ? 1.0 : 0.0;
+    if (pert->row >= 0) {
+      const int k = pert->row / nh, i = pert->row % nh;
+      for (int b2 = lane; b2 < NZ; b2 += TM_NL) s.r[k * NZ + b2] -= P.C[(size_t)i * NZ + b2];
+    }
+    TM_SYNC();
+  }
+  // weight of the terminal rows' augmented-Lagrangian term: relative to the largest Hessian diagonal entry of the horizon
+  double rho = 0.0;
+  {
+    double qmax = 0.0;
+    for (int e = lane; e < N * NZ; e += TM_NL) { const int k = e / NZ, i = e % NZ; qmax = fmax(qmax, fabs(s.Q[(size_t)k * NZ * NZ + i * NZ + i])); }
+    rho = P.rho_rel * fmax(tm_wmax(qmax), 1e-300);
+  }
+  int ret = tm_qp_factor(P, s, amask, e0, rho);
+  int m = 0, n_gi = 0, n_ricc = 1;
+  if (!ret && (NI > 0 || nxt > 0)) {
+    if (pert) {                                   // tabulation: equality rows only
+      unsigned all[TM_ALW];
+      for (int wd = 0; wd < TM_ALW; ++wd) all[wd] = 0xffffffffu;
+      ret = tm_qp_gi(P, s, all, m, n_gi, n_ricc);
+    } else {
+      ret = tm_qp_gi(P, s, amask, m, n_gi, n_ricc);
+    }
+  }
+  n_gi_out = n_gi;
+  if (!ret) {
+    // gradient including the dual active-set rows (kept in s.rhs for the multiplier recovery), correction solve
+    for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.rhs[e] = 0.0;
+    for (int e = lane; e < NI + nxt; e += TM_NL) s.lh[e] = 0.0;
+    TM_SYNC();
+    int kfrom = -1;
+    if (lane == 0)
+      for (int j2 = 0; j2 < m; ++j2) {
+        const int e = (int)s.acte[j2];
+        s.lh[e] = -s.nu[j2];
+        if (e >= NI) { s.rhs[N * NZ + P.term_idx[e - NI]] -= s.nu[j2]; continue; }
+        const int k = e / nh, i = e % nh;
+        const double* Ci = P.C + (size_t)i * NZ;
+        for (int b2 = 0; b2 < NZ; ++b2) s.rhs[k * NZ + b2] -= s.nu[j2] * Ci[b2];
+      }
+    for (int j2 = 0; j2 < m; ++j2) { const int e = (int)s.acte[j2]; const int k = e < NI ? e / nh : N; if (k > kfrom) kfrom = k; }
+    TM_SYNC();
+    if (m > 0) {
+      tm_ricc_solve(P, s, s.rhs, s.y, kfrom);
+      ++n_ricc;
+      for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.d[e] += s.y[e];
+    } else {
+      for (int e = lane; e < (N + 1) * NX; e += TM_NL) s.py[e] = 0.0;
+    }
+    TM_SYNC();
+    for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.rhs[e] += s.r[e];
+    TM_SYNC();
+  }
+  if (lane == 0 && !pert) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(S.counters + 5, 1ull); atomicAdd(S.counters + 6, (unsigned long long)n_gi); atomicAdd(S.counters + 7, (unsigned long long)n_ricc);
+#else
+    S.counters[5] += 1; S.counters[6] += n_gi; S.counters[7] += n_ricc;
+#endif
+  }
+  if (ret) return ret;
+  double* dout = pert ? pert->dout : S.D + inst * P.n_w;
+  double* lq = pert ? pert->lout : S.LAMQ + inst * P.n_g;
+  for (int e = lane; e < P.n_g; e += TM_NL) lq[e] = 0.0;
+  TM_SYNC();
+  tm_qp_recover(P, s, amask, lq);
+  for (int e = lane; e < NI; e += TM_NL) if (s.lh[e] != 0.0) lq[tm_gh(P, e / nh) + e % nh] = s.lh[e];
+#ifndef TM_TERM_ELIM
+  for (int t = lane; t < nxt; t += TM_NL) lq[tm_gterm(P) + t] = s.lh[NI + t];
+#endif
+  TM_SYNC();
+  // base rows must carry the multiplier sign of an active lower bound (CasADi convention: lam < 0)
+  int nw = 0;
+  for (int wd = 0; wd < TM_ALW; ++wd) amask_next[wd] = amask[wd];
+  if (!pert) {
+    double lmax = 0.0;
+    for (int e = 0; e < NI; ++e) if (tm_mask_get(amask, e)) lmax = fmax(lmax, fabs(lq[tm_gh(P, e / nh) + e % nh]));
+#ifdef TM_RELEASE_ONE
+    {
+      double worst = 1e-12 * lmax; int we = -1;
+      for (int e = 0; e < NI; ++e) {
+        if (!tm_mask_get(amask, e)) continue;
+        const double l = lq[tm_gh(P, e / nh) + e % nh];
+        if (l > worst) { worst = l; we = e; }
+      }
+      if (we >= 0) { tm_mask_clr(amask_next, we); ++nw; }
+    }
+#else
+    for (int e = 0; e < NI; ++e) {
+      if (!tm_mask_get(amask, e)) continue;
+      if (lq[tm_gh(P, e / nh) + e % nh] > 1e-12 * lmax) { tm_mask_clr(amask_next, e); ++nw; }
+    }
+#endif
+    for (int j2 = 0; j2 < m; ++j2) if ((int)s.acte[j2] < NI) tm_mask_set(amask_next, (int)s.acte[j2]);
+  }
+  nwrong = nw;
+  if (nw == 0) {
+    for (int e = lane; e < P.n_w; e += TM_NL) dout[e] = s.d[e];
+    TM_SYNC();
+  }
+  return 0;
+}

@@ -33,7 +33,7 @@ class TmpcDims(ctypes.Structure):
 class TmpcOpts(ctypes.Structure):
     _fields_ = [("hessian_exact", ctypes.c_int32), ("max_iter", ctypes.c_int32), ("max_ls_iter", ctypes.c_int32),
                 ("tol", ctypes.c_double), ("lam_tresh", ctypes.c_double), ("ls_step_factor", ctypes.c_double),
-                ("reg_tol", ctypes.c_double), ("term_penalty", ctypes.c_double), ("al_gamma", ctypes.c_double),
+                ("reg_tol", ctypes.c_double), ("term_weight", ctypes.c_double), ("max_working_set", ctypes.c_int32),
                 ("economic", ctypes.c_int32)]
 
 
@@ -46,6 +46,7 @@ def build_model_lib(name, force=False, verbose=False):
     out = lib_path(name)
     srcs = [os.path.join(_PKG, "csrc", "tmpc.cu"), os.path.join(_PKG, "csrc", "tmpc_qp_thread.cu"),
             os.path.join(_PKG, "csrc", "tmpc_core.cuh"), os.path.join(_PKG, "csrc", "tmpc_lin2.cuh"),
+            os.path.join(_PKG, "csrc", "tmpc_qp.cuh"),
             os.path.join(_PKG, "csrc", "gen", "model_%s.h" % name), os.path.join(_ROOT, "include", "tmpc.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
         return out
