@@ -222,7 +222,8 @@ def main():
     status = ctrl.status
     flags = ctrl.log["flags"][-1]
     stat_hist = torch.bincount(status.to(torch.int64), minlength=5)[:5].to(torch.float64)
-    fl_hist = torch.bincount(flags.to(torch.int64), minlength=4)[:4].to(torch.float64)
+    # per-bit counts: [no flag, GN fallback (1), damped step (2), GN re-solve (4), non-convex primal step (8)]
+    fl_hist = torch.stack([(flags == 0).sum()] + [((flags & b) != 0).sum() for b in (1, 2, 4, 8)]).to(torch.float64)
 
     # ---- end-to-end arm: host buffers through the C ABI (tmpc_step_host), H2D + D2H inside the timed region ----
     x_np = [x.numpy() for x in X0_host]
@@ -295,7 +296,8 @@ def main():
                                     "lane-interleaved Riccati / working-set workspace streams through HBM" % (qp_alg_bytes, qp_traffic_per_qp),
                             "peak_source": hbm_src},
             "stats": {"sqp_iter_mean": n_it / (B * K), "qp_solves": int(n_qp), "ls_dynamics_evals": int(n_dyn),
-                      "status_hist": [int(v) for v in stat_hist.tolist()], "flags_hist": [int(v) for v in fl_hist.tolist()]},
+                      "status_hist": [int(v) for v in stat_hist.tolist()], "flags_hist": [int(v) for v in fl_hist.tolist()],
+                      "flags_hist_keys": ["none", "gn_fallback", "damped", "gn_resolve", "nonconvex_step"]},
         }
         # ---- CPU baseline: the oracle port on a bounded sample of the same workload, 1 core ----
         try:

@@ -41,6 +41,8 @@ typedef struct tmpc_handle tmpc_handle;
                                     eigen-clips its reduced Hessian (sqp_method.py:345-376)                         */
 #define TMPC_FLAG_GN_RESOLVE 4   /* >=1 QP fell back to the Gauss-Newton Hessian after releasing wrong-signed base rows
                                     (the reference's QP is non-convex there)                                        */
+#define TMPC_FLAG_NONCONVEX_STEP 8 /* >=1 QP was non-convex once wrong-signed rows were released and was continued by an
+                                    inertia-controlling primal active-set step (the reference's qpOASES: flipping bounds)   */
 #define TMPC_FLAG_DAMPED 2       /* >=1 line-search backtrack (alpha < 1)                                           */
 
 typedef struct {

@@ -57,7 +57,7 @@ def test_twin_cstr_golden(env):
     for b in range(n):                                                # identical active sets
         assert set(np.nonzero(o["lam"][b])[0]) == set(np.nonzero(gold["lam_t6"][b])[0])
     assert np.array_equal(o["nAS"], gold["nAS_t6"][:n])
-    clean = (o["flags"] & 5) == 0                                         # no convexification: same iteration path
+    clean = (o["flags"] & 13) == 0                                        # no convexification: same iteration path
     assert clean.any() and np.array_equal(o["iter"][clean], gold["iter_t6"][:n][clean])
 
 
@@ -182,7 +182,7 @@ def test_twin_economic_controller(env):
         assert _relerr(o["u0"], gold["u0_t6"]) < 1e-6 and _relerr(o["w"], gold["w_t6"]) < 1e-5
         for b in range(n):
             assert set(np.nonzero(o["lam"][b])[0]) == set(np.nonzero(gold["lam_t6"][b])[0]), (name, b)
-        clean = (o["flags"] & 5) == 0
+        clean = (o["flags"] & 13) == 0
         assert np.array_equal(o["iter"][clean], gold["iter_t6"][clean])
         # at the reference the economic controller returns the reference input in one iteration (P1)
         tw.reset(1)

@@ -57,6 +57,8 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
   P.max_ls = iopts[2];
   P.maxact = (iopts[3] < P.N * P.nh ? iopts[3] : P.N * P.nh) + P.nxt; if (P.maxact < 1) P.maxact = 1;
   P.economic = iopts[4];
+  P.reg_mode = iopts[5];
+  P.nonconvex_after = iopts[6];
   if (P.economic) P.hessian_exact = 1;
   P.tol = dopts[0]; P.lam_tresh = dopts[1]; P.beta = dopts[2]; P.reg_tol = dopts[3]; P.rho_rel = dopts[4];
   P.wref = wref; P.H = H; P.q = q; P.ref_du = ref_du; P.C = C; P.c = c; P.term_idx = term_idx; P.relax0 = relax0;

@@ -26,17 +26,18 @@ def build(name):
             os.path.join(_ROOT, "tunempc_b200/csrc/gen/model_%s.h" % name)]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
         return out
-    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-w",
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-w"] + os.environ.get("TWIN_CXXFLAGS", "").split() + [
                            "-I" + os.path.join(_ROOT, "tunempc_b200/csrc"), "-I" + os.path.join(_ROOT, "tunempc_b200/csrc/gen"),
                            '-DTMPC_MODEL_HEADER="model_%s.h"' % name, srcs[0], "-o", out])
     return out
 
 
 class Twin:
-    def __init__(self, pb, tables, maxact=32, rho_rel=1e4, **_ignored):
+    def __init__(self, pb, tables, maxact=32, rho_rel=1e4, reg_mode=8, nonconvex_after=10, **_ignored):
         self.pb, self.tab = pb, tables
         self.lib = ctypes.CDLL(build(pb.name))
-        self.maxact, self.rho_rel = maxact, rho_rel
+        self.maxact, self.rho_rel, self.reg_mode = maxact, rho_rel, int(os.environ.get("TWIN_REG_MODE", reg_mode))
+        self.nonconvex_after = nonconvex_after
         self.reset(1)
 
     def reset(self, B):
@@ -62,7 +63,7 @@ class Twin:
         dims = np.array([pb.N, pb.nh, pb.nx_term, pb.p], dtype=np.int32)
         hm = pb.hessian_approximation if hessian is None else hessian
         iopts = np.array([1 if hm == "exact" else 0, pb.max_iter, 300, self.maxact,
-                          1 if getattr(pb, "mpc_type", "tuned") == "economic" else 0], dtype=np.int32)
+                          1 if getattr(pb, "mpc_type", "tuned") == "economic" else 0, self.reg_mode, self.nonconvex_after], dtype=np.int32)
         dopts = np.array([pb.tol if tol is None else tol, 1e-8, 0.8, 1e-8, self.rho_rel], dtype=np.float64)
         Hs = np.ascontiguousarray(0.5 * (pb.H + np.transpose(pb.H, (0, 2, 1))))
         relax0 = np.zeros(max(pb.nh, 1), dtype=np.int32)

@@ -7,6 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import load_problem, sample_x0
 from tunempc_b200.pmpc import Pmpc
 pb = load_problem()
+pb.max_iter = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 ctrl = Pmpc(pb, device=0)
 B = 1 << 20
 X0 = sample_x0(pb, B, 100)

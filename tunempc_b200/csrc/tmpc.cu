@@ -399,6 +399,9 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
   }
   P.tol = h->opts.tol; P.lam_tresh = h->opts.lam_tresh; P.beta = h->opts.ls_step_factor;
   P.reg_tol = h->opts.reg_tol; P.rho_rel = h->opts.term_weight;
+  P.reg_mode = 8; P.nonconvex_after = TM_NONCONVEX_AFTER;
+  { const char* na = getenv("TMPC_NONCONVEX_AFTER"); if (na) P.nonconvex_after = atoi(na); }
+  { const char* rm = getenv("TMPC_REG_MODE"); if (rm) P.reg_mode = atoi(rm); }
   {
     // warp-per-instance QP kernels keep the workspace of their instances in shared memory: 2 per CTA if that fits, else
     // 1, else those kernels are not used at all (thread-per-instance kernel for every launch, no shared first QP)

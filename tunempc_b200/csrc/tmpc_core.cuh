@@ -101,6 +101,8 @@ TM_HD TmP tm_mkp(double* base, size_t off) { return base + off; }
 struct TmProb {
   int N, nh, nxt, p, n_w, n_g;
   int hessian_exact, max_iter, max_ls, filter_cap, maxact;
+  int reg_mode;           // 8: primal active-set continuation of non-convex QPs for instances past TM_NONCONVEX_AFTER iterations (default); 24: for every instance; 0: Gauss-Newton re-solve only
+  int nonconvex_after;    // SQP iteration from which reg_mode 8 applies (default TM_NONCONVEX_AFTER)
   int economic;           // 1: stage cost = the model card's l(x,u) (economic MPC, pmpc.py:97-107), 0: tuned tracking cost (mtools.py:43-57)
   double tol, lam_tresh, beta, reg_tol, rho_rel;
   const double *wref, *H, *q, *ref_du, *C, *c;   // wref p*nz | H p*nz*nz (symmetric) | q p*nz | ref_du p*n_g | C nh*nz | c nh
@@ -1275,11 +1277,15 @@ TM_HD void tm_qp0_finish(const TmProb& P, const TmState& S, int64_t inst, int re
 #ifndef TM_MAX_ATTEMPTS
 #define TM_MAX_ATTEMPTS 6
 #endif
+#ifndef TM_NONCONVEX_AFTER
+#define TM_NONCONVEX_AFTER 3
+#endif
 TM_HD void tm_qp(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& ws) {
   unsigned mask[TM_ALW], next[TM_ALW];
   const int NI = P.N * P.nh;
   int use_exact = P.hessian_exact;
-  int flag = 0, work = 0, ret = 0, emptied = 0, attempts = 0;
+  int flag = 0, work = 0, ret = 0, emptied = 0, attempts = 0, have_held = 0, nflip = 0, rel_stage = 0, we = -1;
+  unsigned held[TM_ALW], wrongm[TM_ALW];
   for (int wd = 0; wd < TM_ALW; ++wd) mask[wd] = 0u;
   {
     const double* lam = S.LAM + inst * P.n_g;
@@ -1290,9 +1296,15 @@ TM_HD void tm_qp(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& ws) {
     }
   }
   tm_qp_setup(P, S, inst, ws, use_exact);
-  for (int guard = 0; guard < 4 * TM_MAX_ATTEMPTS; ++guard) {
+  // Instances that are still iterating after TM_NONCONVEX_AFTER SQP iterations sit on non-convex QPs where the Gauss-Newton
+  // re-solve converges slowly or cycles (measured on the CSTR sweep: 20 of 2^20 never converge, the reference needs 5-7
+  // iterations): from then on a QP that turns non-convex is continued by primal active-set steps on the exact Hessian, and the
+  // terminal rows' augmented-Lagrangian weight is raised so that the positive-definiteness test is the one on the reference's space.
+  const int late = (P.reg_mode & 8) && (P.reg_mode >= 16 || S.iter[inst] >= P.nonconvex_after);
+  const double rho_scale = late ? 100.0 : 1.0;
+  for (int guard = 0; guard < 4 * TM_MAX_ATTEMPTS + 12; ++guard) {
     int nwrong = 0, ngi = 0;
-    ret = tm_qp_solve(P, S, inst, ws, mask, next, nwrong, ngi);
+    ret = tm_qp_solve(P, S, inst, ws, mask, next, nwrong, ngi, nullptr, 0, rho_scale);
     work += 1 + ngi;
     int hr = ret == 0 ? (nwrong ? 3 : 0) : (ret == 3 ? 2 : 1);
     if (TM_LANE == 0) {   // attempt histogram: [8 + 4*(0 exact first | 1 exact re-solve | 2 Gauss-Newton) + (0 ok | 1 infeasible | 2 not PD | 3 wrong-signed base rows)]
@@ -1329,16 +1341,88 @@ TM_HD void tm_qp(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& ws) {
         rs = fmax(rs, fabs(v));
       }
       for (int t = 0; t < P.nxt; ++t) rf = fmax(rf, fabs(ws.tr[t] + d[P.N * NZ + P.term_idx[t]]));
-      fprintf(stderr, "[qp] inst %lld guard %d exact %d nwrong %d ngi %d: stationarity %.2e feasibility %.2e\n", (long long)inst, guard, use_exact, nwrong, ngi, rs, rf);
+      double qv = 0.0;
+      for (int k = 0; k < P.N; ++k) for (int c = 0; c < NZ; ++c) {
+        double v = ws.r[k * NZ + c];
+        for (int e = 0; e < NZ; ++e) v += 0.25 * (ws.Q[(size_t)k * NZ * NZ + c * NZ + e] + ws.Q[(size_t)k * NZ * NZ + e * NZ + c]) * d[k * NZ + e];
+        qv += v * d[k * NZ + c];
+      }
+      double smin = 1e300; int nact = 0;
+      for (int e = 0; e < NI; ++e) { double sl = ws.hv[e] + tm_erow_dot(P, e, ws.d); if (sl < smin) smin = sl; if (fabs(sl) < 1e-9) ++nact; }
+      fprintf(stderr, "[qp] inst %lld guard %d exact %d nwrong %d ngi %d: stationarity %.2e feasibility %.2e  q %.10e  min slack %.2e  rows at bound %d\n", (long long)inst, guard, use_exact, nwrong, ngi, rs, rf, qv, smin, nact);
     }
 #endif
     if (ret == 0 && nwrong == 0) break;
     int any = 0;
     for (int wd = 0; wd < TM_ALW; ++wd) any |= (mask[wd] != 0u);
     if (ret == 0) {                                  // wrong-signed base rows
+      for (int wd = 0; wd < TM_ALW; ++wd) { held[wd] = mask[wd] | next[wd]; wrongm[wd] = mask[wd] & ~next[wd]; }   // the working set this solution sits on
+      have_held = 1; rel_stage = 1;
       ++attempts;
       if (attempts < TM_MAX_ATTEMPTS) { for (int wd = 0; wd < TM_ALW; ++wd) mask[wd] = next[wd]; continue; }
       ret = 3;                                       // cycling: treat like a failed factorisation
+    }
+    if (ret == 3 && use_exact && have_held && late && nflip < 3 * TM_MAX_ATTEMPTS) {
+      // Releasing the wrong-signed rows exposes negative curvature: the QP is not convex.  The reference's QP solver then
+      // follows its homotopy until the next constraint blocks ("flipping bounds", external/acados/external/qpoases/
+      // src/QProblem.c:5037-5060).  Here: one inertia-controlling primal active-set step from the held solution.  The
+      // worst wrong-signed row r is moved off its bound along d(t) = argmin over {held rows active, row r at value t},
+      // which is linear in t and descends (multiplier sign) without a minimiser (negative curvature), until the first
+      // row outside the working set blocks; that row takes r's place, which keeps the reduced Hessian positive definite.
+      int jblock = -1, tzero = 0;
+      if (rel_stage == 1) {
+        const double* lqh = S.LAMQ + inst * P.n_g;       // multipliers of the held solution (a failed solve leaves them)
+        double worst = 0.0;
+        we = -1;
+        for (int e = 0; e < NI; ++e) {
+          if (!tm_mask_get(wrongm, e)) continue;
+          const double l = lqh[tm_gh(P, e / P.nh) + e % P.nh];
+          if (l > worst) { worst = l; we = e; }
+        }
+        if (we >= 0) {                                   // first release the worst row alone: positive definite -> ordinary re-solve
+          for (int wd = 0; wd < TM_ALW; ++wd) mask[wd] = held[wd];
+          tm_mask_clr(mask, we);
+          rel_stage = 2; ++nflip;
+          continue;
+        }
+      }
+      if (we >= 0 && rel_stage == 2) {
+        int nw2 = 0, ngi2 = 0, r0, r1 = 1;
+        r0 = tm_qp_solve(P, S, inst, ws, held, next, nw2, ngi2, nullptr, 1, rho_scale);
+        if (r0 == 0) {
+          for (int e = TM_LANE; e < NI; e += TM_NL) ws.sl0[e] = ws.hv[e] + tm_erow_dot(P, e, ws.d);
+          TM_SYNC();
+          if (TM_LANE == 0) ws.hv[we] -= 1.0;
+          TM_SYNC();
+          r1 = tm_qp_solve(P, S, inst, ws, held, next, nw2, ngi2, nullptr, 1, rho_scale);
+          if (TM_LANE == 0) ws.hv[we] += 1.0;
+          TM_SYNC();
+        }
+        work += 2;
+        if (r0 == 0 && r1 == 0) {
+          double tb = TM_INF;
+          int jb = 0x7fffffff;
+          for (int e = TM_LANE; e < NI; e += TM_NL) {
+            const int k = e / P.nh, i = e % P.nh;
+            if ((k == 0 && P.relax0[i]) || tm_mask_get(held, e)) continue;
+            const double s0 = fmax(ws.sl0[e], 0.0), ds = ws.hv[e] + tm_erow_dot(P, e, ws.d) - ws.sl0[e];
+            if (ds < -1e-12 * fmax(1.0, fabs(P.c[i]))) { const double te = s0 / (-ds); if (te < tb) { tb = te; jb = e; } }
+          }
+          tm_wargmin(tb, jb);
+          if (tb < TM_INF) { jblock = jb; tzero = !(tb > 1e-9); }
+        }
+      }
+#if defined(TM_DEBUG_QP) && !defined(__CUDA_ARCH__)
+      fprintf(stderr, "[qp] primal step: release row %d (stage %d row %d, lam %.3e), blocking row %d (stage %d row %d) tzero %d\n", we, we / P.nh, we % P.nh,
+              we >= 0 ? S.LAMQ[inst * P.n_g + tm_gh(P, we / P.nh) + we % P.nh] : 0.0, jblock, jblock / P.nh, jblock % P.nh, tzero);
+#endif
+      if (jblock >= 0) {
+        for (int wd = 0; wd < TM_ALW; ++wd) mask[wd] = held[wd];
+        if (!tzero) tm_mask_clr(mask, we);       // degenerate (zero-length) step: the blocking row joins, r stays
+        tm_mask_set(mask, jblock);
+        have_held = 0; rel_stage = 0; ++nflip; attempts = 0; flag |= 8;
+        continue;
+      }
     }
     if (ret == 3 && use_exact) {
       use_exact = 0; flag |= (guard == 0 ? 1 : 4); attempts = 0;

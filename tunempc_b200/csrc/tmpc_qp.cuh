@@ -32,7 +32,7 @@ struct TmQpWs {
   TmP Gc, gc, ncs;                        // constraint-to-go rows (N+1)*nx*nx, offsets (N+1)*nx, row counts (N+1)
   TmP kk, d, y, rhs;                      // feed-forward of the current sweep; step, correction, right-hand side
   TmP sl, Mc, Lf, cA, rv, nu, acts, acte, sc;   // dual active set: row values, dual-Hessian columns, Schur factor, members
-  TmP Ew, F, f, PAB, pv, tr, lh;          // scratch: elimination rows, stage KKT block, vectors; terminal residual; row multipliers
+  TmP Ew, F, f, PAB, pv, tr, lh, sl0;     // scratch: elimination rows, stage KKT block, vectors; terminal residual; row multipliers; row values of a held solution
 };
 
 TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
@@ -44,7 +44,7 @@ TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
   n += (size_t)(N + 1) * NX * NX + (size_t)(N + 1) * NX + (size_t)(N + 1);                             // Gc gc ncs
   n += (size_t)N * NV + 3 * (size_t)(N + 1) * NZ;                                                      // kk d y rhs
   n += NI + (size_t)(M + 1) * NI + (size_t)M * M + 5 * (size_t)M + 8;                                  // sl Mc Lf cA rv nu acts acte sc
-  n += (size_t)(NX + nh) * TM_ES + NZ * NZ + NZ + NX * NZ + 4 * NX + (nxt > 0 ? nxt : 1) + NI;         // Ew F f PAB pv tr lh
+  n += (size_t)(NX + nh) * TM_ES + NZ * NZ + NZ + NX * NZ + 4 * NX + (nxt > 0 ? nxt : 1) + 2 * NI;     // Ew F f PAB pv tr lh sl0
   return n;
 }
 
@@ -86,6 +86,7 @@ TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s)
   TM_CARVE(pv, 4 * NX);
   TM_CARVE(tr, (nxt > 0 ? nxt : 1));
   TM_CARVE(lh, NI);
+  TM_CARVE(sl0, NI);
 #undef TM_CARVE
 }
 
@@ -980,7 +981,8 @@ TM_HD void tm_qp_setup(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
 // amask_next = base rows with a correctly signed multiplier + the rows the dual active set added: the working set a
 // re-solve starts from.
 TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& s, const unsigned* amask,
-                       unsigned* amask_next, int& nwrong, int& n_gi_out, const TmQpPert* pert = nullptr) {
+                       unsigned* amask_next, int& nwrong, int& n_gi_out, const TmQpPert* pert = nullptr, int eq_only = 0,
+                       double rho_scale = 1.0) {
   const int N = P.N, nh = P.nh, nxt = P.nxt;
   const int lane = TM_LANE;
   const int NI = N * nh;
@@ -1005,12 +1007,12 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   {
     double qmax = 0.0;
     for (int e = lane; e < N * NZ; e += TM_NL) { const int k = e / NZ, i = e % NZ; qmax = fmax(qmax, fabs(s.Q[(size_t)k * NZ * NZ + i * NZ + i])); }
-    rho = P.rho_rel * fmax(tm_wmax(qmax), 1e-300);
+    rho = rho_scale * P.rho_rel * fmax(tm_wmax(qmax), 1e-300);
   }
   int ret = tm_qp_factor(P, s, amask, e0, rho);
   int m = 0, n_gi = 0, n_ricc = 1;
   if (!ret && (NI > 0 || nxt > 0)) {
-    if (pert) {                                   // tabulation: equality rows only
+    if (pert || eq_only) {                        // tabulation / parametric line (tm_qp): equality rows only
       unsigned all[TM_ALW];
       for (int wd = 0; wd < TM_ALW; ++wd) all[wd] = 0xffffffffu;
       ret = tm_qp_gi(P, s, all, m, n_gi, n_ricc);
@@ -1055,6 +1057,7 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
 #endif
   }
   if (ret) return ret;
+  if (eq_only) { nwrong = 0; return 0; }            // the step of the equality-constrained problem is in s.d
   double* dout = pert ? pert->dout : S.D + inst * P.n_w;
   double* lq = pert ? pert->lout : S.LAMQ + inst * P.n_g;
   for (int e = lane; e < P.n_g; e += TM_NL) lq[e] = 0.0;
