@@ -3,6 +3,8 @@
 
   python bench.py --gpus N --steps K --warmup W            B200 arm (under torchrun for N > 1, one rank per GPU)
   python bench.py --impl reference --gpus N --steps K ...  CPU arm: the oracle port of the reference loop on host cores
+  python bench.py --config lq|evaporation|unicycle ...     the other BASELINE.json configs at their own batch sizes
+  python bench.py --scaling strong ...                     fixed 2^20 instances in total, split over the ranks
 
 A "step" = one pass of the hot path over one batch: `ctrl.reset(); ctrl.step(X0)` for B = 2^20 seeded initial states
 per GPU (the alpha-sweep loop of tunempc/closed_loop_tools.py:43-68 as one batched call).  Weak scaling: every rank
@@ -31,34 +33,53 @@ METRIC = "tuned-MPC solves/sec (batched step, fp64)"
 UNIT = "solves/s"
 
 
-def sample_x0(pb, B, seed):
-    """cA-direction sweep alpha in [-0.1, 1.0] of examples/cstr/main.py:124-131 plus
-    1e-2*|x_s| jitter on the other states (same generator as tests/golden/make_golden.py)."""
-    rng = np.random.default_rng(seed)
-    xs = pb.wref[0, :pb.nx]
-    alpha = rng.uniform(-0.1, 1.0, B)
-    X0 = np.tile(xs, (B, 1))
-    X0[:, 0] += alpha * (1.0 - xs[0])
-    X0[:, 1:] += 1e-2 * np.abs(xs[1:]) * rng.uniform(-1, 1, (B, pb.nx - 1))
-    return X0
+# BASELINE.json configs: fixture, default batch per GPU, MPC steps per bench step (closed loop), workload text
+CONFIGS = {
+    "cstr": dict(B=1 << 20, cl=1, text="cstr N=20 tuned NMPC (examples/cstr)"),
+    "lq": dict(B=1 << 10, cl=1, text="convex LQR N=10 tuned MPC (examples/convex_lqr.py)"),
+    "evaporation": dict(B=1 << 18, cl=1, text="evaporation process N=30 tuned NMPC, collocation, state constraints (examples/evaporation_process)"),
+    "unicycle": dict(B=1 << 16, cl=100, text="unicycle p=N=30 periodic tuned MPC, 100-step closed loop, plant = model (examples/unicycle)"),
+}
 
 
-def load_problem():
+def sample_x0(pb, B, seed, name="cstr"):
+    """the examples' own perturbation recipes, seeded (cstr: cA sweep alpha in [-0.1, 1.0] of
+    examples/cstr/main.py:124-131 plus 1e-2*|x_s| jitter); same generator as the golden fixtures."""
+    from tunempc_b200 import configs
+    return configs.sample_x0(name, pb, B, seed)
+
+
+def load_problem(name="cstr"):
     from tunempc_b200.problem import MpcProblem
-    return MpcProblem.load(os.path.join(ROOT, "tests", "golden", "problem_cstr.npz"))
+    return MpcProblem.load(os.path.join(ROOT, "tests", "golden", "problem_%s.npz" % name))
 
 
-def algorithmic_flops_per_stage_lin(exact=True):
-    """fp64 add/mul/div = 1, FMA = 2, op counts of the generated model code (modelgen)."""
+def algorithmic_flops_per_stage_lin(exact=True, name="cstr"):
+    """fp64 add/mul/div = 1, FMA = 2, op counts of the generated model code (modelgen).
+    RK4 models: the formula of SURVEY 8(d).  Discrete models: one evaluation (M = 1/4 of an RK4 step).  Collocation models:
+    per finite element 4 Newton iterations (3 stage evaluations f + J, LU of the 3nx x 3nx iteration matrix, one solve), then
+    one solve per first-order direction and per second-order pair against the same factorisation (tm_colloc_stage)."""
     from tunempc_b200 import configs, modelgen
     import tempfile
-    m = configs.cstr()["model"]
+    m = configs.CONFIGS[name]()["model"]
     with tempfile.TemporaryDirectory() as d:
         oc = modelgen.generate_header(m, os.path.join(d, "m.h"))
     nx, nu, M = m.nx, m.nu, m.rk_steps
     nz = nx + nu
     c_f, c_J = oc["c_f"], oc["c_J"] - oc["c_f"]
     c_H = (oc["c_H"] - oc["c_J"]) + oc["c_bilin"]
+    if getattr(m, "discrete", False):
+        f_gn = c_f + c_J + 2 * nx * nx * nz
+        f_ex = f_gn + c_H + 2 * nz * nz * nx + 2 * nx * nz * nz
+        return (f_ex if exact else f_gn), c_f
+    if getattr(m, "integrator", "rk") == "collocation":
+        n = 3 * nx
+        lu, sol = 2 * n ** 3 // 3, 2 * n * n
+        newton = 4 * (3 * (c_f + c_J) + lu + sol)
+        first = nz * (3 * 2 * nx * nz + sol)
+        second = (nz * (nz + 1) // 2) * (3 * (c_H // max(nz * (nz + 1) // 2, 1) + 2 * nz * nz + 2 * nx * nx) + sol)
+        f_gn = M * (newton + first)
+        return (f_gn + M * second if exact else f_gn), M * newton
     f_gn = M * (4 * (c_f + c_J + 2 * nx * nx * nz) + 16 * nx * (1 + nz))
     f_ex = f_gn + M * 4 * (c_H + 2 * nz * nz * nx + 2 * nx * nz * nz)
     f_dyn = M * (4 * c_f + 16 * nx)
@@ -98,18 +119,51 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------------------
 def _oracle_worker(args):
-    idx_list, seed = args
+    idx_list, seed, name = args
     from threadpoolctl import threadpool_limits
     from oracle import reference_port as rp
-    pb = load_problem()
+    pb = load_problem(name)
     ctrl = rp.Pmpc(pb)
-    X0 = sample_x0(pb, max(idx_list) + 1, seed)
+    X0 = sample_x0(pb, max(idx_list) + 1, seed, name)
     t = time.perf_counter()
     with threadpool_limits(limits=1):
         for i in idx_list:
             ctrl.reset()                                   # closed_loop_tools.py:68
             ctrl.step(X0[i])                               # closed_loop_tools.py:56
     return time.perf_counter() - t, len(idx_list)
+
+
+def _twin_worker(args):
+    """compiled CPU baseline: the solver source of the CUDA library compiled as a sequential host program
+    (tests/twin, test infrastructure), one process per core, each on its own chunk of the sample"""
+    lo, hi, seed, name = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from twin.twin import Twin
+    from tunempc_b200.problem import build_tables
+    pb = load_problem(name)
+    X0 = sample_x0(pb, hi, seed, name)[lo:hi]
+    tw = Twin(pb, build_tables(pb))
+    tw.reset(hi - lo)
+    t = time.perf_counter()
+    o = tw.step(X0)
+    return time.perf_counter() - t, hi - lo, int((o["status"] == 0).sum())
+
+
+def compiled_cpu_baseline(name, per_core=48, seed=1000):
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from twin.twin import build as twin_build
+    twin_build(name)                                       # g++ once, before the pool forks
+    cores = len(os.sched_getaffinity(0))
+    n = cores * per_core
+    jobs = [(c * per_core, (c + 1) * per_core, seed, name) for c in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_twin_worker, jobs)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d x0 of the same distribution (%d per core, %d converged), the CUDA library's solver source compiled with g++ -O2 "
+                      "as a sequential host program (tests/twin), one process per core" % (n, per_core, sum(r[2] for r in res))}
 
 
 def run_reference_arm(args):
@@ -119,17 +173,19 @@ def run_reference_arm(args):
         return
     import multiprocessing as mp
     from oracle import reference_port as rp
-    rp.build(("cstr",))
+    name = args.config
+    rp.build((name,))
+    backend = "qpOASES_e (reference tree, oracle/_ref)" if rp.qpoases_available() else "dense null-space + Goldfarb-Idnani (oracle fallback: oracle/_ref missing)"
     cores = len(os.sched_getaffinity(0))
     per_core = 6                                   # ~2 s of CPU work per core and step
     n = cores * per_core
-    chunks = [(list(range(c, n, cores)), 1000) for c in range(cores)]
+    chunks = [list(range(c, n, cores)) for c in range(cores)]
     ctx = mp.get_context("fork")
     times = []
     with ctx.Pool(cores) as pool:
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            pool.map(_oracle_worker, [(c[0], 1000 + s) for c in chunks])
+            pool.map(_oracle_worker, [(c, 1000 + s, name) for c in chunks])
             dt = time.perf_counter() - t0
             if s >= args.warmup:
                 times.append(dt)
@@ -138,12 +194,26 @@ def run_reference_arm(args):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "cstr N=20 tuned NMPC (examples/cstr), exact Hessian, reset+step per x0",
-                       "sample": "%d x0 per step (bounded sample of the B=2^20-per-GPU workload of the B200 arm)" % n},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d instances per step (oracle port: numpy + C stage functions + qpOASES_e), %d steps" % (n, len(times))},
+            "config": {"workload": "%s, exact Hessian, reset+step per x0" % CONFIGS[name]["text"],
+                       "sample": "%d x0 per step (bounded sample of the workload of the B200 arm)" % n},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "qp_backend": backend,
+                             "sample": "%d instances per step (oracle port: numpy + C stage functions + QP backend), %d steps" % (n, len(times))},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    try:
+        line["cpu_baseline_compiled"] = compiled_cpu_baseline(name)
+    except Exception as e:
+        line["cpu_baseline_compiled"] = {"value": None, "sample": "failed: %r" % (e,)}
     print(json.dumps(line))
+
+
+def ncu_traffic():
+    """DRAM bytes per unit of the dominant kernels from the newest committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep of the same code)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -153,7 +223,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--batch", type=int, default=1 << 20, help="instances per GPU per step")
+    ap.add_argument("--config", default="cstr", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU per step (default: the config's BASELINE.json size)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: the batch is the TOTAL, split over the ranks")
     ap.add_argument("--hessian", default="exact")
     ap.add_argument("--cpu-sample", type=int, default=40, help="x0 of the batch timed on the CPU oracle port (about 12 s)")
     args = ap.parse_args()
@@ -181,63 +253,77 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    pb = load_problem()
+    name = args.config
+    cfg = CONFIGS[name]
+    pb = load_problem(name)
     pb.hessian_approximation = args.hessian
     ctrl = Pmpc(pb, device=local)
-    B = args.batch
+    B = args.batch or cfg["B"]
+    if args.scaling == "strong":
+        B = B // world                                    # fixed total work
+    CL = cfg["cl"]
     W = max(args.warmup, 3)
     K = args.steps
     nbatches = 2
-    X0_host = [torch.from_numpy(sample_x0(pb, B, 100 + 17 * rank + i)).pin_memory() for i in range(nbatches)]
+    X0_host = [torch.from_numpy(sample_x0(pb, B, 100 + 17 * rank + i, name)).pin_memory() for i in range(nbatches)]
     X0_dev = [x.to(dev) for x in X0_host]
-    U_host = torch.empty((B, pb.nu), dtype=torch.float64).pin_memory()
-    st_host = torch.empty(B, dtype=torch.int32).pin_memory()
     peak_tf = ctrl.fp64_peak_tflops()
+    acc = {"lin_ms": 0.0, "qp_ms": 0.0, "post_ms": 0.0, "n_lin": 0, "n_qp": 0, "n_it": 0, "n_launch": 0, "n_dyn": 0}
+
+    def account():
+        t = ctrl.timing()
+        c = ctrl.counters()
+        acc["lin_ms"] += t["lin_ms"]; acc["qp_ms"] += t["qp_ms"]; acc["post_ms"] += t["post_ms"]
+        acc["n_lin"] += c["stage_linearisations"]; acc["n_qp"] += c["qp_solves"]; acc["n_it"] += c["sqp_iterations"]
+        acc["n_launch"] += c["kernel_launches"]; acc["n_dyn"] += c["ls_dynamics_evals"]
+
+    # ---- one bench step: reset + step (cl = 1) or a CL-step closed loop with the model as plant (unicycle) ----
+    def one_step(x, count=False):
+        ctrl.reset()
+        if CL == 1:
+            u = ctrl.step(x, outputs="u0")
+            if count:
+                account()
+            return u
+        X = x
+        host = not hasattr(X, "device")
+        for _ in range(CL):
+            U = ctrl.step(X, outputs="u0")
+            if count:
+                account()
+            if host:                                      # end-to-end arm: state and input cross the boundary every MPC step
+                X = ctrl.plant_step(torch.as_tensor(X, device=dev), torch.as_tensor(U, device=dev)).cpu().numpy()
+            else:
+                X = ctrl.plant_step(X, U)
+        return U
 
     # ---- device-resident arm: inputs already in HBM --------------------------------------------------------
-    def dev_step(i):
-        ctrl.reset()
-        return ctrl.step(X0_dev[i % nbatches], outputs="u0")
-
     for i in range(W):
-        dev_step(i)
+        one_step(X0_dev[i % nbatches])
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    lin_ms = qp_ms = post_ms = 0.0
-    n_lin = n_qp = n_it = n_launch = n_dyn = 0
     for i in range(K):
-        dev_step(i)
-        t = ctrl.timing()
-        c = ctrl.counters()
-        lin_ms += t["lin_ms"]; qp_ms += t["qp_ms"]; post_ms += t["post_ms"]
-        n_lin += c["stage_linearisations"]; n_qp += c["qp_solves"]; n_it += c["sqp_iterations"]
-        n_launch += c["kernel_launches"]; n_dyn += c["ls_dynamics_evals"]
+        one_step(X0_dev[i % nbatches], count=True)
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1)
     status = ctrl.status
     flags = ctrl.log["flags"][-1]
-    stat_hist = torch.bincount(status.to(torch.int64), minlength=5)[:5].to(torch.float64)
+    stat_hist = torch.bincount(status.to(torch.int64), minlength=6)[:6].to(torch.float64)
     # per-bit counts: [no flag, GN fallback (1), damped step (2), GN re-solve (4), non-convex primal step (8)]
     fl_hist = torch.stack([(flags == 0).sum()] + [((flags & b) != 0).sum() for b in (1, 2, 4, 8)]).to(torch.float64)
 
     # ---- end-to-end arm: host buffers through the C ABI (tmpc_step_host), H2D + D2H inside the timed region ----
     x_np = [x.numpy() for x in X0_host]
-
-    def host_step(i):
-        ctrl.reset()
-        u = ctrl.step(x_np[i % nbatches], outputs="u0")
-        return u
-
-    host_step(0)
+    one_step(x_np[0])
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        host_step(i)
+        one_step(x_np[i % nbatches])
     torch.cuda.synchronize()
     ms_e2e_local = 1e3 * (time.perf_counter() - t0)
     barrier()
@@ -252,16 +338,17 @@ def main():
     ms_dev, ms_e2e = float(tvec[0]), float(tvec[1])
 
     if rank == 0:
-        f_lin, f_dyn = algorithmic_flops_per_stage_lin(args.hessian == "exact")
+        lin_ms, qp_ms, post_ms = acc["lin_ms"], acc["qp_ms"], acc["post_ms"]
+        n_lin, n_qp = acc["n_lin"], acc["n_qp"]
+        f_lin, f_dyn = algorithmic_flops_per_stage_lin(args.hessian == "exact", name)
         ach = (n_lin * f_lin) / (lin_ms * 1e-3) / 1e12 if lin_ms > 0 else 0.0
-        # DRAM traffic of the dominant kernels from the committed ncu --set full captures (profiles/r01e_summary.md):
-        # k_lin2 440.0 MB read + 972.8 MB written per launch of 131072 x 20 stage tasks; k_qp_thread 30.3 + 6.2 GB per
-        # launch of 131072 QPs.  Algorithmic bytes: a stage task reads (x,u,lam_dyn) and writes its 49-double record;
-        # a QP reads its N records + w and writes (d, lam).
-        lin_traffic_per_task = (439.988992e6 + 972.843008e6) / (131072 * 20)
-        lin_alg_bytes_per_task = 8.0 * (pb.nx + pb.nu + pb.nx) + 8.0 * (pb.nx + pb.nx * pb.nz + pb.nz * (pb.nz + 1) // 2)
-        qp_traffic_per_qp = (30.312675e9 + 6.179678e9) / 131072
-        qp_alg_bytes = 8.0 * (pb.N * (pb.nx + pb.nx * pb.nz + pb.nz * (pb.nz + 1) // 2) + 2 * pb.n_w + pb.n_g + pb.nx)
+        # Algorithmic bytes: a stage task reads (x,u,lam_dyn) and writes its record xf | S | W; a QP reads its N records + w and
+        # writes (d, lam).  Measured DRAM traffic: profiles/ncu_traffic.json (ncu --set full of this code, tools/ncu_traffic.py).
+        npair = pb.nz * (pb.nz + 1) // 2
+        lin_alg_bytes_per_task = 8.0 * (pb.nx + pb.nu + pb.nx) + 8.0 * (pb.nx + pb.nx * pb.nz + npair)
+        qp_alg_bytes = 8.0 * (pb.N * (pb.nx + pb.nx * pb.nz + npair) + 2 * pb.n_w + pb.n_g + pb.nx)
+        tr = ncu_traffic().get(name, {})
+        lin_tr, qp_tr = tr.get("lin", {}), tr.get("qp", {})
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
                 hbm_peak = float(json.load(fh)["hbm_gbs"])
@@ -269,40 +356,45 @@ def main():
         except Exception:
             hbm_peak, hbm_src = 6550.0, "fallback (B200_PROFILING.md)"
         qp_ach = n_qp * qp_alg_bytes / (qp_ms * 1e-3) / 1e9 if qp_ms > 0 else 0.0
+        solves = world * B * K * CL
+        roof_lin = {"bound": "fp64", "kernel": lin_tr.get("kernel", "k_lin2 / k_lin"), "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf if peak_tf else None,
+                    "traffic": lin_tr["dram_bytes_per_task"] * B * pb.N if "dram_bytes_per_task" in lin_tr else None,
+                    "traffic_note": "ncu dram read+write per full-batch launch: %s B per stage task (capture %s), algorithmic %.0f B"
+                                    % (lin_tr.get("dram_bytes_per_task"), lin_tr.get("capture"), lin_alg_bytes_per_task),
+                    "peak_source": "in-run DFMA micro-benchmark (tmpc_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                    "flops_per_stage_linearisation": f_lin, "stage_linearisations": int(n_lin),
+                    "kernel_ms": {"k_lin": lin_ms, "k_qp": qp_ms, "k_post": post_ms, "step_total": ms_dev},
+                    "hbm_GBps_boundary_io": (B * K * CL * 8 * (pb.nx + pb.nu) + 0.0) / (ms_dev * 1e-3) / 1e9}
+        roof_qp = {"bound": "hbm", "kernel": qp_tr.get("kernel", "k_qp_thread (+ k_qp0, k_qp)"), "achieved": qp_ach, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": qp_ach / hbm_peak,
+                   "traffic": qp_tr["dram_bytes_per_qp"] * B if "dram_bytes_per_qp" in qp_tr else None,
+                   "note": "algorithmic %.0f B per QP (records + w in, d + lam out); measured DRAM traffic %s B per QP (capture %s)"
+                           % (qp_alg_bytes, qp_tr.get("dram_bytes_per_qp"), qp_tr.get("capture")),
+                   "peak_source": hbm_src}
+        lin_dominant = lin_ms >= qp_ms
         line = {
-            "metric": METRIC, "value": world * B * K / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": solves / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cstr N=20 tuned NMPC (examples/cstr), %s Hessian, B=%d x0 per GPU per step, reset+step"
-                                   % (args.hessian, B),
-                       "l2": "working set %.1f GB per step >> L2; %d alternating input batches" % (B * 14.5e3 / 1e9, nbatches),
-                       "x0": "cA sweep alpha~U(-0.1,1.0) + 1e-2 jitter, seed 100+17*rank+i"},
-            "e2e": {"value": world * B * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * pb.nx * 8,
-                    "d2h_bytes_per_step": B * pb.nu * 8 + 3 * B * 4},
-            "gpu_launches": int(n_launch),
+            "config": {"workload": "%s, %s Hessian, B=%d x0 per GPU per step, %s" % (cfg["text"], args.hessian, B,
+                                   "reset+step" if CL == 1 else "reset + %d closed-loop steps" % CL),
+                       "l2": "working set %.1f GB per step >> L2; %d alternating input batches" % (B * 8.0 * (3 * pb.n_w + 3 * pb.n_g + pb.N * (pb.nx + pb.nx * pb.nz + npair)) / 1e9, nbatches),
+                       "x0": "seeded perturbation recipe of the example (tunempc_b200.configs.sample_x0), seed 100+17*rank+i"},
+            "e2e": {"value": solves / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * pb.nx * 8 * CL,
+                    "d2h_bytes_per_step": (B * pb.nu * 8 + 3 * B * 4) * CL + (B * pb.nx * 8 * CL if CL > 1 else 0)},
+            "gpu_launches": int(acc["n_launch"]),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "fp64", "kernel": "k_lin2", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": ach / peak_tf if peak_tf else None,
-                         "traffic": lin_traffic_per_task * 32 * ((B * pb.N + 31) // 32),
-                         "traffic_note": "ncu dram read+write per full-batch launch (%.0f B per stage task measured at B=131072, "
-                                         "algorithmic %.0f B: DRAM traffic = the records)" % (lin_traffic_per_task, lin_alg_bytes_per_task),
-                         "peak_source": "in-run DFMA micro-benchmark (tmpc_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-                         "flops_per_stage_linearisation": f_lin, "stage_linearisations": int(n_lin),
-                         "kernel_ms": {"k_lin": lin_ms, "k_qp": qp_ms, "k_post": post_ms, "step_total": ms_dev},
-                         "hbm_GBps_boundary_io": (B * K * 8 * (pb.nx + pb.nu) + 0.0) / (ms_dev * 1e-3) / 1e9},
-            "roofline_qp": {"bound": "hbm", "kernel": "k_qp_thread (+ k_qp0, k_qp)", "achieved": qp_ach, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": qp_ach / hbm_peak, "traffic": qp_traffic_per_qp * B,
-                            "note": "algorithmic %.0f B per QP (records + w in, d + lam out); measured DRAM traffic %.0f B per QP: the "
-                                    "lane-interleaved Riccati / working-set workspace streams through HBM" % (qp_alg_bytes, qp_traffic_per_qp),
-                            "peak_source": hbm_src},
-            "stats": {"sqp_iter_mean": n_it / (B * K), "qp_solves": int(n_qp), "ls_dynamics_evals": int(n_dyn),
+            "roofline": roof_lin if lin_dominant else roof_qp,
+            ("roofline_qp" if lin_dominant else "roofline_lin"): roof_qp if lin_dominant else roof_lin,
+            "stats": {"sqp_iter_mean": acc["n_it"] / (B * K * CL), "qp_solves": int(n_qp), "ls_dynamics_evals": int(acc["n_dyn"]),
                       "status_hist": [int(v) for v in stat_hist.tolist()], "flags_hist": [int(v) for v in fl_hist.tolist()],
                       "flags_hist_keys": ["none", "gn_fallback", "damped", "gn_resolve", "nonconvex_step"]},
         }
-        # ---- CPU baseline: the oracle port on a bounded sample of the same workload, 1 core ----
+        # ---- CPU baselines on bounded samples of the same workload: the oracle port on one core, the compiled twin on all ----
         try:
             from oracle import reference_port as rp
-            oc = rp.Pmpc(load_problem())
+            oc = rp.Pmpc(load_problem(name))
             n = args.cpu_sample
             xs = x_np[0][:n]
             from threadpoolctl import threadpool_limits
@@ -313,9 +405,15 @@ def main():
                     oc.step(xs[i])
                 dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "first %d x0 of the same batch, oracle port (numpy + C stage functions + qpOASES_e)" % n}
+                                    "qp_backend": "qpOASES_e (reference tree, oracle/_ref)" if rp.qpoases_available() else "dense fallback",
+                                    "sample": "first %d x0 of the same batch, oracle port (numpy + C stage functions + QP backend)" % n}
         except Exception as e:   # the oracle is a checker, its absence must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
+        if args.cpu_sample > 1:
+            try:
+                line["cpu_baseline_compiled"] = compiled_cpu_baseline(name)
+            except Exception as e:
+                line["cpu_baseline_compiled"] = {"value": None, "sample": "failed: %r" % (e,)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

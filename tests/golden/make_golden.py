@@ -21,28 +21,7 @@ from tunempc_b200.problem import build_tables      # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def sample_x0(name, pb, B, seed=0):
-    """synthetic initial states of SURVEY.md section 8(d) (same generator as bench.py)"""
-    rng = np.random.default_rng(seed)
-    xs = pb.wref[0, :pb.nx]
-    if name == "lq":
-        return xs + rng.uniform(-1, 1, (B, pb.nx))
-    if name == "cstr":
-        alpha = rng.uniform(-0.1, 1.0, B)                       # examples/cstr/main.py:124
-        X0 = np.tile(xs, (B, 1))
-        X0[:, 0] += alpha * (1.0 - xs[0])                       # dx_diehl direction, examples/cstr/main.py:126-131
-        X0[:, 1:] += 1e-2 * np.abs(xs[1:]) * rng.uniform(-1, 1, (B, pb.nx - 1))
-        return X0
-    if name == "evaporation":
-        # SURVEY.md 8(d) #3: X2 sits on its bound 25.0 -> perturb upward only; P2 +-1.0 (evaporation_process/main.py:178-180)
-        return xs + np.stack([0.5 * np.abs(rng.uniform(-1, 1, B)), 1.0 * rng.uniform(-1, 1, B)], axis=1)
-    if name == "chain":
-        return xs + np.array([0.5, 0.5, 0.5, 0.8, 0.8, 0.8]) * rng.uniform(-1, 1, (B, pb.nx))
-    if name == "dims9":
-        return xs + np.array([0.4] * 4 + [0.6] * 4 + [0.3]) * rng.uniform(-1, 1, (B, pb.nx))
-    if name == "unicycle":
-        return xs + np.array([0.5, 0.1, 0.0, 0.0]) * rng.uniform(-1, 1, (B, pb.nx))   # examples/unicycle/main.py:172
-    raise KeyError(name)
+sample_x0 = configs.sample_x0      # synthetic initial states of SURVEY.md section 8(d) (same generator as bench.py)
 
 
 def unicycle():

@@ -381,3 +381,42 @@ def test_generic_dimensions(torch_mod, name, lin_mode, monkeypatch):
     assert _relerr(U, gold["u0_t6"]) < 1e-6 and _relerr(ctrl.w_sol.cpu().numpy(), gold["w_t6"]) < 1e-6
     assert np.array_equal(ctrl.log["iter"][-1].cpu().numpy(), gold["iter_t6"])
     assert np.array_equal(ctrl.log["nAS"][-1].cpu().numpy(), gold["nAS_t6"])
+
+
+@pytest.mark.parametrize("name,qpmode", [("lq", None), ("cstr", None), ("cstr", "t"), ("cstr", "w"), ("evaporation", None),
+                                         ("evaporation", "t"), ("unicycle", None), ("unicycle", "t")])
+def test_large_fixture(torch_mod, name, qpmode, monkeypatch):
+    """4096 seeded x0 per config against the committed oracle fixture (tests/golden/make_golden_large.py):
+    u0 and x_1 to 1e-6 relative, identical active sets, the log outputs f / nAS / nACtot / nAC, iteration counts on the
+    instances whose QPs stayed convex -- with the default kernel dispatch and with each QP kernel forced."""
+    torch = torch_mod
+    import os
+    from test_twin import _large_compare
+    from tunempc_b200 import configs
+    if qpmode is not None:
+        monkeypatch.setenv("TMPC_QP_MODE", qpmode)
+        monkeypatch.setenv("TMPC_QP_THREAD_MIN", "1")
+    ctrl, pb = _ctrl(name)
+    L = np.load(os.path.join(os.path.dirname(__file__), "golden", "large_%s.npz" % name))
+    n = int(L["B"])
+    X0 = configs.sample_x0(name, pb, n, int(L["seed"]))
+    U = ctrl.step(torch.tensor(X0, device="cuda:0")).cpu().numpy()
+    lg = ctrl.log
+    o = {"status": ctrl.status.cpu().numpy(), "u0": U, "x1": ctrl.w_sol[:, pb.nz:pb.nz + pb.nx].cpu().numpy(),
+         "nAS": lg["nAS"][-1].cpu().numpy(), "nACtot": lg["nACtot"][-1].cpu().numpy(), "nAC": lg["nAC"][-1].cpu().numpy(),
+         "f": lg["f"][-1].cpu().numpy(), "flags": lg["flags"][-1].cpu().numpy(), "iter": lg["iter"][-1].cpu().numpy()}
+    nclean = _large_compare(name, pb, L, n, o, ctrl.lam_g.cpu().numpy(), "gpu")
+    if name != "cstr":
+        assert nclean == n                                                       # convex throughout: the oracle's iteration counts everywhere
+
+
+def test_status_not_pd(torch_mod):
+    """status 3 (sqp_method.py:193-201), same case as tests/test_twin.py::test_twin_status_not_pd"""
+    torch = torch_mod
+    pb = load_problem("lq")
+    pb.H = 0.0 * pb.H
+    pb.q = 0.0 * pb.q
+    from tunempc_b200.pmpc import Pmpc
+    ctrl = Pmpc(pb, device=0)
+    ctrl.step(torch.tensor(load_golden("lq")["X0"][:8], device="cuda:0"))
+    assert (ctrl.status.cpu().numpy() == 3).all()

@@ -153,6 +153,7 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
     nact = cnts[0];
     if (++guard > P.max_iter + 2) return 9;
   }
+  for (long long i = 0; i < B; ++i) tm_pd_check(P, S, i, ws);          // sqp_method.py:190-201
   for (long long i = 0; i < B; ++i) tm_shift(P, W + i * P.n_w, LAM + i * P.n_g, Wsh + i * P.n_w, Lsh + i * P.n_g);
   if (counters_out) { counters_out[0] = (long long)counters[0]; counters_out[2] = nqp; counters_out[3] = nlin; counters_out[4] = (long long)counters[4]; counters_out[5] = (long long)counters[5]; counters_out[6] = (long long)counters[6]; counters_out[7] = (long long)counters[7]; for (int i = 8; i < TM_NCNT; ++i) counters_out[i] = (long long)counters[i]; }
   return 0;

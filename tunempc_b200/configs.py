@@ -186,6 +186,30 @@ def dims9():
     return dict(model=model, cost=cost, C=C, c=cc, w_guess=w_guess, period=1, N=20, term_idx=[1, 2, 4, 5, 6, 7, 8])
 
 
+def sample_x0(name, pb, B, seed=0):
+    """synthetic initial states of SURVEY.md section 8(d): the reference examples' own perturbation recipes, seeded"""
+    rng = np.random.default_rng(seed)
+    xs = pb.wref[0, :pb.nx]
+    if name == "lq":
+        return xs + rng.uniform(-1, 1, (B, pb.nx))
+    if name == "cstr":
+        alpha = rng.uniform(-0.1, 1.0, B)                       # examples/cstr/main.py:124
+        X0 = np.tile(xs, (B, 1))
+        X0[:, 0] += alpha * (1.0 - xs[0])                       # dx_diehl direction, examples/cstr/main.py:126-131
+        X0[:, 1:] += 1e-2 * np.abs(xs[1:]) * rng.uniform(-1, 1, (B, pb.nx - 1))
+        return X0
+    if name == "evaporation":
+        # X2 sits on its bound 25.0 -> perturb upward only; P2 +-1.0 (examples/evaporation_process/main.py:178-180)
+        return xs + np.stack([0.5 * np.abs(rng.uniform(-1, 1, B)), 1.0 * rng.uniform(-1, 1, B)], axis=1)
+    if name == "chain":
+        return xs + np.array([0.5, 0.5, 0.5, 0.8, 0.8, 0.8]) * rng.uniform(-1, 1, (B, pb.nx))
+    if name == "dims9":
+        return xs + np.array([0.4] * 4 + [0.6] * 4 + [0.3]) * rng.uniform(-1, 1, (B, pb.nx))
+    if name == "unicycle":
+        return xs + np.array([0.5, 0.1, 0.0, 0.0]) * rng.uniform(-1, 1, (B, pb.nx))   # examples/unicycle/main.py:172
+    raise KeyError(name)
+
+
 CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle, "evaporation": evaporation, "chain": chain, "dims9": dims9}
 
 

@@ -56,6 +56,7 @@ struct tmpc_handle {
   int qp_mode = 2;             // 2: hybrid (thread per instance for big launches, warp per instance for the tail), 1: thread, 0: warp
   int qp_thread_min = 16384;   // hybrid: launches with fewer candidate instances use the low-latency warp kernel
   bool trace = false;
+  bool pd_check = true;        // run the reference's post-solve reduced-Hessian test (status 3); TMPC_PD_CHECK=0 skips it
   int lin_mode = 2;             // 2: warp-specialised k_lin2 (RK4 models), 1: thread per (instance, stage, pair) k_lin
   bool uniform_ws = false;     // warm start identical for every instance (right after tmpc_reset)
   int qp_blocks = 0;           // resident CTAs of the thread-per-instance kernel
@@ -420,6 +421,7 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
     if (m && m[0] == 'w' && h->qp_warps > 0) h->qp_mode = 0;
     if (m && m[0] == 't') h->qp_mode = 1;
     h->trace = getenv("TMPC_TRACE") != nullptr;
+    { const char* pc = getenv("TMPC_PD_CHECK"); if (pc) h->pd_check = atoi(pc) != 0; }
     const char* lm = getenv("TMPC_LIN_MODE");
     if (lm) h->lin_mode = atoi(lm);
 #if !TMPC_RK4
@@ -738,6 +740,18 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
     src = S.list_next;
     nact = hc[0];
     if (++iter_guard > P.max_iter + 2) { h->err = "tmpc_step: iteration guard tripped"; return 1; }
+  }
+  // post-solve sanity check of the reference (sqp_method.py:190-201): reduced Hessian positive definite at the solution
+  if (h->pd_check) {
+    TmState Sc = S;
+    Sc.pd_check = 1;
+    const bool use_thread = h->qp_mode == 1 || (h->qp_mode == 2 && B >= h->qp_thread_min);
+    if (use_thread)
+      CK(tm_launch_qp_thread(P, Sc, nullptr, (int)B, nullptr, h->qp_ws, h->qp_ws_per_inst, h->qp_blocks, h->qp_counter, st));
+    else
+      k_qp<<<(unsigned)((B + h->qp_warps - 1) / h->qp_warps), h->qp_warps * 32, h->qp_smem, st>>>(P, Sc, nullptr, (int)B, nullptr);
+    CK(cudaGetLastError());
+    ++launches;
   }
   // outputs, then the warm-start shift (pmpc.py:410-423)
   const size_t b = (size_t)B;

@@ -126,6 +126,7 @@ struct TmState {
                           //    kernel is fed instances of similar cost so that the lanes of a warp stay in step)
   unsigned* almask;       // B*TM_ALW: augmented-Lagrangian row mask carried between retries
   int *list_retry, *cnt_retry;   // instances whose QP must be re-solved (filled by tm_qp)
+  int pd_check;           // 1: the QP kernels run tm_pd_check instead of a QP (same workspace, same dispatch)
   unsigned* asinit;       // B*aswords bitmask of initially active inequality rows
   int aswords;
   int *list_next, *cnt_next, *list_relin, *cnt_relin;
@@ -1267,6 +1268,31 @@ TM_HD void tm_qp0_finish(const TmProb& P, const TmState& S, int64_t inst, int re
   }
 }
 
+// __postprocessing's sanity check (sqp_method.py:190-201): at the returned point the Hessian (exact or Gauss-Newton, as
+// configured) must be positive definite on the null space of [equality rows; inequality rows with a non-zero multiplier],
+// else the reference raises AssertionError -> status TMPC_NOT_PD here.  Test = the constraint-to-go factorisation with those
+// rows held (its projected-block Cholesky pivots), terminal rows weighted 100x so the test space is the reference's.
+// LIN must be valid at (W, LAM) -- it is for every finished instance (tm_finalize).
+TM_HD void tm_pd_check(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& ws) {
+  const int st = S.status[inst];
+  if (st != 0 && st != 1) return;
+  unsigned mask[TM_ALW];
+  for (int wd = 0; wd < TM_ALW; ++wd) mask[wd] = 0u;
+  const double* lam = S.LAM + inst * P.n_g;
+  for (int e = 0; e < P.N * P.nh; ++e) {
+    const int k = e / P.nh, i = e % P.nh;
+    if (k == 0 && P.relax0[i]) continue;
+    if (lam[tm_gh(P, k) + i] != 0.0) tm_mask_set(mask, e);
+  }
+  tm_qp_setup(P, S, inst, ws, P.hessian_exact);
+  double qmax = 0.0;
+  for (int e = TM_LANE; e < P.N * NZ; e += TM_NL) { const int k = e / NZ, i = e % NZ; qmax = fmax(qmax, fabs(ws.Q[(size_t)k * NZ * NZ + i * NZ + i])); }
+  const double rho = 100.0 * P.rho_rel * fmax(tm_wmax(qmax), 1e-300);
+  const int ret = tm_qp_factor(P, ws, mask, ws.pv + 2 * NX, rho);
+  if (ret == 3 && TM_LANE == 0) S.status[inst] = 3;
+  TM_SYNC();
+}
+
 // The QP of one SQP iteration for one instance.  Base rows = the inequality rows active in the current multipliers
 // (the reference's reduced space, sqp_method.py:338-341,417-423).  Outcomes of the base factorisation:
 //   positive definite                      -> solve; base rows that come back with a wrong-signed multiplier are released
@@ -1281,6 +1307,7 @@ TM_HD void tm_qp0_finish(const TmProb& P, const TmState& S, int64_t inst, int re
 #define TM_NONCONVEX_AFTER 3
 #endif
 TM_HD void tm_qp(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& ws) {
+  if (S.pd_check) { tm_pd_check(P, S, inst, ws); return; }
   unsigned mask[TM_ALW], next[TM_ALW];
   const int NI = P.N * P.nh;
   int use_exact = P.hessian_exact;

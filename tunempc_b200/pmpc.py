@@ -9,6 +9,7 @@ marshals pointers.  No CPU fallback: construction raises if the library or the G
 """
 from __future__ import annotations
 
+import copy
 import ctypes
 
 import numpy as np
@@ -17,7 +18,7 @@ from .lib import ModelLib, TmpcDims, _dp, _ip
 from .problem import MpcProblem, build_tables
 
 STATUS_NAMES = {0: "Solve_Succeeded", 1: "Maximum_Iterations_Exceeded", 2: "QP_Infeasible",
-                3: "Reduced_Hessian_Not_PD", 4: "NaN_Detected"}
+                3: "Reduced_Hessian_Not_PD", 4: "NaN_Detected", 5: "Working_Set_Overflow"}
 
 _LOG_KEYS = ("cpu", "iter", "f", "status", "sol_x", "lam_x", "lam_g", "u0", "nACtot", "nAC", "idx_AC", "nAS", "flags")
 
@@ -40,6 +41,7 @@ class Pmpc:
             raise NotImplementedError("ipopt_presolve is a host-side IPOPT call in the reference (pmpc.py:394-404); not available")
         if opts["slack_flag"] != "none":
             raise NotImplementedError("slack_flag != 'none' (usc slacks) is not built yet")
+        problem = copy.copy(problem)                                     # the caller's problem object is never modified
         if options and "hessian_approximation" in options:
             problem.hessian_approximation = opts["hessian_approximation"]
         if options and "max_iter" in options:
@@ -115,6 +117,7 @@ class Pmpc:
             if self.__index != 0 and self.__B != 0:
                 raise ValueError("batch size changed from %d to %d without reset()" % (self.__B, B))
             self.__B = B
+            self.__index = 0                                              # tmpc_reset zeroes the device phase index too
             self.__check(self.__lib.lib.tmpc_reset(self.__h, B))
 
     # ---- the hot path --------------------------------------------------------------------------------
