@@ -286,7 +286,7 @@ def main():
                 account()
             return u
         X = x
-        host = not hasattr(X, "device")
+        host = isinstance(X, np.ndarray)
         for _ in range(CL):
             U = ctrl.step(X, outputs="u0")
             if count:
@@ -364,7 +364,6 @@ def main():
                                     % (lin_tr.get("dram_bytes_per_task"), lin_tr.get("capture"), lin_alg_bytes_per_task),
                     "peak_source": "in-run DFMA micro-benchmark (tmpc_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                     "flops_per_stage_linearisation": f_lin, "stage_linearisations": int(n_lin),
-                    "kernel_ms": {"k_lin": lin_ms, "k_qp": qp_ms, "k_post": post_ms, "step_total": ms_dev},
                     "hbm_GBps_boundary_io": (B * K * CL * 8 * (pb.nx + pb.nu) + 0.0) / (ms_dev * 1e-3) / 1e9}
         roof_qp = {"bound": "hbm", "kernel": qp_tr.get("kernel", "k_qp_thread (+ k_qp0, k_qp)"), "achieved": qp_ach, "peak": hbm_peak, "unit": "GB/s",
                    "frac": qp_ach / hbm_peak,
@@ -372,7 +371,7 @@ def main():
                    "note": "algorithmic %.0f B per QP (records + w in, d + lam out); measured DRAM traffic %s B per QP (capture %s)"
                            % (qp_alg_bytes, qp_tr.get("dram_bytes_per_qp"), qp_tr.get("capture")),
                    "peak_source": hbm_src}
-        lin_dominant = lin_ms >= qp_ms
+        lin_dominant = lin_ms >= 0.8 * qp_ms            # the linearisation is the named kernel unless the QP clearly dominates
         line = {
             "metric": METRIC, "value": solves / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -384,6 +383,7 @@ def main():
             "e2e": {"value": solves / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * pb.nx * 8 * CL,
                     "d2h_bytes_per_step": (B * pb.nu * 8 + 3 * B * 4) * CL + (B * pb.nx * 8 * CL if CL > 1 else 0)},
             "gpu_launches": int(acc["n_launch"]),
+            "kernel_ms": {"k_lin": lin_ms, "k_qp": qp_ms, "k_post": post_ms, "step_total": ms_dev},
             "clocks": sampler.summary(),
             "roofline": roof_lin if lin_dominant else roof_qp,
             ("roofline_qp" if lin_dominant else "roofline_lin"): roof_qp if lin_dominant else roof_lin,

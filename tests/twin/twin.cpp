@@ -41,6 +41,17 @@ void twin_stage_eval(int n, const double* x, const double* u, int order, double*
   }
 }
 
+// forward / adjoint stage linearisation (tmpc_lin3.cuh): record xf | S | W for n stage points with multipliers lam (n x nx)
+int twin_lin_adjoint(int n, const double* x, const double* u, const double* lam, int order, double* rec) {
+#if TMPC_RK4
+  for (int s = 0; s < n; ++s) tm_lin_adjoint(x + (size_t)s * NX, u + (size_t)s * NU, order, lam + (size_t)s * NX, rec + (size_t)s * TM_LSZ);
+  return 0;
+#else
+  (void)n; (void)x; (void)u; (void)lam; (void)order; (void)rec;
+  return 1;
+#endif
+}
+
 // dims: N nh nxt p ; iopts: hessian_exact max_iter max_ls maxact economic ; dopts: tol lam_tresh beta reg_tol rho_rel
 int twin_step(const int* dims, const int* iopts, const double* dopts, const double* wref, const double* H,
               const double* q, const double* ref_du, const double* C, const double* c, const int* term_idx,
@@ -59,6 +70,7 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
   P.economic = iopts[4];
   P.reg_mode = iopts[5];
   P.nonconvex_after = iopts[6];
+  P.lin_adjoint = (getenv("TWIN_LIN_ADJOINT") && TMPC_RK4) ? 1 : 0;
   if (P.economic) P.hessian_exact = 1;
   P.tol = dopts[0]; P.lam_tresh = dopts[1]; P.beta = dopts[2]; P.reg_tol = dopts[3]; P.rho_rel = dopts[4];
   P.wref = wref; P.H = H; P.q = q; P.ref_du = ref_du; P.C = C; P.c = c; P.term_idx = term_idx; P.relax0 = relax0;

@@ -55,6 +55,19 @@ class Twin:
         self.lib.twin_stage_eval(n, _p(x), _p(u), order, _p(xf), _p(S), _p(T))
         return (xf, S, T)[: order + 1] if order else xf
 
+    def lin_adjoint(self, x, u, lam, order=2):
+        """record xf | S (nx x nz) | W packed of the forward / adjoint linearisation (tmpc_lin3.cuh); None for non-RK4 models"""
+        pb = self.pb
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, pb.nx)
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, pb.nu)
+        lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(-1, pb.nx)
+        n = x.shape[0]
+        lsz = pb.nx + pb.nx * pb.nz + pb.nz * (pb.nz + 1) // 2
+        rec = np.zeros((n, lsz))
+        if self.lib.twin_lin_adjoint(n, _p(x), _p(u), _p(lam), order, _p(rec)):
+            return None
+        return rec
+
     def step(self, X0, hessian=None, tol=None, shared_first_qp=False):
         pb = self.pb
         X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, pb.nx)

@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, capture E: GPU tests, bench lines of all configs, launch list + ncu --set full of the dominant kernels
+set -x
+python -m pytest tests -m gpu -x -q > gpurun_out/r02e_gputests.log 2>&1; tail -5 gpurun_out/r02e_gputests.log
+python bench.py --steps 3 --warmup 3 > gpurun_out/r02e_bench_cstr.json 2> gpurun_out/r02e_bench_cstr.err; tail -c 1200 gpurun_out/r02e_bench_cstr.json
+for c in lq evaporation unicycle; do python bench.py --config $c --steps 2 --warmup 3 --cpu-sample 4 > gpurun_out/r02e_bench_$c.json 2> gpurun_out/r02e_bench_$c.err; tail -c 900 gpurun_out/r02e_bench_$c.json; done
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r02e_launches.csv \
+    python bench.py --batch 131072 --steps 1 --warmup 3 --cpu-sample 1 > gpurun_out/r02e_launch_run.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_lin2 -s 1 -c 1 -f -o gpurun_out/r02e_lin2 \
+    python bench.py --batch 131072 --steps 1 --warmup 3 --cpu-sample 1 > gpurun_out/r02e_lin2_run.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_qp_thread -s 1 -c 1 -f -o gpurun_out/r02e_qpt1 \
+    python bench.py --batch 131072 --steps 1 --warmup 3 --cpu-sample 1 > gpurun_out/r02e_qpt1_run.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_qp_thread -s 3 -c 1 -f -o gpurun_out/r02e_qpt3 \
+    python bench.py --batch 131072 --steps 1 --warmup 3 --cpu-sample 1 > gpurun_out/r02e_qpt3_run.log 2>&1
+for f in gpurun_out/r02e_lin2 gpurun_out/r02e_qpt1 gpurun_out/r02e_qpt3; do python tools/ncu_summary.py $f.ncu-rep > $f.txt; done

@@ -57,7 +57,7 @@ struct tmpc_handle {
   int qp_thread_min = 16384;   // hybrid: launches with fewer candidate instances use the low-latency warp kernel
   bool trace = false;
   bool pd_check = true;        // run the reference's post-solve reduced-Hessian test (status 3); TMPC_PD_CHECK=0 skips it
-  int lin_mode = 2;             // 2: warp-specialised k_lin2 (RK4 models), 1: thread per (instance, stage, pair) k_lin
+  int lin_mode = 3;             // 3: forward / adjoint sweep k_lin3 (RK4 models, default), 2: warp-specialised pair-wise k_lin2, 1: thread per (instance, stage, pair) k_lin
   bool uniform_ws = false;     // warm start identical for every instance (right after tmpc_reset)
   int qp_blocks = 0;           // resident CTAs of the thread-per-instance kernel
   double* qp_ws = nullptr;     // its workspace
@@ -90,6 +90,43 @@ __global__ void __launch_bounds__(LIN_THREADS) k_lin(TmProb P, TmState S, const 
   const int64_t inst = list ? list[slot] : slot;
   tm_lin_task(P, S, inst, k, pr, trial);
 }
+
+#if TMPC_RK4
+// K1 by the forward / adjoint sweep (tmpc_lin3.cuh): one thread per (instance, stage) task, state in registers, the M stored
+// states of the forward pass in local memory
+#ifndef LIN3_THREADS
+#define LIN3_THREADS 128
+#endif
+#ifndef LIN3_MINB
+#define LIN3_MINB 1
+#endif
+template <bool EXACT>
+__global__ void __launch_bounds__(LIN3_THREADS, LIN3_MINB) k_lin3(TmProb P, TmState S, const int* list, int cnt, int trial) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)cnt * P.N) return;
+  const int k = (int)(t % P.N);
+  const int64_t slot = t / P.N;
+  const int64_t inst = list ? list[slot] : slot;
+  if (trial && S.qpstat[inst] != 0) return;          // failed QP: keep LIN at W for the final statistics
+  const double* w = S.W + inst * P.n_w + (int64_t)k * NZ;
+  double x[NX], u[NU], lam[NX];
+#pragma unroll
+  for (int a = 0; a < NX; ++a) x[a] = w[a];
+#pragma unroll
+  for (int b = 0; b < NU; ++b) u[b] = w[NX + b];
+  if (trial) {
+    const double* d = S.D + inst * P.n_w + (int64_t)k * NZ;
+#pragma unroll
+    for (int a = 0; a < NX; ++a) x[a] += d[a];
+#pragma unroll
+    for (int b = 0; b < NU; ++b) u[b] += d[NX + b];
+  }
+  const double* lamp = (trial ? S.LAMQ : S.LAM) + inst * P.n_g + tm_gdyn(P, k);
+#pragma unroll
+  for (int a = 0; a < NX; ++a) lam[a] = EXACT ? lamp[a] : 0.0;
+  tm_lin_adjoint(x, u, EXACT ? 2 : 1, lam, S.LIN + (inst * P.N + k) * (int64_t)TM_LSZ);
+}
+#endif
 
 __global__ void k_prefilter(TmProb P, TmState S) {
   const int64_t inst = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
@@ -304,6 +341,12 @@ static cudaError_t launch_lin(tmpc_handle* h, const int* list, int64_t cnt, int 
   const TmProb& P = h->P;
   const TmState& S = h->S;
 #if TMPC_RK4
+  if (h->lin_mode == 3) {
+    const unsigned grid = (unsigned)((cnt * P.N + LIN3_THREADS - 1) / LIN3_THREADS);
+    if (P.hessian_exact) k_lin3<true><<<grid, LIN3_THREADS, 0, st>>>(P, S, list, (int)cnt, trial);
+    else k_lin3<false><<<grid, LIN3_THREADS, 0, st>>>(P, S, list, (int)cnt, trial);
+    return cudaGetLastError();
+  }
   if (h->lin_mode == 2) {
     const unsigned grid = (unsigned)((cnt * P.N + 31) / 32);
     if (P.hessian_exact) k_lin2<true><<<grid, L2_THREADS, tm_lin2_smem_bytes(), st>>>(P, S, list, nullptr, (int)cnt, trial);
@@ -438,7 +481,7 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
       cudaError_t oe = (L2_THREADS <= 1024 && tm_lin2_smem_bytes() <= 227 * 1024)
                            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lin2<true>, L2_THREADS, tm_lin2_smem_bytes())
                            : cudaErrorInvalidConfiguration;
-      if (oe != cudaSuccess || nb < 1) { h->lin_mode = 1; cudaGetLastError(); }
+      if (h->lin_mode == 2 && (oe != cudaSuccess || nb < 1)) { h->lin_mode = 1; cudaGetLastError(); }
       // ... or only with the registers capped so low that the state spills (dims9, 27 warps: 1.4 KB of stack per thread, 3.3x
       // slower than the pair-per-thread kernel; chain, 13 warps: 0.4 KB, on par; the reference configs: none)
       cudaFuncAttributes fa;

@@ -102,6 +102,7 @@ struct TmProb {
   int N, nh, nxt, p, n_w, n_g;
   int hessian_exact, max_iter, max_ls, filter_cap, maxact;
   int reg_mode;           // 8: primal active-set continuation of non-convex QPs for instances past TM_NONCONVEX_AFTER iterations (default); 24: for every instance; 0: Gauss-Newton re-solve only
+  int lin_adjoint;        // 1: stage linearisation by the forward / adjoint sweep (tmpc_lin3.cuh), one task per stage
   int nonconvex_after;    // SQP iteration from which reg_mode 8 applies (default TM_NONCONVEX_AFTER)
   int economic;           // 1: stage cost = the model card's l(x,u) (economic MPC, pmpc.py:97-107), 0: tuned tracking cost (mtools.py:43-57)
   double tol, lam_tresh, beta, reg_tol, rho_rel;
@@ -656,6 +657,8 @@ TM_HD int tm_lin_tasks_per_stage(int hessian_exact) { return hessian_exact ? TMP
 TM_HD int tm_lin_tasks_per_stage(int hessian_exact) { return hessian_exact ? TM_NPAIR : TM_GN_NG; }
 #endif
 
+#include "tmpc_lin3.cuh"
+
 // one linearisation task.  trial = 1: evaluate at (W + D, LAMQ), else at (W, LAM).  g = group id.
 TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, int g, int trial) {
   const double* w = S.W + inst * P.n_w + (int64_t)k * NZ;
@@ -673,6 +676,17 @@ TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, i
     for (int b = 0; b < NU; ++b) u[b] += d[NX + b];
   }
   double* rec = S.LIN + (inst * P.N + k) * (int64_t)TM_LSZ;
+#if TMPC_RK4
+  if (P.lin_adjoint) {
+    if (g != 0) return;
+    double lamv[NX];
+    const double* lamq = (trial ? S.LAMQ : S.LAM) + inst * P.n_g + tm_gdyn(P, k);
+#pragma unroll
+    for (int a = 0; a < NX; ++a) lamv[a] = P.hessian_exact ? lamq[a] : 0.0;
+    tm_lin_adjoint(x, u, P.hessian_exact ? 2 : 1, lamv, rec);
+    return;
+  }
+#endif
 #if TMPC_COLLOCATION
   {
     double lamc[NX];
