@@ -494,12 +494,14 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
     if (tm) h->qp_thread_min = atoi(tm);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
-    int tps = 512;
+    h->qp_ws_per_inst = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact);
+    int tps = 1024;                        // resident threads per SM of the thread-per-instance kernel (its register budget: QT_MINB)
+    // the workspace is sized by the resident grid: keep it below 24 GB for models with many rows
+    while (tps > 256 && (double)prop.multiProcessorCount * tps * h->qp_ws_per_inst * sizeof(double) > 24e9) tps /= 2;
     const char* t = getenv("TMPC_QP_THREADS_PER_SM");
     if (t) tps = atoi(t);
     if (tps < 32) tps = 32;
     h->qp_blocks = prop.multiProcessorCount * (tps / tm_qp_thread_block() > 0 ? tps / tm_qp_thread_block() : 1);
-    h->qp_ws_per_inst = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact);
     if (h->qp_mode >= 1) {
       const size_t nthreads = (size_t)h->qp_blocks * tm_qp_thread_block();
       if (cudaMalloc(&h->qp_ws, nthreads * h->qp_ws_per_inst * sizeof(double)) != cudaSuccess ||

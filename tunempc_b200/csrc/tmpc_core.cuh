@@ -85,6 +85,7 @@ TM_HD TmP tm_mkp(double* base, size_t off) { TmP r; r.p = base + off * TM_WS_STR
 typedef double* TmP;
 TM_HD TmP tm_mkp(double* base, size_t off) { return base + off; }
 #endif
+typedef double* TmL;    // plain pointer in every mode (shared memory / host memory / thread-local scratch)
 
 #define NX TMPC_NX
 #define NU TMPC_NU

@@ -32,7 +32,8 @@ struct TmQpWs {
   TmP Gc, gc, ncs;                        // constraint-to-go rows (N+1)*nx*nx, offsets (N+1)*nx, row counts (N+1)
   TmP kk, d, y, rhs;                      // feed-forward of the current sweep; step, correction, right-hand side
   TmP sl, Mc, Lf, cA, rv, nu, acts, acte, sc;   // dual active set: row values, dual-Hessian columns, Schur factor, members
-  TmP Ew, F, f, PAB, pv, tr, lh, sl0;     // scratch: elimination rows, stage KKT block, vectors; terminal residual; row multipliers; row values of a held solution
+  TmP Ew, tr, lh, sl0;                    // scratch: elimination rows; terminal residual; row multipliers; row values of a held solution
+  TmL F, f, PAB, pv;                      // per-stage scratch of the factorisation: KKT block, gradient, products, vectors (thread mode: thread-local)
 };
 
 TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
@@ -48,6 +49,8 @@ TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
   return n;
 }
 
+#define TM_QP_LSCR (NZ * NZ + NZ + NX * NZ + 4 * NX)
+TM_HD void tm_qpws_local(double* l, TmQpWs& s) { s.F = l; s.f = l + NZ * NZ; s.PAB = l + NZ * NZ + NZ; s.pv = l + NZ * NZ + NZ + NX * NZ; }
 TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s) {
   const size_t NI = (size_t)N * nh + nxt + 1;
   size_t o = 0;
@@ -80,10 +83,14 @@ TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s)
   TM_CARVE(acte, M);
   TM_CARVE(sc, 8);
   TM_CARVE(Ew, (size_t)(NX + nh) * TM_ES);
+#ifndef TM_WS_STRIDE
   TM_CARVE(F, NZ * NZ);
   TM_CARVE(f, NZ);
   TM_CARVE(PAB, NX * NZ);
   TM_CARVE(pv, 4 * NX);
+#else
+  o += NZ * NZ + NZ + NX * NZ + 4 * NX;     // thread mode: the caller points F, f, PAB, pv at a thread-local array (TM_QP_LSCR doubles)
+#endif
   TM_CARVE(tr, (nxt > 0 ? nxt : 1));
   TM_CARVE(lh, NI);
   TM_CARVE(sl0, NI);
@@ -202,7 +209,7 @@ TM_HD int tm_stage_factor(const TmProb& P, TmQpWs& s, int k, int nr) {
     ku[j] = ri >= 0 ? -E[ri * TM_ES + NZ] : 0.0;
     for (int c = 0; c < nf; ++c) Zu[j * NV + c] = ri >= 0 ? -E[ri * TM_ES + NX + fl[c]] : (fl[c] == j ? 1.0 : 0.0);
   }
-  const TmP F = s.F;
+  const TmL F = s.F;
   // projected block Rt = Zu' Fuu Zu and its Cholesky factor (lower, in place)
   double Rt[(NV > 0 ? NV : 1) * (NV > 0 ? NV : 1)], FZ[(NV > 0 ? NV : 1) * (NV > 0 ? NV : 1)];
   for (int a = 0; a < NV; ++a)
@@ -281,7 +288,7 @@ TM_HD int tm_stage_factor(const TmProb& P, TmQpWs& s, int k, int nr) {
 // ---- base factorisation + main solve ----------------------------------------------------------------------------
 // amask: inequality rows (k*nh + i) held as equalities.  Fills K, Wm, Pk, pm, Gc, gc, ncs and the step s.d of the base
 // problem.  returns 0 ok, 3 not positive definite on the null space of the base rows, 6 base rows inconsistent.
-TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const TmP e0, double rho) {
+TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const double* e0, double rho) {
   const int N = P.N, nh = P.nh, nxt = P.nxt;
   const int lane = TM_LANE;
 #ifdef TM_TERM_ELIM
@@ -309,11 +316,24 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
 #endif
   TM_SYNC();
   for (int k = N - 1; k >= 0; --k) {
-    const TmP AB = s.AB + (size_t)k * NX * NZ;
+    const TmP ABw = s.AB + (size_t)k * NX * NZ;
     const TmP Qk = s.Q + (size_t)k * NZ * NZ;
-    const TmP Pn = s.Pk + (size_t)(k + 1) * NX * NX;
+    const TmP Pnw = s.Pk + (size_t)(k + 1) * NX * NX;
     const TmP Gn = s.Gc + (size_t)(k + 1) * NX * NX;
     const int ncn = (int)s.ncs[k + 1];
+#if TM_NL == 1
+    // one thread per instance: the blocks every product below re-reads are staged once (registers / thread-local memory)
+    double AB[NX * NZ], Pn[NX * NX], bk[NX];
+#pragma unroll
+    for (int e = 0; e < NX * NZ; ++e) AB[e] = ABw[e];
+#pragma unroll
+    for (int e = 0; e < NX * NX; ++e) Pn[e] = Pnw[e];
+#pragma unroll
+    for (int e = 0; e < NX; ++e) bk[e] = s.b[k * NX + e];
+#else
+    const TmP AB = ABw, Pn = Pnw;
+    const TmP bk = s.b + k * NX;
+#endif
     for (int e = lane; e < NX * NZ; e += TM_NL) {
       const int i = e / NZ, c = e % NZ;
       double v = 0.0;
@@ -324,7 +344,7 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
     for (int i = lane; i < NX; i += TM_NL) {           // vv = P b + p
       double v = s.pm[(k + 1) * NX + i];
 #pragma unroll
-      for (int l = 0; l < NX; ++l) v += Pn[i * NX + l] * s.b[k * NX + l];
+      for (int l = 0; l < NX; ++l) v += Pn[i * NX + l] * bk[l];
       s.pv[i] = v;
     }
     // candidate rows: constraint-to-go of stage k+1 through the dynamics, then the stage's own base rows
@@ -332,7 +352,7 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
       const int i = e / (NZ + 1), c = e % (NZ + 1);
       double v = (c == NZ) ? s.gc[(k + 1) * NX + i] : 0.0;
 #pragma unroll
-      for (int l = 0; l < NX; ++l) v += Gn[i * NX + l] * (c == NZ ? s.b[k * NX + l] : AB[l * NZ + c]);
+      for (int l = 0; l < NX; ++l) v += Gn[i * NX + l] * (c == NZ ? bk[l] : AB[l * NZ + c]);
       s.Ew[i * TM_ES + c] = v;
     }
     int nr = ncn;
@@ -360,7 +380,13 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
     TM_SYNC();
     if (s.sc[2] != 0.0) return (int)s.sc[2];
     // P_k = [I;K]' F [I;K] (symmetrised), p_k = ftil_x + K' ftil_u
+#if TM_NL == 1
+    double Kk[(NV > 0 ? NV : 1) * NX];
+#pragma unroll
+    for (int e = 0; e < NV * NX; ++e) Kk[e] = s.K[(size_t)k * NV * NX + e];
+#else
     const TmP Kk = s.K + (size_t)k * NV * NX;
+#endif
     for (int e = lane; e < NX * NZ; e += TM_NL) {      // X = F_x. + K' F_u.
       const int i = e / NZ, c = e % NZ;
       double v = 0.5 * (s.F[i * NZ + c] + s.F[c * NZ + i]);
@@ -639,8 +665,24 @@ TM_HD int tm_qp_gi(const TmProb& P, TmQpWs& s, const unsigned* amask, int& m_out
   const int neq = P.nxt;
 #endif
   const int E = NI + P.nxt;
-  for (int e = lane; e < E; e += TM_NL)
-    s.sl[e] = (e < NI) ? (tm_mask_get(amask, e) ? 0.0 : s.hv[e] + tm_erow_dot(P, e, s.d)) : s.tr[e - NI] + tm_erow_dot(P, e, s.d);
+  for (int k = lane; k < N; k += TM_NL) {       // row values at the base solution, one stage's step loaded once
+    double z[NZ];
+#pragma unroll
+    for (int b = 0; b < NZ; ++b) z[b] = s.d[k * NZ + b];
+    for (int i = 0; i < nh; ++i) {
+      const int e = k * nh + i;
+      double v = 0.0;
+      if (!tm_mask_get(amask, e)) {
+        const double* Ci = P.C + (size_t)i * NZ;
+        double t = 0.0;
+#pragma unroll
+        for (int b = 0; b < NZ; ++b) t += Ci[b] * z[b];
+        v = s.hv[e] + t;
+      }
+      s.sl[e] = v;
+    }
+  }
+  for (int t = lane; t < P.nxt; t += TM_NL) s.sl[NI + t] = s.tr[t] + s.d[N * NZ + P.term_idx[t]];
   TM_SYNC();
   int m = 0, ret = 0, eq_next = 0;
   const int maxit = 4 * NI + 8 + neq;
@@ -717,10 +759,24 @@ TM_HD int tm_qp_gi(const TmProb& P, TmQpWs& s, const unsigned* amask, int& m_out
       } else {
         const double t2 = -sval / zn;
         if (is_eq || t2 <= t1) { t = t2; do_add = 1; } else t = t1;
-        for (int e = lane; e < E; e += TM_NL) {
-          double acc = mq[e];
-          for (int j2 = 0; j2 < m; ++j2) acc -= s.rv[j2] * s.Mc[(size_t)j2 * E + e];
-          s.sl[e] += t * acc;
+        // row values along the step: four rows at a time (independent chains); base rows are never candidates
+        for (int e0 = lane; e0 < E; e0 += 4 * TM_NL) {
+          int ee[4];
+          double acc[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            ee[q] = e0 + q * TM_NL;
+            if (ee[q] >= E || (ee[q] < NI && tm_mask_get(amask, ee[q]))) ee[q] = -1;
+            acc[q] = ee[q] >= 0 ? mq[ee[q]] : 0.0;
+          }
+          for (int j2 = 0; j2 < m; ++j2) {
+            const double rj = s.rv[j2];
+            const TmP col = s.Mc + (size_t)j2 * E;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (ee[q] >= 0) acc[q] -= rj * col[ee[q]];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (ee[q] >= 0) s.sl[ee[q]] += t * acc[q];
         }
         sval += t * zn;
       }
@@ -967,7 +1023,7 @@ TM_HD void tm_qp_setup(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     for (int j = 0; j < NZ; ++j) v += P.C[(size_t)i * NZ + j] * w[k * NZ + j];
     s.hv[e] = v;
   }
-  TmP e0 = s.pv + 2 * NX;
+  TmL e0 = s.pv + 2 * NX;
   for (int a = lane; a < NX; a += TM_NL) e0[a] = S.X0[inst * NX + a] - w[a];
   {
     const double* xrN = P.wref + (size_t)((S.phase + N) % P.p) * NZ;
@@ -986,7 +1042,7 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   const int N = P.N, nh = P.nh, nxt = P.nxt;
   const int lane = TM_LANE;
   const int NI = N * nh;
-  TmP e0 = s.pv + 2 * NX;
+  TmL e0 = s.pv + 2 * NX;
   if (pert) {
     if (pert->homog) {
       for (int e = lane; e < (N + 1) * NZ; e += TM_NL) s.r[e] = 0.0;

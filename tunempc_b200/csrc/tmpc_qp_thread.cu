@@ -14,7 +14,10 @@
 
 #define QT_THREADS 128
 #ifndef QT_MINB
-#define QT_MINB 4          /* resident CTAs / SM the register allocation aims for (128 registers at 4) */
+#define QT_MINB 8          /* resident CTAs / SM the register allocation aims for: 64 registers, 1024 threads / SM.  The kernel
+                              waits on its workspace (DRAM latency), so resident warps matter more than spills: measured
+                              QP time per 2^20-instance step 991 / 894 / 818 / 860 / 894 ms at 4 / 6 / 8 / 12 / 16 CTAs
+                              (profiles/r02g_summary.md) */
 #endif
 
 __global__ void __launch_bounds__(QT_THREADS, QT_MINB) k_qp_thread(TmProb P, TmState S, const int* list, int cnt, const int* cnt_dev,
@@ -25,6 +28,8 @@ __global__ void __launch_bounds__(QT_THREADS, QT_MINB) k_qp_thread(TmProb P, TmS
   double* base = wsbase + gwarp * ws_per_inst * 32 + lane;
   TmQpWs ws;
   tm_qpws_carve(base, P.N, P.nh, P.nxt, P.maxact, ws);
+  double lscr[TM_QP_LSCR];                      // per-stage scratch of the factorisation: thread-local (registers / L1)
+  tm_qpws_local(lscr, ws);
   for (;;) {
     int start = 0;
     if (lane == 0) start = atomicAdd(work_counter, 32);
