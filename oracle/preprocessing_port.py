@@ -1,4 +1,5 @@
-"""Host-side restatement of `tunempc/preprocessing.py` (runs once; defines the constraint functions the device sees).
+"""TEST INFRASTRUCTURE (oracle/): sympy restatement of `tunempc/preprocessing.py`, pinned by the known answers of the reference's own
+tests (test/test_processing.py).  Nothing in the product package imports it; the device path of this round has ns = nsc = 0.
 
   input_formatting(sys)        preprocessing.py:35-76    split h(x,u) >= 0 into linear rows and slacked nonlinear equalities
   detect_nonlinear_inequalities  :78-118                 g(x,u,us) = h_nl(x,u) - us = 0,  h(x,u,us) = [h_lin(x,u); us] >= 0

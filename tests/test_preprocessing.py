@@ -5,8 +5,8 @@ import collections
 import numpy as np
 import sympy as sp
 
-from tunempc_b200 import preprocessing
-from tunempc_b200.preprocessing import SymFunction
+from oracle import preprocessing_port as preprocessing
+from oracle.preprocessing_port import SymFunction
 
 
 def _xu():

@@ -71,3 +71,36 @@ def test_tuner_create_mpc_gpu(built):
     assert (trk.status == 0).all() and np.allclose(Ut[0], t.w_sol[0, 4:], rtol=1e-8)
     with pytest.raises(ValueError):
         t.create_mpc("tuned", 20, opts={"no_such_option": 1})            # pmpc.py:94
+
+
+def test_reference_constructor_arguments():
+    """Pmpc(N, sys, cost, wref, tuning, lam_g_ref, sensitivities, options) (tunempc/pmpc.py:39): the reference's argument
+    set maps onto the same problem IR (and phase tables) as the committed fixtures; its assertions are kept."""
+    from tunempc_b200.pmpc import problem_from_reference_args
+    from tunempc_b200.problem import build_tables
+    for name in ("unicycle", "evaporation", "cstr"):
+        pb = load_problem(name)
+        card = {"f": name, "vars": {"x": list(range(pb.nx)), "u": list(range(pb.nu))}, "h": (pb.C, pb.c)}
+        wref = {"x": [pb.wref[k, :pb.nx] for k in range(pb.p)], "u": [pb.wref[k, pb.nx:] for k in range(pb.p)]}
+        lam = {"dyn": list(pb.lam_dyn_ref), "h": list(pb.lam_h_ref)}
+        sens = None if pb.S_A is None else {"A": pb.S_A, "B": pb.S_B}
+        pb2 = problem_from_reference_args(pb.N, card, "tracking", wref, {"H": list(pb.H), "q": list(pb.q)}, lam, sens,
+                                          {"p_operator": pb.term_idx})
+        for fld in ("nx", "nu", "N", "p", "term_idx", "mpc_type"):
+            assert getattr(pb2, fld) == getattr(pb, fld), fld
+        for fld in ("wref", "H", "q", "C", "c", "lam_h_ref", "lam_dyn_ref"):
+            assert np.array_equal(getattr(pb2, fld), getattr(pb, fld)), fld
+        ta, tb = build_tables(pb), build_tables(pb2)
+        assert np.array_equal(ta.ref, tb.ref) and np.array_equal(ta.ref_du, tb.ref_du)
+    pb = load_problem("cstr")
+    card = {"f": "cstr", "vars": {"x": [0] * 4, "u": [0] * 2}, "h": (pb.C, pb.c)}
+    wref = pb.wref
+    with pytest.raises(AssertionError):
+        problem_from_reference_args(20, card, "tracking", wref, None, None, None, {})       # pmpc.py:118
+    with pytest.raises(AssertionError):
+        problem_from_reference_args(20, card, "tracking", None, {"H": [pb.H[0]], "q": [pb.q[0]]}, None, None, {})   # pmpc.py:134
+    eco = problem_from_reference_args(20, card, lambda x, u: 0.0, wref, None, {"dyn": [np.ones(4)], "h": [pb.lam_h_ref[0]]}, None,
+                                      {"hessian_approximation": "gauss_newton"})
+    assert eco.mpc_type == "economic" and eco.hessian_approximation == "exact"                # pmpc.py:97-107
+    with pytest.raises(NotImplementedError):
+        problem_from_reference_args(20, dict(card, g="g"), "tracking", wref, {"H": [pb.H[0]], "q": [pb.q[0]]}, None, None, {})

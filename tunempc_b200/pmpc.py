@@ -29,8 +29,73 @@ def default_options():
             "slack_flag": "none"}
 
 
+def problem_from_reference_args(N, sys, cost, wref, tuning, lam_g_ref, sensitivities, options):
+    """The reference constructor's arguments (tunempc/pmpc.py:39-147) -> the problem IR.
+
+    sys            model card: {'f': OdeModel or compiled-model name, 'vars': {'x': .., 'u': ..}, 'h': (C, c) with
+                   h(x,u) = C z + c >= 0} -- what Tuner.sys returns (tuner.py:201-207 hands CasADi Functions here)
+    cost           'tracking' / 'economic', or a callable: two arguments l(x,u) -> economic, otherwise tracking
+                   (the reference tells them apart by cost.n_in(), pmpc.py:97-118)
+    wref           {'x': [p arrays (nx,)], 'u': [p arrays (nu,)]} or an array (p, nz)   (pmpc.py:692-706)
+    tuning         {'H': [p (nz,nz)], 'q': [p (nz,)]}; required for tracking MPC (pmpc.py:117-118), ignored for economic
+    lam_g_ref      {'dyn': [p (nx,)], 'h': [p (nh,)]}   (pmpc.py:709-720)
+    sensitivities  {'A': [p (nx,nx)], 'B': [p (nx,nu)]}: only read when the terminal constraint is projected (pmpc.py:724-767)
+    """
+    import inspect
+    f = sys["f"]
+    name = f if isinstance(f, str) else f.name
+    nx, nu = len(sys["vars"]["x"]), len(sys["vars"]["u"])
+    nz = nx + nu
+    if "us" in sys["vars"] or "usc" in sys["vars"] or "g" in sys:
+        raise NotImplementedError("slack variables us/usc and nonlinear rows g (pmpc.py:50-76) are not built")
+    if isinstance(cost, str):
+        economic = cost == "economic"
+    else:
+        economic = callable(cost) and len(inspect.signature(cost).parameters) == 2          # pmpc.py:97
+    assert wref is not None, "Provide reference trajectory!"                                 # pmpc.py:134
+    if isinstance(wref, dict):
+        w = np.array([np.concatenate([np.ravel(wref["x"][k]), np.ravel(wref["u"][k])]) for k in range(len(wref["u"]))])
+    else:
+        w = np.atleast_2d(np.asarray(wref, dtype=np.float64))
+    P = w.shape[0]
+    if economic:
+        H, q = np.zeros((P, nz, nz)), np.zeros((P, nz))                                        # pmpc.py:103: no tuning required
+    else:
+        assert tuning is not None, "Provide tuning matrices for tracking MPC!"                # pmpc.py:118
+        Hs = [np.asarray(h, dtype=np.float64) for h in tuning["H"]]
+        qs = [np.asarray(v, dtype=np.float64).ravel() for v in tuning["q"]]
+        H = np.array(Hs * P if len(Hs) == 1 and P > 1 else Hs)
+        q = np.array(qs * P if len(qs) == 1 and P > 1 else qs)
+    C, c = sys.get("h", (np.zeros((0, nz)), np.zeros(0)))
+    C, c = np.asarray(C, dtype=np.float64).reshape(-1, nz), np.asarray(c, dtype=np.float64).ravel()
+    nh = C.shape[0]
+    lam_dyn = (np.zeros((P, nx)) if lam_g_ref is None
+               else np.array([np.ravel(v) for v in lam_g_ref["dyn"]], dtype=np.float64).reshape(P, nx))
+    lam_h = (np.zeros((P, nh)) if lam_g_ref is None or "h" not in lam_g_ref
+             else np.array([np.ravel(v) for v in lam_g_ref["h"]], dtype=np.float64).reshape(P, nh))
+    term = (options or {}).get("p_operator")
+    pb = MpcProblem(name=name, nx=nx, nu=nu, N=int(N), p=P, wref=w, H=H, q=q, C=C, c=c, lam_h_ref=lam_h, lam_dyn_ref=lam_dyn,
+                    term_idx=list(range(nx)) if term is None else [int(i) for i in term],
+                    S_A=None if sensitivities is None else np.array(sensitivities["A"], dtype=np.float64),
+                    S_B=None if sensitivities is None else np.array(sensitivities["B"], dtype=np.float64),
+                    mpc_type="economic" if economic else "tuned")
+    if economic:
+        pb.hessian_approximation = "exact"                                                     # pmpc.py:105-107
+    return pb
+
+
 class Pmpc:
-    def __init__(self, problem: MpcProblem, options=None, device=0, solver_options=None):
+    def __init__(self, N=None, sys=None, cost=None, wref=None, tuning=None, lam_g_ref=None, sensitivities=None, options=None,
+                 device=0, solver_options=None, problem: MpcProblem = None):
+        """Two ways in: the reference's own signature `Pmpc(N, sys, cost, wref, tuning, lam_g_ref, sensitivities, options)`
+        (tunempc/pmpc.py:39) with `sys` a model card, or the problem IR `Pmpc(problem, options)` /
+        `Pmpc(problem=problem)` (an `MpcProblem`, e.g. loaded from a fixture).  `device`: CUDA device index."""
+        if isinstance(N, MpcProblem):                                    # Pmpc(problem[, options])
+            problem, N = N, None
+            if isinstance(sys, dict) and options is None:
+                options, sys = sys, None
+        if problem is None:
+            problem = problem_from_reference_args(N, sys, cost, wref, tuning, lam_g_ref, sensitivities, options)
         opts = default_options()
         for k, v in (options or {}).items():
             if k in opts:

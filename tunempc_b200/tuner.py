@@ -114,27 +114,19 @@ class Tuner(object):
                 raise RuntimeError("call convexify() first")
             tuning = {"H": self.__S["Hc"], "q": self.__S["q"]}                              # tuner.py:195
         from .pmpc import Pmpc
-        p = self.__p
-        if mpc_type == "economic":                                                           # tuner.py:180-182
-            nz = self.__nw
-            tuning = {"H": [np.zeros((nz, nz))] * p, "q": [np.zeros(nz)] * p}
-        Hs = [np.asarray(Hk, dtype=np.float64) for Hk in tuning["H"]]
-        qs = [np.asarray(qk, dtype=np.float64).ravel() for qk in tuning["q"]]
-        if len(Hs) == 1 and p > 1:
-            Hs = Hs * p
-        if len(qs) == 1 and p > 1:
-            qs = qs * p
         opts = dict(opts)
-        term_idx = opts.pop("p_operator", None)
-        if term_idx is None:
-            term_idx = self.__card.get("term_idx", list(range(self.__nx)))
-        pb = MpcProblem(name=self.__model.name, nx=self.__nx, nu=self.__nu, N=int(N), p=p, wref=self.__w_sol.copy(),
-                        H=np.array(Hs), q=np.array(qs), C=self.__C, c=self.__c, lam_h_ref=self.__lam_h.copy(),
-                        lam_dyn_ref=(self.__lam_dyn.copy() if mpc_type == "economic"          # tuner.py:180-182: full lam_g
-                                     else np.zeros((p, self.__nx))),                        # tuner.py:186-189: lam_g0['dyn'] = 0
-                        term_idx=[int(i) for i in term_idx], S_A=np.array(self.__S["A"]), S_B=np.array(self.__S["B"]),
-                        mpc_type="economic" if mpc_type == "economic" else "tuned")
-        return Pmpc(pb, options=opts, device=device)
+        if opts.get("p_operator") is None:
+            opts["p_operator"] = self.__card.get("term_idx", list(range(self.__nx)))
+        p = self.__p
+        wref = {"x": [self.__w_sol[k, :self.__nx] for k in range(p)], "u": [self.__w_sol[k, self.__nx:] for k in range(p)]}
+        sens = {"A": self.__S["A"], "B": self.__S["B"]}
+        if mpc_type == "economic":                                                           # tuner.py:180-182: full lam_g
+            lam_g_ref = {"dyn": list(self.__lam_dyn), "h": list(self.__lam_h)}
+            return Pmpc(N=N, sys=self.sys, cost="economic", wref=wref, lam_g_ref=lam_g_ref, sensitivities=sens,
+                        options=opts, device=device)
+        lam_g0 = {"dyn": [np.zeros(self.__nx)] * p, "h": list(self.__lam_h)}                # tuner.py:186-189: lam_g0['dyn'] = 0
+        return Pmpc(N=N, sys=self.sys, cost="tracking", wref=wref, tuning=tuning, lam_g_ref=lam_g0, sensitivities=sens,
+                    options=opts, device=device)
 
     # ---- properties (tuner.py:201-264) -------------------------------------------------------------------
     @property
