@@ -22,6 +22,11 @@
 // QP re-solved.  Exact active-set solution: inactive multipliers are exact zeros (sqp_method.py:421 relies on it).
 #pragma once
 
+#if TM_NL == 1
+#define TM_UNROLL_T _Pragma("unroll")   /* one thread per instance: element loops have constant trip counts; unrolled, the staged blocks index statically */
+#else
+#define TM_UNROLL_T
+#endif
 #define NV NU               /* free variables of a stage block (inputs; + slacks in the slack formulation) */
 #define TM_ES (NZ + 2)      /* row stride of the elimination scratch: coefficients | offset | state */
 
@@ -49,8 +54,9 @@ TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
   return n;
 }
 
-#define TM_QP_LSCR (NZ * NZ + NZ + NX * NZ + 4 * NX)
-TM_HD void tm_qpws_local(double* l, TmQpWs& s) { s.F = l; s.f = l + NZ * NZ; s.PAB = l + NZ * NZ + NZ; s.pv = l + NZ * NZ + NZ + NX * NZ; }
+#define TM_QP_LSCR (4 * NX)               /* thread mode: only pv (the x_0 offset lives in pv[2nx..3nx)) is addressed through the
+                                             workspace struct; F, f, PAB are arrays local to tm_qp_factor */
+TM_HD void tm_qpws_local(double* l, TmQpWs& s) { s.F = nullptr; s.f = nullptr; s.PAB = nullptr; s.pv = l; }
 TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s) {
   const size_t NI = (size_t)N * nh + nxt + 1;
   size_t o = 0;
@@ -107,7 +113,7 @@ TM_HD void tm_mask_clr(unsigned* m, int e) { m[e >> 5] &= ~(1u << (e & 31)); }
 //      stage's own active rows)
 // out: K, Wm, kkm of stage k; constraint-to-go (Gc, gc, ncs) of stage k; s.f <- f + F[:,u] ku
 // returns 0 ok, 3 projected block not positive definite, 6 rows inconsistent
-TM_HD int tm_stage_factor(const TmProb& P, TmQpWs& s, int k, int nr) {
+TM_HD int tm_stage_factor(const TmProb& P, TmQpWs& s, int k, int nr, double* F, double* fv) {
   const TmP E = s.Ew;
   const double tolp = 1e-9, tolc = 1e-7;
   int colrow[NV > 0 ? NV : 1];
@@ -209,7 +215,6 @@ TM_HD int tm_stage_factor(const TmProb& P, TmQpWs& s, int k, int nr) {
     ku[j] = ri >= 0 ? -E[ri * TM_ES + NZ] : 0.0;
     for (int c = 0; c < nf; ++c) Zu[j * NV + c] = ri >= 0 ? -E[ri * TM_ES + NX + fl[c]] : (fl[c] == j ? 1.0 : 0.0);
   }
-  const TmL F = s.F;
   // projected block Rt = Zu' Fuu Zu and its Cholesky factor (lower, in place)
   double Rt[(NV > 0 ? NV : 1) * (NV > 0 ? NV : 1)], FZ[(NV > 0 ? NV : 1) * (NV > 0 ? NV : 1)];
   for (int a = 0; a < NV; ++a)
@@ -273,13 +278,13 @@ TM_HD int tm_stage_factor(const TmProb& P, TmQpWs& s, int k, int nr) {
   }
   // main solve: ftil = f + F[:,u] ku ;  kk = ku - Wm ftil_u
   for (int c = 0; c < NZ; ++c) {
-    double v = s.f[c];
+    double v = fv[c];
     for (int b2 = 0; b2 < NV; ++b2) v += 0.5 * (F[c * NZ + NX + b2] + F[(NX + b2) * NZ + c]) * ku[b2];
-    s.f[c] = v;
+    fv[c] = v;
   }
   for (int a = 0; a < NV; ++a) {
     double v = ku[a];
-    for (int b2 = 0; b2 < NV; ++b2) v -= Wk[a * NV + b2] * s.f[NX + b2];
+    for (int b2 = 0; b2 < NV; ++b2) v -= Wk[a * NV + b2] * fv[NX + b2];
     s.kkm[k * NV + a] = v;
   }
   return 0;
@@ -291,16 +296,25 @@ TM_HD int tm_stage_factor(const TmProb& P, TmQpWs& s, int k, int nr) {
 TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const double* e0, double rho) {
   const int N = P.N, nh = P.nh, nxt = P.nxt;
   const int lane = TM_LANE;
+#if TM_NL == 1
+  double Fl[NZ * NZ], fl[NZ], PABl[NX * NZ], pvl[NX];     // per-stage scratch: thread-local, statically indexed once the loops are unrolled
+  double *const sF = Fl, *const sf = fl, *const sPAB = PABl, *const spv = pvl;
+#else
+  double *const sF = s.F, *const sf = s.f, *const sPAB = s.PAB, *const spv = s.pv;
+#endif
 #ifdef TM_TERM_ELIM
   // validation mode: terminal rows eliminated like base rows (exact null space; ill-conditioned when the inputs couple weakly)
+  TM_UNROLL_T
   for (int e = lane; e < NX * NX; e += TM_NL) s.Pk[(size_t)N * NX * NX + e] = 0.0;
   for (int a = lane; a < NX; a += TM_NL) s.pm[N * NX + a] = 0.0;
+  TM_UNROLL_T
   for (int e = lane; e < nxt * NX; e += TM_NL) s.Gc[(size_t)N * NX * NX + e] = (P.term_idx[e / NX] == e % NX) ? 1.0 : 0.0;
   for (int t = lane; t < nxt; t += TM_NL) s.gc[N * NX + t] = s.tr[t];
   if (lane == 0) s.ncs[N] = (double)nxt;
 #else
   // terminal rows live in the dual active set (always-active equality members of the Schur complement); the base carries
   // their augmented-Lagrangian term rho/2 |T d_N + t|^2, which vanishes -- value and gradient -- at the QP solution
+  TM_UNROLL_T
   for (int e = lane; e < NX * NX; e += TM_NL) {
     const int i = e / NX, j = e % NX;
     double v = 0.0;
@@ -334,20 +348,23 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
     const TmP AB = ABw, Pn = Pnw;
     const TmP bk = s.b + k * NX;
 #endif
+    TM_UNROLL_T
     for (int e = lane; e < NX * NZ; e += TM_NL) {
       const int i = e / NZ, c = e % NZ;
       double v = 0.0;
 #pragma unroll
       for (int l = 0; l < NX; ++l) v += Pn[i * NX + l] * AB[l * NZ + c];
-      s.PAB[e] = v;
+      sPAB[e] = v;
     }
+    TM_UNROLL_T
     for (int i = lane; i < NX; i += TM_NL) {           // vv = P b + p
       double v = s.pm[(k + 1) * NX + i];
 #pragma unroll
       for (int l = 0; l < NX; ++l) v += Pn[i * NX + l] * bk[l];
-      s.pv[i] = v;
+      spv[i] = v;
     }
     // candidate rows: constraint-to-go of stage k+1 through the dynamics, then the stage's own base rows
+    TM_UNROLL_T
     for (int e = lane; e < ncn * (NZ + 1); e += TM_NL) {
       const int i = e / (NZ + 1), c = e % (NZ + 1);
       double v = (c == NZ) ? s.gc[(k + 1) * NX + i] : 0.0;
@@ -358,25 +375,28 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
     int nr = ncn;
     for (int i = 0; i < nh; ++i) {
       if (!tm_mask_get(amask, k * nh + i)) continue;
+      TM_UNROLL_T
       for (int c = lane; c <= NZ; c += TM_NL) s.Ew[nr * TM_ES + c] = (c == NZ) ? s.hv[k * nh + i] : P.C[(size_t)i * NZ + c];
       ++nr;
     }
     TM_SYNC();
+    TM_UNROLL_T
     for (int e = lane; e < NZ * NZ; e += TM_NL) {
       const int a = e / NZ, c = e % NZ;
       double v = Qk[e];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) v += AB[i * NZ + a] * s.PAB[i * NZ + c];
-      s.F[e] = v;
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + a] * sPAB[i * NZ + c];
+      sF[e] = v;
     }
+    TM_UNROLL_T
     for (int c = lane; c < NZ; c += TM_NL) {
       double v = s.r[k * NZ + c];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) v += AB[i * NZ + c] * s.pv[i];
-      s.f[c] = v;
+      for (int i = 0; i < NX; ++i) v += AB[i * NZ + c] * spv[i];
+      sf[c] = v;
     }
     TM_SYNC();
-    if (lane == 0) s.sc[2] = (double)tm_stage_factor(P, s, k, nr);
+    if (lane == 0) s.sc[2] = (double)tm_stage_factor(P, s, k, nr, sF, sf);
     TM_SYNC();
     if (s.sc[2] != 0.0) return (int)s.sc[2];
     // P_k = [I;K]' F [I;K] (symmetrised), p_k = ftil_x + K' ftil_u
@@ -387,26 +407,29 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
 #else
     const TmP Kk = s.K + (size_t)k * NV * NX;
 #endif
+    TM_UNROLL_T
     for (int e = lane; e < NX * NZ; e += TM_NL) {      // X = F_x. + K' F_u.
       const int i = e / NZ, c = e % NZ;
-      double v = 0.5 * (s.F[i * NZ + c] + s.F[c * NZ + i]);
+      double v = 0.5 * (sF[i * NZ + c] + sF[c * NZ + i]);
 #pragma unroll
-      for (int a = 0; a < NV; ++a) v += Kk[a * NX + i] * 0.5 * (s.F[(NX + a) * NZ + c] + s.F[c * NZ + NX + a]);
-      s.PAB[e] = v;
+      for (int a = 0; a < NV; ++a) v += Kk[a * NX + i] * 0.5 * (sF[(NX + a) * NZ + c] + sF[c * NZ + NX + a]);
+      sPAB[e] = v;
     }
     TM_SYNC();
     const TmP Pc = s.Pk + (size_t)k * NX * NX;
+    TM_UNROLL_T
     for (int e = lane; e < NX * NX; e += TM_NL) {
       const int i = e / NX, j = e % NX;
-      double vij = s.PAB[i * NZ + j], vji = s.PAB[j * NZ + i];
+      double vij = sPAB[i * NZ + j], vji = sPAB[j * NZ + i];
 #pragma unroll
-      for (int a = 0; a < NV; ++a) { vij += s.PAB[i * NZ + NX + a] * Kk[a * NX + j]; vji += s.PAB[j * NZ + NX + a] * Kk[a * NX + i]; }
+      for (int a = 0; a < NV; ++a) { vij += sPAB[i * NZ + NX + a] * Kk[a * NX + j]; vji += sPAB[j * NZ + NX + a] * Kk[a * NX + i]; }
       Pc[e] = 0.5 * (vij + vji);
     }
+    TM_UNROLL_T
     for (int i = lane; i < NX; i += TM_NL) {
-      double v = s.f[i];
+      double v = sf[i];
 #pragma unroll
-      for (int a = 0; a < NV; ++a) v += Kk[a * NX + i] * s.f[NX + a];
+      for (int a = 0; a < NV; ++a) v += Kk[a * NX + i] * sf[NX + a];
       s.pm[k * NX + i] = v;
     }
     TM_SYNC();
@@ -697,12 +720,21 @@ TM_HD int tm_qp_gi(const TmProb& P, TmQpWs& s, const unsigned* amask, int& m_out
     } else {
       double best = TM_INF;
       int bid = 0x7fffffff;
+#if TM_NL == 1
+      for (int k = 0, e = 0; k < N; ++k)
+        for (int i = 0; i < nh; ++i, ++e) {
+          if ((k == 0 && P.relax0[i]) || tm_mask_get(amask, e)) continue;
+          const double v = s.sl[e] / fmax(1.0, fabs(P.c[i]));
+          if (v < best) { best = v; bid = e; }
+        }
+#else
       for (int e = lane; e < NI; e += TM_NL) {
         const int k = e / nh, i = e % nh;
         if ((k == 0 && P.relax0[i]) || tm_mask_get(amask, e)) continue;
         const double v = s.sl[e] / fmax(1.0, fabs(P.c[i]));
         if (v < best) { best = v; bid = e; }
       }
+#endif
       tm_wargmin(best, bid);
       if (!(best < -1e-10)) break;            // primal feasible: optimal
       int dup = 0;                            // a working-set row can only show up here through round-off
