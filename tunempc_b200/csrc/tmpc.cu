@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "tmpc.h"
@@ -61,6 +62,8 @@ struct tmpc_handle {
   bool uniform_ws = false;     // warm start identical for every instance (right after tmpc_reset)
   int qp_blocks = 0;           // resident CTAs of the thread-per-instance kernel
   double* qp_ws = nullptr;     // its workspace
+  double* qp_cold = nullptr;   // warp-per-instance kernels: dual-Hessian columns + Schur factor of every resident warp
+  int qp_wgrid = 0;            // resident CTAs of the warp-per-instance kernels
   size_t qp_ws_per_inst = 0;
   int* qp_counter = nullptr;
   TmQp0Tab q0{};               // tables of the shared first QP after reset (tm_qp0_*)
@@ -140,29 +143,35 @@ __global__ void k_init(TmProb P, TmState S) {
   tm_init(P, S, inst);
 }
 
-__global__ void __launch_bounds__(QP_WARPS * 32) k_qp(TmProb P, TmState S, const int* list, int cnt, const int* cnt_dev) {
+// warp per instance, resident CTAs striding over the list: the hot part of the workspace in shared memory, the dual-Hessian
+// columns and the Schur factor in this warp's slot of a small global buffer (cold)
+__global__ void __launch_bounds__(QP_WARPS * 32) k_qp(TmProb P, TmState S, const int* list, int cnt, const int* cnt_dev, double* cold) {
   extern __shared__ double smem[];
   if (cnt_dev) cnt = *cnt_dev;
-  const int wid = threadIdx.x / 32;
-  const int64_t slot = (int64_t)blockIdx.x * (blockDim.x / 32) + wid;   // 1 or QP_WARPS instances per CTA (shared-memory fit)
-  if (slot >= cnt) return;
-  const int64_t inst = list ? list[slot] : slot;
-  const size_t per = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact);
+  const int wid = threadIdx.x / 32, W = blockDim.x / 32;
+  const size_t cper = tm_qpws_cold_doubles(P.N, P.nh, P.nxt, P.maxact);
+  const size_t per = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact) - cper;
   TmQpWs ws;
-  tm_qpws_carve(smem + (size_t)wid * per, P.N, P.nh, P.nxt, P.maxact, ws);
-  tm_qp(P, S, inst, ws);
+  tm_qpws_carve(smem + (size_t)wid * per, P.N, P.nh, P.nxt, P.maxact, ws, cold + ((size_t)blockIdx.x * W + wid) * cper);
+  for (int64_t slot = (int64_t)blockIdx.x * W + wid; slot < cnt; slot += (int64_t)gridDim.x * W) {   // 1 or QP_WARPS instances per CTA
+    const int64_t inst = list ? list[slot] : slot;
+    tm_qp(P, S, inst, ws);
+    __syncwarp();
+  }
 }
 
 // ---- first QP after reset(): tabulate the shared parametric QP, then one thread per instance on the tables ----------
-__global__ void __launch_bounds__(QP_WARPS * 32) k_qp0_build(TmProb P, TmState S, TmQp0Tab T) {
+__global__ void __launch_bounds__(QP_WARPS * 32) k_qp0_build(TmProb P, TmState S, TmQp0Tab T, double* cold) {
   extern __shared__ double smem[];
-  const int wid = threadIdx.x / 32;
-  const int t = blockIdx.x * (blockDim.x / 32) + wid;
-  if (t >= T.nT) return;
-  const size_t per = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact);
+  const int wid = threadIdx.x / 32, W = blockDim.x / 32;
+  const size_t cper = tm_qpws_cold_doubles(P.N, P.nh, P.nxt, P.maxact);
+  const size_t per = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact) - cper;
   TmQpWs ws;
-  tm_qpws_carve(smem + (size_t)wid * per, P.N, P.nh, P.nxt, P.maxact, ws);
-  tm_qp0_build_row(P, S, 0, ws, T, t);
+  tm_qpws_carve(smem + (size_t)wid * per, P.N, P.nh, P.nxt, P.maxact, ws, cold + ((size_t)blockIdx.x * W + wid) * cper);
+  for (int t = blockIdx.x * W + wid; t < T.nT; t += gridDim.x * W) {
+    tm_qp0_build_row(P, S, 0, ws, T, t);
+    __syncwarp();
+  }
 }
 
 __global__ void k_qp0_derive(TmProb P, TmState S, TmQp0Tab T) {
@@ -449,13 +458,22 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
   {
     // warp-per-instance QP kernels keep the workspace of their instances in shared memory: 2 per CTA if that fits, else
     // 1, else those kernels are not used at all (thread-per-instance kernel for every launch, no shared first QP)
-    const size_t per = tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact) * sizeof(double);
+    const size_t cold = tm_qpws_cold_doubles(P.N, P.nh, P.nxt, P.maxact);
+    const size_t per = (tm_qpws_doubles(P.N, P.nh, P.nxt, P.maxact) - cold) * sizeof(double);
     h->qp_warps = (QP_WARPS * per <= 227 * 1024) ? QP_WARPS : (per <= 227 * 1024 ? 1 : 0);
     h->qp_smem = (size_t)h->qp_warps * per;
     if (h->qp_warps > 0 &&
         cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem) != cudaSuccess) {
       cudaGetLastError();
       h->qp_warps = 0;
+    }
+    if (h->qp_warps > 0) {
+      // resident CTAs of the warp kernels (they stride over their list): every resident warp owns one slot of the cold buffer
+      int nb = 0, nsm = 148;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_qp, h->qp_warps * 32, h->qp_smem) != cudaSuccess || nb < 1) { nb = 1; cudaGetLastError(); }
+      h->qp_wgrid = nsm * nb;
+      if (cudaMalloc(&h->qp_cold, (size_t)h->qp_wgrid * h->qp_warps * cold * sizeof(double)) != cudaSuccess) { cudaGetLastError(); h->qp_warps = 0; }
     }
     if (h->qp_warps == 0) h->qp_mode = 1;
   }
@@ -545,6 +563,7 @@ void tmpc_destroy(tmpc_handle* h) {
   free_list(h->ws_allocs);
   if (h->qp_ws) cudaFree(h->qp_ws);
   if (h->qp_counter) cudaFree(h->qp_counter);
+  if (h->qp_cold) cudaFree(h->qp_cold);
   if (h->q0.TAB) cudaFree(h->q0.TAB);
   if (h->q0.SL0) cudaFree(h->q0.SL0);
   if (h->q0.SLPHI) cudaFree(h->q0.SLPHI);
@@ -738,7 +757,7 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
         // every instance shares (w0, lam0): tabulate the parametric QP once, then one thread per instance on the tables
         const TmQp0Tab& T = h->q0;
         CK(cudaMemsetAsync(T.bad, 0, sizeof(int), st));
-        k_qp0_build<<<(T.nT + h->qp_warps - 1) / h->qp_warps, h->qp_warps * 32, h->qp_smem, st>>>(P, S, T);
+        k_qp0_build<<<std::min((T.nT + h->qp_warps - 1) / h->qp_warps, h->qp_wgrid), h->qp_warps * 32, h->qp_smem, st>>>(P, S, T, h->qp_cold);
         k_qp0_derive<<<(T.nT * T.EI + 127) / 128, 128, 0, st>>>(P, S, T);
         k_qp0<<<(unsigned)((B + Q0_THREADS - 1) / Q0_THREADS), Q0_THREADS, 0, st>>>(P, S, T, (int)B);
         launches += 2;
@@ -748,7 +767,7 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
       } else if (use_thread)
         CK(tm_launch_qp_thread(P, S, plist, (int)nact, pcnt, h->qp_ws, h->qp_ws_per_inst, h->qp_blocks, h->qp_counter, st));
       else
-        k_qp<<<(unsigned)((nact + h->qp_warps - 1) / h->qp_warps), h->qp_warps * 32, h->qp_smem, st>>>(P, S, plist, (int)nact, pcnt);
+        k_qp<<<(unsigned)std::min<int64_t>((nact + h->qp_warps - 1) / h->qp_warps, h->qp_wgrid), h->qp_warps * 32, h->qp_smem, st>>>(P, S, plist, (int)nact, pcnt, h->qp_cold);
       ++launches;
       if (pass == 0 && !q0) break;
     }
@@ -794,7 +813,7 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
     if (use_thread)
       CK(tm_launch_qp_thread(P, Sc, nullptr, (int)B, nullptr, h->qp_ws, h->qp_ws_per_inst, h->qp_blocks, h->qp_counter, st));
     else
-      k_qp<<<(unsigned)((B + h->qp_warps - 1) / h->qp_warps), h->qp_warps * 32, h->qp_smem, st>>>(P, Sc, nullptr, (int)B, nullptr);
+      k_qp<<<(unsigned)std::min<int64_t>((B + h->qp_warps - 1) / h->qp_warps, h->qp_wgrid), h->qp_warps * 32, h->qp_smem, st>>>(P, Sc, nullptr, (int)B, nullptr, h->qp_cold);
     CK(cudaGetLastError());
     ++launches;
   }

@@ -41,6 +41,12 @@ struct TmQpWs {
   TmL F, f, PAB, pv;                      // per-stage scratch of the factorisation: KKT block, gradient, products, vectors (thread mode: thread-local)
 };
 
+// the two large, rarely swept arrays of the dual active set (dual-Hessian columns Mc, Schur factor Lf): the warp-per-instance
+// kernels keep them in global memory (L2-resident: only the resident CTAs own a slot) so that several instances fit one SM
+TM_HD size_t tm_qpws_cold_doubles(int N, int nh, int nxt, int M) {
+  const size_t NI = (size_t)N * nh + nxt + 1;
+  return (size_t)(M + 1) * NI + (size_t)M * M;
+}
 TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
   const size_t NI = (size_t)N * nh + nxt + 1;        // row universe of the dual active set: inequality rows, then terminal rows
   size_t n = 0;
@@ -57,7 +63,7 @@ TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
 #define TM_QP_LSCR (4 * NX)               /* thread mode: only pv (the x_0 offset lives in pv[2nx..3nx)) is addressed through the
                                              workspace struct; F, f, PAB are arrays local to tm_qp_factor */
 TM_HD void tm_qpws_local(double* l, TmQpWs& s) { s.F = nullptr; s.f = nullptr; s.PAB = nullptr; s.pv = l; }
-TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s) {
+TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s, double* cold = nullptr) {
   const size_t NI = (size_t)N * nh + nxt + 1;
   size_t o = 0;
 #define TM_CARVE(member, n) s.member = tm_mkp(base, o); o += (size_t)(n)
@@ -80,8 +86,13 @@ TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s)
   TM_CARVE(y, (size_t)(N + 1) * NZ);
   TM_CARVE(rhs, (size_t)(N + 1) * NZ);
   TM_CARVE(sl, NI);
-  TM_CARVE(Mc, (size_t)(M + 1) * NI);
-  TM_CARVE(Lf, (size_t)M * M);
+  if (cold) {                                 // Mc, Lf outside the (shared-memory) block: base then spans tm_qpws_doubles - tm_qpws_cold_doubles
+    s.Mc = tm_mkp(cold, 0);
+    s.Lf = tm_mkp(cold, (size_t)(M + 1) * NI);
+  } else {
+    TM_CARVE(Mc, (size_t)(M + 1) * NI);
+    TM_CARVE(Lf, (size_t)M * M);
+  }
   TM_CARVE(cA, M);
   TM_CARVE(rv, M);
   TM_CARVE(nu, M);
