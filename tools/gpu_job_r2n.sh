@@ -1,0 +1,14 @@
+#!/bin/bash
+# round 2, capture N: lane <-> stage Riccati sweeps in the warp-per-instance QP kernel
+set -x
+python -m pytest tests -m gpu -x -q > gpurun_out/r02n_gputests.log 2>&1; tail -3 gpurun_out/r02n_gputests.log
+for b in 4096 32768 131072; do
+python bench.py --batch $b --steps 4 --warmup 3 --cpu-sample 1 > gpurun_out/r02n_bench_b$b.json 2> gpurun_out/r02n_err.log
+python - <<PY
+import json
+d = json.loads([l for l in open("gpurun_out/r02n_bench_b$b.json").read().splitlines() if l.startswith("{")][-1])
+print("B=$b", "%.0f solves/s" % d["value"], "%.2f ms" % d["ms_per_step"], d["kernel_ms"], d["stats"]["status_hist"][:3])
+PY
+done
+cp tunempc_b200/libtmpc_cstr.so /tmp/keep.so; cp variants/libtmpc_cstr_prof.so tunempc_b200/libtmpc_cstr.so
+TMPC_QP0_MIN=-1 TMPC_TRACE=1 python bench.py --batch 2048 --steps 1 --warmup 3 --cpu-sample 1 2>&1 >/dev/null | grep "cycles per" | tail -1

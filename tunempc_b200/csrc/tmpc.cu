@@ -850,6 +850,8 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
     fprintf(stderr, "[tmpc] qp attempts %llu gi %llu ricc %llu | fresh ok/inf/npd/mask %llu %llu %llu %llu | retry %llu %llu %llu %llu | gn %llu %llu %llu %llu\n",
             cnt_host[5], cnt_host[6], cnt_host[7], cnt_host[8], cnt_host[9], cnt_host[10], cnt_host[11], cnt_host[12],
             cnt_host[13], cnt_host[14], cnt_host[15], cnt_host[16], cnt_host[17], cnt_host[18], cnt_host[19]);
+    if (cnt_host[20]) fprintf(stderr, "[tmpc] warp-kernel cycles per attempt: factor %.0f  dual active set %.0f  correction solve %.0f  multiplier recovery %.0f\n",
+                              (double)cnt_host[20] / cnt_host[5], (double)cnt_host[21] / cnt_host[5], (double)cnt_host[22] / cnt_host[5], (double)cnt_host[23] / cnt_host[5]);
   }
   return 0;
 }

@@ -28,6 +28,7 @@
 #define TM_UNROLL_T
 #endif
 #define NV NU               /* free variables of a stage block (inputs; + slacks in the slack formulation) */
+#define TM_LFI(i, l) ((i) * ((i) + 1) / 2 + (l))   /* packed lower triangle of the Schur factor, l <= i */
 #define TM_ES (NZ + 2)      /* row stride of the elimination scratch: coefficients | offset | state */
 
 struct TmQpWs {
@@ -41,11 +42,11 @@ struct TmQpWs {
   TmL F, f, PAB, pv;                      // per-stage scratch of the factorisation: KKT block, gradient, products, vectors (thread mode: thread-local)
 };
 
-// the two large, rarely swept arrays of the dual active set (dual-Hessian columns Mc, Schur factor Lf): the warp-per-instance
-// kernels keep them in global memory (L2-resident: only the resident CTAs own a slot) so that several instances fit one SM
+// the large array of the dual active set (dual-Hessian columns Mc, swept with independent loads): the warp-per-instance
+// kernels keep it in global memory (L2-resident: only the resident CTAs own a slot) so that several instances fit one SM
 TM_HD size_t tm_qpws_cold_doubles(int N, int nh, int nxt, int M) {
   const size_t NI = (size_t)N * nh + nxt + 1;
-  return (size_t)(M + 1) * NI + (size_t)M * M;
+  return (size_t)(M + 1) * NI;
 }
 TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
   const size_t NI = (size_t)N * nh + nxt + 1;        // row universe of the dual active set: inequality rows, then terminal rows
@@ -55,7 +56,7 @@ TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
   n += (size_t)(N + 1) * NX * NX + 2 * (size_t)(N + 1) * NX;                                           // Pk pm py
   n += (size_t)(N + 1) * NX * NX + (size_t)(N + 1) * NX + (size_t)(N + 1);                             // Gc gc ncs
   n += (size_t)N * NV + 3 * (size_t)(N + 1) * NZ;                                                      // kk d y rhs
-  n += NI + (size_t)(M + 1) * NI + (size_t)M * M + 5 * (size_t)M + 8;                                  // sl Mc Lf cA rv nu acts acte sc
+  n += NI + (size_t)(M + 1) * NI + (size_t)M * (M + 1) / 2 + 5 * (size_t)M + 8;                                  // sl Mc Lf cA rv nu acts acte sc
   n += (size_t)(NX + nh) * TM_ES + NZ * NZ + NZ + NX * NZ + 4 * NX + (nxt > 0 ? nxt : 1) + 2 * NI;     // Ew F f PAB pv tr lh sl0
   return n;
 }
@@ -86,13 +87,9 @@ TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s,
   TM_CARVE(y, (size_t)(N + 1) * NZ);
   TM_CARVE(rhs, (size_t)(N + 1) * NZ);
   TM_CARVE(sl, NI);
-  if (cold) {                                 // Mc, Lf outside the (shared-memory) block: base then spans tm_qpws_doubles - tm_qpws_cold_doubles
-    s.Mc = tm_mkp(cold, 0);
-    s.Lf = tm_mkp(cold, (size_t)(M + 1) * NI);
-  } else {
-    TM_CARVE(Mc, (size_t)(M + 1) * NI);
-    TM_CARVE(Lf, (size_t)M * M);
-  }
+  if (cold) s.Mc = tm_mkp(cold, 0);           // Mc outside the (shared-memory) block: base then spans tm_qpws_doubles - tm_qpws_cold_doubles
+  else { TM_CARVE(Mc, (size_t)(M + 1) * NI); }
+  TM_CARVE(Lf, (size_t)M * (M + 1) / 2);
   TM_CARVE(cA, M);
   TM_CARVE(rv, M);
   TM_CARVE(nu, M);
@@ -301,6 +298,74 @@ TM_HD int tm_stage_factor(const TmProb& P, TmQpWs& s, int k, int nr, double* F, 
   return 0;
 }
 
+#if TM_NL > 1
+// ---- lane <-> stage sweeps (warp per instance, N <= 32) -----------------------------------------------------------
+// The Riccati sweeps are chains over the stages with a handful of small mat-vecs per link.  Every lane keeps the blocks of
+// "its" stage (A, B, K, W) in registers and the NX-vector travels from lane to lane by shuffle, so a sweep costs N links of
+// register arithmetic instead of N rounds of shared-memory traffic and warp barriers.  Each scalar is computed by the same
+// sequence of operations as in the sequential form below (one thread per instance, host twin): results are bitwise equal.
+__device__ __forceinline__ double tm_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+struct TmLaneStage { double AB[NX * NZ], K[(NV > 0 ? NV : 1) * NX], W[(NV > 0 ? NV : 1) * (NV > 0 ? NV : 1)]; };
+__device__ __forceinline__ void tm_lane_stage_load(const TmQpWs& s, int k, bool mine, TmLaneStage& L) {
+#pragma unroll
+  for (int e = 0; e < NX * NZ; ++e) L.AB[e] = mine ? s.AB[(size_t)k * NX * NZ + e] : 0.0;
+#pragma unroll
+  for (int e = 0; e < NV * NX; ++e) L.K[e] = mine ? s.K[(size_t)k * NV * NX + e] : 0.0;
+#pragma unroll
+  for (int e = 0; e < NV * NV; ++e) L.W[e] = mine ? s.Wm[(size_t)k * NV * NV + e] : 0.0;
+}
+
+// forward link: du = kk + K dx;  xo = [bk +] A dx + B du
+__device__ __forceinline__ void tm_lane_fwd(const TmLaneStage& L, const double* kk, const double* dx, const double* bk, double* du, double* xo) {
+#pragma unroll
+  for (int a = 0; a < NV; ++a) {
+    double v = kk[a];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) v += L.K[a * NX + j] * dx[j];
+    du[a] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    double v = bk ? bk[i] : 0.0;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) v += L.AB[i * NZ + j] * dx[j];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) v += L.AB[i * NZ + NX + a] * du[a];
+    xo[i] = v;
+  }
+}
+
+// backward link: fu = ru + B'p;  pn = rx + A'p + K'fu;  kk = -W fu
+__device__ __forceinline__ void tm_lane_bwd(const TmLaneStage& L, const double* rk, const double* pin, double* pn, double* kk) {
+  double fu[NV > 0 ? NV : 1];
+#pragma unroll
+  for (int a = 0; a < NV; ++a) {
+    double v = rk[NX + a];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) v += L.AB[i * NZ + NX + a] * pin[i];
+    fu[a] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < NX; ++j) {
+    double v = rk[j];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) v += L.AB[i * NZ + j] * pin[i];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) v += L.K[a * NX + j] * fu[a];
+    pn[j] = v;
+  }
+#pragma unroll
+  for (int a = 0; a < NV; ++a) {
+    double v = 0.0;
+#pragma unroll
+    for (int b2 = 0; b2 < NV; ++b2) v -= L.W[a * NV + b2] * fu[b2];
+    kk[a] = v;
+  }
+}
+
+#endif  // TM_NL > 1 (lane <-> stage helpers)
+
 // ---- base factorisation + main solve ----------------------------------------------------------------------------
 // amask: inequality rows (k*nh + i) held as equalities.  Fills K, Wm, Pk, pm, Gc, gc, ncs and the step s.d of the base
 // problem.  returns 0 ok, 3 not positive definite on the null space of the base rows, 6 base rows inconsistent.
@@ -458,6 +523,36 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
     if (bad) return 6;
   }
   // forward sweep of the main solve
+#if TM_NL > 1
+  if (N <= TM_NL) {                                    // lane <-> stage (tm_lane_fwd): same operations per scalar as the loop below
+    const bool mine = lane < N;
+    TmLaneStage L;
+    tm_lane_stage_load(s, lane, mine, L);
+    double dx[NX], du[NV > 0 ? NV : 1], xo[NX], kz[NV > 0 ? NV : 1], bk[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { dx[i] = (lane == 0) ? e0[i] : 0.0; xo[i] = 0.0; bk[i] = mine ? s.b[lane * NX + i] : 0.0; }
+#pragma unroll
+    for (int a = 0; a < NV; ++a) { kz[a] = mine ? s.kkm[lane * NV + a] : 0.0; du[a] = 0.0; }
+    for (int step = 0; step < N; ++step) {
+      if (lane == step) tm_lane_fwd(L, kz, dx, bk, du, xo);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { const double t = tm_shfl(xo[i], step); if (lane == step + 1) dx[i] = t; }
+    }
+    if (mine) {
+#pragma unroll
+      for (int j = 0; j < NX; ++j) s.d[lane * NZ + j] = dx[j];
+#pragma unroll
+      for (int a = 0; a < NV; ++a) s.d[lane * NZ + NX + a] = du[a];
+      if (lane == N - 1) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) s.d[N * NZ + i] = xo[i];
+      }
+    }
+    for (int a = lane; a < NV; a += TM_NL) s.d[N * NZ + NX + a] = 0.0;
+    TM_SYNC();
+    return 0;
+  }
+#endif
   for (int a = lane; a < NX; a += TM_NL) s.d[a] = e0[a];
   TM_SYNC();
   for (int k = 0; k < N; ++k) {
@@ -488,11 +583,126 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
   return 0;
 }
 
+#if TM_NL > 1
+__device__ __forceinline__ void tm_ricc_solve_lanes(const TmProb& P, TmQpWs& s, TmP rhs, TmP out, int kfrom) {
+  const int N = P.N, lane = TM_LANE;
+  const int kb = (kfrom >= N) ? N - 1 : kfrom;
+  const bool mine = lane < N;
+  TmLaneStage L;
+  tm_lane_stage_load(s, lane, mine, L);
+  double rk[NZ], pin[NX], pn[NX], kk[NV > 0 ? NV : 1];
+#pragma unroll
+  for (int c = 0; c < NZ; ++c) rk[c] = mine ? rhs[lane * NZ + c] : 0.0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) { pin[i] = (lane == kb && kfrom >= N) ? rhs[N * NZ + i] : 0.0; pn[i] = 0.0; }
+#pragma unroll
+  for (int a = 0; a < NV; ++a) kk[a] = 0.0;
+  for (int step = kb; step >= 0; --step) {
+    if (lane == step) tm_lane_bwd(L, rk, pin, pn, kk);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) { const double t = tm_shfl(pn[j], step); if (lane == step - 1) pin[j] = t; }
+  }
+  // cost-to-go gradients of this solve (multiplier recovery): py_k = pn of lane k <= kb, the terminal right-hand side at N, else 0
+  if (mine) {
+#pragma unroll
+    for (int j = 0; j < NX; ++j) s.py[lane * NX + j] = (lane <= kb) ? pn[j] : 0.0;
+  }
+  for (int a = lane; a < NX; a += TM_NL) s.py[N * NX + a] = (kfrom >= N) ? rhs[N * NZ + a] : 0.0;
+  double dx[NX], du[NV > 0 ? NV : 1], xo[NX], kz[NV > 0 ? NV : 1];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) { dx[i] = 0.0; xo[i] = 0.0; }
+#pragma unroll
+  for (int a = 0; a < NV; ++a) { kz[a] = (lane <= kb) ? kk[a] : 0.0; du[a] = 0.0; }
+  for (int step = 0; step < N; ++step) {
+    if (lane == step) tm_lane_fwd(L, kz, dx, nullptr, du, xo);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { const double t = tm_shfl(xo[i], step); if (lane == step + 1) dx[i] = t; }
+  }
+  if (mine) {
+#pragma unroll
+    for (int j = 0; j < NX; ++j) out[lane * NZ + j] = dx[j];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) out[lane * NZ + NX + a] = du[a];
+    if (lane == N - 1) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) out[N * NZ + i] = xo[i];
+    }
+  }
+  for (int a = lane; a < NV; a += TM_NL) out[N * NZ + NX + a] = 0.0;
+  TM_SYNC();
+}
+
+__device__ __forceinline__ void tm_ricc_col_lanes(const TmProb& P, TmQpWs& s, int qe, TmP mq) {
+  const int N = P.N, nh = P.nh, NI = N * nh, lane = TM_LANE;
+  const bool mine = lane < N;
+  TmLaneStage L;
+  tm_lane_stage_load(s, lane, mine, L);
+  double rk[NZ], pin[NX], pn[NX], kk[NV > 0 ? NV : 1];
+#pragma unroll
+  for (int c = 0; c < NZ; ++c) rk[c] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) { pin[i] = 0.0; pn[i] = 0.0; }
+#pragma unroll
+  for (int a = 0; a < NV; ++a) kk[a] = 0.0;
+  int kb;
+  if (qe >= NI) {
+    const int ti = P.term_idx[qe - NI];
+    kb = N - 1;
+#pragma unroll
+    for (int a = 0; a < NX; ++a) if (a == ti && lane == kb) pin[a] = -1.0;
+  } else {
+    kb = qe / nh;
+    const double* Ci = P.C + (size_t)(qe % nh) * NZ;
+#pragma unroll
+    for (int b = 0; b < NZ; ++b) if (lane == kb) rk[b] = -Ci[b];
+  }
+  for (int step = kb; step >= 0; --step) {
+    if (lane == step) tm_lane_bwd(L, rk, pin, pn, kk);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) { const double t = tm_shfl(pn[j], step); if (lane == step - 1) pin[j] = t; }
+  }
+  double z[NZ], xo[NX], kz[NV > 0 ? NV : 1];
+#pragma unroll
+  for (int b = 0; b < NZ; ++b) z[b] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) xo[i] = 0.0;
+#pragma unroll
+  for (int a = 0; a < NV; ++a) kz[a] = (lane <= kb) ? kk[a] : 0.0;
+  for (int step = 0; step < N; ++step) {
+    if (lane == step) tm_lane_fwd(L, kz, z, nullptr, z + NX, xo);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { const double t = tm_shfl(xo[i], step); if (lane == step + 1) z[i] = t; }
+  }
+  // row values of every stage, all lanes at once
+  if (mine) {
+    for (int i = 0; i < nh; ++i) {
+      const double* Ci = P.C + (size_t)i * NZ;
+      double t = 0.0;
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) t += Ci[b] * z[b];
+      mq[lane * nh + i] = t;
+    }
+  }
+  for (int t = 0; t < P.nxt; ++t) {
+    const int ti = P.term_idx[t];
+    double v = 0.0;
+#pragma unroll
+    for (int a = 0; a < NX; ++a) if (a == ti) v = xo[a];
+    v = tm_shfl(v, N - 1);
+    if (lane == 0) mq[NI + t] = v;
+  }
+  TM_SYNC();
+}
+#endif  // TM_NL > 1
+
 // homogeneous base solve:  out = argmin 1/2 d'Hd + rhs'd  over the null space of the base rows ( = -G rhs ).
 // kfrom: last stage with a non-zero right-hand side.  The cost-to-go gradients go to s.py (multiplier recovery).
 TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, TmP rhs, TmP out, int kfrom) {
   const int N = P.N;
   const int lane = TM_LANE;
+#if TM_NL > 1
+  if (N <= TM_NL) { tm_ricc_solve_lanes(P, s, rhs, out, kfrom); return; }
+#endif
   const int kb = (kfrom >= N) ? N - 1 : kfrom;
   for (int e = lane; e < (N + 1) * NX; e += TM_NL) s.py[e] = (kfrom >= N && e >= N * NX) ? rhs[N * NZ + (e - N * NX)] : 0.0;
   TM_SYNC();
@@ -565,6 +775,9 @@ TM_HD void tm_ricc_solve(const TmProb& P, TmQpWs& s, TmP rhs, TmP out, int kfrom
 TM_HD void tm_ricc_col(const TmProb& P, TmQpWs& s, int qe, TmP mq) {
   const int N = P.N, nh = P.nh, NI = N * nh;
   const int lane = TM_LANE;
+#if TM_NL > 1
+  if (N <= TM_NL) { tm_ricc_col_lanes(P, s, qe, mq); return; }
+#endif
   double pv[NX], rz[NZ];
 #pragma unroll
   for (int a = 0; a < NX; ++a) pv[a] = 0.0;
@@ -668,17 +881,17 @@ TM_HD double tm_erow_dot(const TmProb& P, int e, TmP v) {       // n_e' v: e < N
 // rebuild the Cholesky factor Lf of S_ij = Mc[j][acte_i] (i, j < m) after a deletion (single lane)
 TM_HD int tm_schur_refactor(TmQpWs& s, int m, int M, int E) {
   for (int i = 0; i < m; ++i)
-    for (int j = 0; j <= i; ++j) s.Lf[i * M + j] = s.Mc[(size_t)j * E + (int)s.acte[i]];
+    for (int j = 0; j <= i; ++j) s.Lf[TM_LFI(i, j)] = s.Mc[(size_t)j * E + (int)s.acte[i]];
   for (int c = 0; c < m; ++c) {
-    double dg = s.Lf[c * M + c];
-    for (int l = 0; l < c; ++l) dg -= s.Lf[c * M + l] * s.Lf[c * M + l];
+    double dg = s.Lf[TM_LFI(c, c)];
+    for (int l = 0; l < c; ++l) dg -= s.Lf[TM_LFI(c, l)] * s.Lf[TM_LFI(c, l)];
     if (!(dg > 0.0)) return 0;
     const double ld = sqrt(dg);
-    s.Lf[c * M + c] = ld;
+    s.Lf[TM_LFI(c, c)] = ld;
     for (int i = c + 1; i < m; ++i) {
-      double v = s.Lf[i * M + c];
-      for (int l = 0; l < c; ++l) v -= s.Lf[i * M + l] * s.Lf[c * M + l];
-      s.Lf[i * M + c] = v / ld;
+      double v = s.Lf[TM_LFI(i, c)];
+      for (int l = 0; l < c; ++l) v -= s.Lf[TM_LFI(i, l)] * s.Lf[TM_LFI(c, l)];
+      s.Lf[TM_LFI(i, c)] = v / ld;
     }
   }
   return 1;
@@ -767,15 +980,15 @@ TM_HD int tm_qp_gi(const TmProb& P, TmQpWs& s, const unsigned* amask, int& m_out
         double ll = 0.0;
         for (int i = 0; i < m; ++i) {
           double v = mq[(int)s.acte[i]];
-          for (int l = 0; l < i; ++l) v -= s.Lf[i * M + l] * s.cA[l];
-          v /= s.Lf[i * M + i];
+          for (int l = 0; l < i; ++l) v -= s.Lf[TM_LFI(i, l)] * s.cA[l];
+          v /= s.Lf[TM_LFI(i, i)];
           s.cA[i] = v;
           ll += v * v;
         }
         for (int i = m - 1; i >= 0; --i) {
           double v = s.cA[i];
-          for (int l = i + 1; l < m; ++l) v -= s.Lf[l * M + i] * s.rv[l];
-          s.rv[i] = v / s.Lf[i * M + i];
+          for (int l = i + 1; l < m; ++l) v -= s.Lf[TM_LFI(l, i)] * s.rv[l];
+          s.rv[i] = v / s.Lf[TM_LFI(i, i)];
         }
         s.sc[0] = ll;
       }
@@ -829,8 +1042,8 @@ TM_HD int tm_qp_gi(const TmProb& P, TmQpWs& s, const unsigned* amask, int& m_out
       TM_SYNC();
       if (do_add) {
         if (lane == 0) {
-          for (int l = 0; l < m; ++l) s.Lf[m * M + l] = s.cA[l];
-          s.Lf[m * M + m] = sqrt(zn);
+          for (int l = 0; l < m; ++l) s.Lf[TM_LFI(m, l)] = s.cA[l];
+          s.Lf[TM_LFI(m, m)] = sqrt(zn);
           s.acte[m] = (double)qe; s.nu[m] = nq;
         }
         TM_SYNC();
@@ -1108,7 +1321,13 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     for (int e = lane; e < N * NZ; e += TM_NL) { const int k = e / NZ, i = e % NZ; qmax = fmax(qmax, fabs(s.Q[(size_t)k * NZ * NZ + i * NZ + i])); }
     rho = rho_scale * P.rho_rel * fmax(tm_wmax(qmax), 1e-300);
   }
+#if defined(TM_PROF_W) && defined(__CUDA_ARCH__)
+  long long tp0 = clock64();
+#endif
   int ret = tm_qp_factor(P, s, amask, e0, rho);
+#if defined(TM_PROF_W) && defined(__CUDA_ARCH__)
+  long long tp1 = clock64();
+#endif
   int m = 0, n_gi = 0, n_ricc = 1;
   if (!ret && (NI > 0 || nxt > 0)) {
     if (pert || eq_only) {                        // tabulation / parametric line (tm_qp): equality rows only
@@ -1119,6 +1338,9 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
       ret = tm_qp_gi(P, s, amask, m, n_gi, n_ricc);
     }
   }
+#if defined(TM_PROF_W) && defined(__CUDA_ARCH__)
+  long long tp2 = clock64();
+#endif
   n_gi_out = n_gi;
   if (!ret) {
     // gradient including the dual active-set rows (kept in s.rhs for the multiplier recovery), correction solve
@@ -1155,6 +1377,10 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     S.counters[5] += 1; S.counters[6] += n_gi; S.counters[7] += n_ricc;
 #endif
   }
+#if defined(TM_PROF_W) && defined(__CUDA_ARCH__)
+  long long tp3 = clock64();
+  if (lane == 0 && !pert) { atomicAdd(S.counters + 20, (unsigned long long)(tp1 - tp0)); atomicAdd(S.counters + 21, (unsigned long long)(tp2 - tp1)); atomicAdd(S.counters + 22, (unsigned long long)(tp3 - tp2)); }
+#endif
   if (ret) return ret;
   if (eq_only) { nwrong = 0; return 0; }            // the step of the equality-constrained problem is in s.d
   double* dout = pert ? pert->dout : S.D + inst * P.n_w;
@@ -1191,6 +1417,9 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
 #endif
     for (int j2 = 0; j2 < m; ++j2) if ((int)s.acte[j2] < NI) tm_mask_set(amask_next, (int)s.acte[j2]);
   }
+#if defined(TM_PROF_W) && defined(__CUDA_ARCH__)
+  if (lane == 0 && !pert) atomicAdd(S.counters + 23, (unsigned long long)(clock64() - tp3));
+#endif
   nwrong = nw;
   if (nw == 0) {
     for (int e = lane; e < P.n_w; e += TM_NL) dout[e] = s.d[e];
