@@ -127,6 +127,32 @@ def economic():
         np.savez_compressed(os.path.join(HERE, "golden_%s_economic.npz" % name), **out)
 
 
+def unicycle_economic():
+    """economic MPC on the periodic unicycle reference (pmpc.py:97-107 with p = N = 30): 8 instances x 6 closed-loop steps"""
+    from tunempc_b200 import tuning
+    name = "unicycle"
+    st = rp.StageLib(name)
+    pb, info = configs.make_problem(name, st.F, mpc_type="economic")
+    pb.save(os.path.join(HERE, "problem_unicycle_economic.npz"))
+    cf = tuning.lambdify_cost(info["cfg"]["model"], info["cfg"]["cost"])
+    B, ns = 8, 6
+    X0 = sample_x0(name, pb, B, 3)
+    ctrl = rp.Pmpc(pb, qp="qpoases", cost_funs=cf)
+    Xcl, Ucl, Icl = [], [], []
+    for b in range(B):
+        ctrl.reset()
+        x = X0[b].copy()
+        xs_, us_, it_ = [x.copy()], [], []
+        for _ in range(ns):
+            u = ctrl.step(x)
+            assert ctrl.log["status"][-1] == 0
+            x = st.F(x[None, :], u[None, :])[0]
+            xs_.append(x.copy()); us_.append(u.copy()); it_.append(ctrl.log["iter"][-1])
+        Xcl.append(xs_); Ucl.append(us_); Icl.append(it_)
+    np.savez_compressed(os.path.join(HERE, "golden_unicycle_economic.npz"), X0=X0, cl_X=np.array(Xcl), cl_U=np.array(Ucl), cl_iter=np.array(Icl))
+    print("unicycle economic: iter hist", np.bincount(np.array(Icl).ravel()))
+
+
 def chain(name="chain", B=32):
     """synthetic models (configs.chain nz = 8, configs.dims9 nz = 12 with the AWE config's dimensions): generic-dimension paths"""
     st = rp.StageLib(name)
@@ -159,6 +185,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "unicycle":
         unicycle()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "unicycle_economic":
+        unicycle_economic()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "evaporation":
         evaporation()

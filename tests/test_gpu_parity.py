@@ -365,6 +365,21 @@ def test_economic_controller(torch_mod, name):
     assert 3.5 < d2 / d1 < 4.5, (d1, d2)                                         # the difference is second order in alpha
 
 
+def test_economic_periodic_unicycle(torch_mod):
+    """economic MPC on the periodic unicycle reference (pmpc.py:97-107,709-767, p = N = 30): closed loops of the oracle"""
+    torch = torch_mod
+    ctrl, pb = _ctrl("unicycle_economic")
+    gold = load_golden("unicycle_economic")
+    X = torch.tensor(gold["X0"], device="cuda:0")
+    for s in range(gold["cl_U"].shape[1]):
+        U = ctrl.step(X)
+        assert (ctrl.status.cpu().numpy() == 0).all()
+        assert np.array_equal(ctrl.log["iter"][-1].cpu().numpy(), gold["cl_iter"][:, s])
+        assert _relerr(U.cpu().numpy(), gold["cl_U"][:, s]) < 1e-8, s
+        X = ctrl.plant_step(X, U)
+    assert _relerr(X.cpu().numpy(), gold["cl_X"][:, -1]) < 1e-8
+
+
 @pytest.mark.parametrize("name,lin_mode", [("chain", "2"), ("chain", "1"), ("dims9", "2"), ("dims9", "1"), ("dims9", None)])
 def test_generic_dimensions(torch_mod, name, lin_mode, monkeypatch):
     """synthetic models beyond the reference configs' dimensions -- chain (nz = 8) and dims9 (nz = 12: the AWE config's

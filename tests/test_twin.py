@@ -192,6 +192,24 @@ def test_twin_economic_controller(env):
         assert o["iter"][0] == 1 and np.allclose(o["u0"][0], pb.wref[0, pb.nx:], rtol=1e-9)
 
 
+def test_twin_economic_periodic_unicycle(env):
+    """economic MPC on a periodic reference (pmpc.py:97-107,709-767 with p = N = 30): closed loops of the oracle, phase-indexed
+    dual reference with non-zero dynamics multipliers and the projected terminal multiplier"""
+    rp, build_tables, Twin = env
+    pb, gold = load_problem("unicycle_economic"), load_golden("unicycle_economic")
+    assert pb.mpc_type == "economic" and pb.p == 30 and np.abs(pb.lam_dyn_ref).max() > 0
+    st = rp.StageLib("unicycle")
+    tw = Twin(pb, build_tables(pb))
+    tw.reset(gold["X0"].shape[0])
+    x = gold["X0"].copy()
+    for s in range(gold["cl_U"].shape[1]):
+        o = tw.step(x)
+        assert (o["status"] == 0).all() and np.array_equal(o["iter"], gold["cl_iter"][:, s])
+        assert _relerr(o["u0"], gold["cl_U"][:, s]) < 1e-9, s
+        x = st.F(x, o["u0"])
+    assert _relerr(x, gold["cl_X"][:, -1]) < 1e-9
+
+
 def test_twin_generic_dimensions_chain(env):
     """synthetic nx = 6, nu = 2 model (configs.chain, not in the reference): nothing in the device code is tied to the
     dimensions of the four reference configs"""

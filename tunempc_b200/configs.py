@@ -244,6 +244,12 @@ def make_problem(name, stage_F, N=None, hessian_approximation="exact", mpc_type=
         info = {"z_ocp": z, "lam_dyn_ocp": lam_d, "H_ocp": S["H"], "Hc": Hc, "cfg": cfg,
                 "eig_H": np.array([np.linalg.eigvalsh(h) for h in S["H"]]),
                 "eig_Hc": np.array([np.linalg.eigvalsh(h) for h in Hc])}
+        if mpc_type == "economic":                                       # economic MPC on the periodic reference (pmpc.py:97-107,709-767)
+            pb.mpc_type = "economic"
+            pb.hessian_approximation = "exact"
+            pb.lam_dyn_ref = np.array(lam_d).copy()
+            pb.H = np.zeros_like(pb.H)
+            pb.q = np.zeros_like(pb.q)
         return pb, info
     z, lam_d, lam_h = tuning.solve_steady_state(stage_F, cost_funs, cfg["C"], cfg["c"], cfg["w_guess"], nx)
     S = tuning.sensitivities(stage_F, cost_funs, cfg["C"], z, lam_d, lam_h, nx)

@@ -99,13 +99,11 @@ class Tuner(object):
     def create_mpc(self, mpc_type, N, opts={}, tuning=None, device=0):
         """Create an MPC controller of the given type and horizon.  'tuned': H = Hc, q = S['q']; 'tracking': user
         tuning {'H': [...], 'q': [...]} (tuner.py:191-195); 'economic': the stage cost l itself with the OCP's multipliers as
-        dual reference and the exact Hessian (tuner.py:180-182, pmpc.py:97-107), p = 1 only."""
+        dual reference and the exact Hessian (tuner.py:180-182, pmpc.py:97-107), steady-state and periodic references."""
         if mpc_type not in ["economic", "tuned", "tracking"]:
             raise ValueError("Provided MPC type not supported.")                           # tuner.py:168-169
         if self.__w_sol is None:
             raise RuntimeError("call solve_ocp() first")
-        if mpc_type == "economic" and self.__p != 1:
-            raise NotImplementedError("economic MPC on a periodic reference is not built yet")
         if mpc_type == "tracking":
             if tuning is None:
                 raise ValueError("Tracking type MPC controller requires user-provided tuning!")   # tuner.py:193
