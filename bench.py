@@ -3,7 +3,7 @@
 
   python bench.py --gpus N --steps K --warmup W            B200 arm (under torchrun for N > 1, one rank per GPU)
   python bench.py --impl reference --gpus N --steps K ...  CPU arm: the oracle port of the reference loop on host cores
-  python bench.py --config lq|evaporation|unicycle ...     the other BASELINE.json configs at their own batch sizes
+  python bench.py --config lq|evaporation|unicycle|awe9 ...  the other BASELINE.json configs at their own batch sizes
   python bench.py --scaling strong ...                     fixed 2^20 instances in total, split over the ranks
 
 A "step" = one pass of the hot path over one batch: `ctrl.reset(); ctrl.step(X0)` for B = 2^20 seeded initial states
@@ -39,6 +39,8 @@ CONFIGS = {
     "lq": dict(B=1 << 10, cl=1, text="convex LQR N=10 tuned MPC (examples/convex_lqr.py)"),
     "evaporation": dict(B=1 << 18, cl=1, text="evaporation process N=30 tuned NMPC, collocation, state constraints (examples/evaporation_process)"),
     "unicycle": dict(B=1 << 16, cl=100, text="unicycle p=N=30 periodic tuned MPC, 100-step closed loop, plant = model (examples/unicycle)"),
+    "awe9": dict(B=1 << 14, cl=40, text="AWE-shaped stand-in (configs.awe9: nx=9 nu=3 ns=3 nsc=3 nh=17 N=20 p=40, slacks us/usc, nonlinear rows g, "
+                                        "L1 slack cost), 40-step closed loop over one period, plant = model (examples/awe_system dimensions)"),
 }
 
 
@@ -177,7 +179,7 @@ def run_reference_arm(args):
     rp.build((name,))
     backend = "qpOASES_e (reference tree, oracle/_ref)" if rp.qpoases_available() else "dense null-space + Goldfarb-Idnani (oracle fallback: oracle/_ref missing)"
     cores = len(os.sched_getaffinity(0))
-    per_core = 6                                   # ~2 s of CPU work per core and step
+    per_core = 6 if name != "awe9" else 1          # ~2 s of CPU work per core and step
     n = cores * per_core
     chunks = [list(range(c, n, cores)) for c in range(cores)]
     ctx = mp.get_context("fork")
@@ -344,9 +346,10 @@ def main():
         ach = (n_lin * f_lin) / (lin_ms * 1e-3) / 1e12 if lin_ms > 0 else 0.0
         # Algorithmic bytes: a stage task reads (x,u,lam_dyn) and writes its record xf | S | W; a QP reads its N records + w and
         # writes (d, lam).  Measured DRAM traffic: profiles/ncu_traffic.json (ncu --set full of this code, tools/ncu_traffic.py).
-        npair = pb.nz * (pb.nz + 1) // 2
-        lin_alg_bytes_per_task = 8.0 * (pb.nx + pb.nu + pb.nx) + 8.0 * (pb.nx + pb.nx * pb.nz + npair)
-        qp_alg_bytes = 8.0 * (pb.N * (pb.nx + pb.nx * pb.nz + npair) + 2 * pb.n_w + pb.n_g + pb.nx)
+        nzm = pb.nx + pb.nu                                # the linearisation record holds model variables only (no slack columns)
+        npair = nzm * (nzm + 1) // 2
+        lin_alg_bytes_per_task = 8.0 * (pb.nx + pb.nu + pb.nx) + 8.0 * (pb.nx + pb.nx * nzm + npair)
+        qp_alg_bytes = 8.0 * (pb.N * (pb.nx + pb.nx * nzm + npair) + 2 * pb.n_w + pb.n_g + pb.nx)
         tr = ncu_traffic().get(name, {})
         lin_tr, qp_tr = tr.get("lin", {}), tr.get("qp", {})
         try:
@@ -378,7 +381,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s, %s Hessian, B=%d x0 per GPU per step, %s" % (cfg["text"], args.hessian, B,
                                    "reset+step" if CL == 1 else "reset + %d closed-loop steps" % CL),
-                       "l2": "working set %.1f GB per step >> L2; %d alternating input batches" % (B * 8.0 * (3 * pb.n_w + 3 * pb.n_g + pb.N * (pb.nx + pb.nx * pb.nz + npair)) / 1e9, nbatches),
+                       "l2": "working set %.1f GB per step >> L2; %d alternating input batches" % (B * 8.0 * (3 * pb.n_w + 3 * pb.n_g + pb.N * (pb.nx + pb.nx * nzm + npair)) / 1e9, nbatches),
                        "x0": "seeded perturbation recipe of the example (tunempc_b200.configs.sample_x0), seed 100+17*rank+i"},
             "e2e": {"value": solves / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * pb.nx * 8 * CL,
                     "d2h_bytes_per_step": (B * pb.nu * 8 + 3 * B * 4) * CL + (B * pb.nx * 8 * CL if CL > 1 else 0)},
@@ -395,7 +398,7 @@ def main():
         try:
             from oracle import reference_port as rp
             oc = rp.Pmpc(load_problem(name))
-            n = args.cpu_sample
+            n = args.cpu_sample if pb.n_w < 300 else min(args.cpu_sample, 6)     # the dense 369-variable QPs of awe9 take seconds each
             xs = x_np[0][:n]
             from threadpoolctl import threadpool_limits
             with threadpool_limits(limits=1):              # "cores": 1 means one thread, BLAS included

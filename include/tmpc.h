@@ -51,7 +51,14 @@ typedef struct {
   int32_t nx_term;       /* rows of the terminal operator (selection of states) */
   int32_t N;             /* horizon */
   int32_t p;             /* period of the reference tables */
+  int32_t ns;            /* slacks us of the nonlinear path constraints: rows g_k = h_nl(x,u) - us = 0 (tunempc/preprocessing.py:78-118,
+                            pmpc.py:50-55,222-228,270-271); must equal the compiled model's (checked) */
+  int32_t nsc;           /* soft-constraint slacks usc with the linear cost scost'usc (tunempc/preprocessing.py:120-155,
+                            pmpc.py:57-62,230-233,338-339); must equal the compiled model's (checked) */
 } tmpc_dims;
+/* Stage variables z_k = (x, u, us, usc), nz = nx + nu + ns + nsc (pmpc.py:217-235); n_w = N*nz + nx.
+ * g = [init(nx) | k < N: dyn_k(nx), g_k(ns), h_k(nh) | term(nx_term)], n_g = nx + N*(nx+ns+nh) + nx_term (pmpc.py:242-256).
+ * h rows are linear in z: [h_lin(x,u) (+ usc on slacked rows); us; usc] >= 0 (preprocessing.py:110-112,150). */
 
 typedef struct {
   int32_t hessian_exact;   /* 1: exact Lagrangian Hessian (pmpc.py:153 default), 0: gauss_newton (pmpc.py:327-333) */
@@ -74,13 +81,18 @@ typedef struct {
 void tmpc_default_opts(tmpc_opts* o);
 /* compiled model: name, nx, nu, RK4 steps (0 for a discrete map), step length */
 const char* tmpc_model_info(int32_t* nx, int32_t* nu, int32_t* rk_steps, double* dt);
+/* slack dimensions the model library was compiled for (0, 0 for a model without nonlinear / soft constraints) */
+void tmpc_model_slacks(int32_t* ns, int32_t* nsc);
 
 int tmpc_create(tmpc_handle** h, const tmpc_dims* dims, const tmpc_opts* opts, int device);
 void tmpc_destroy(tmpc_handle* h);
 const char* tmpc_last_error(const tmpc_handle* h);
 
 /* host pointers, copied.  wref (p*nz) | H (p*nz*nz) | q (p*nz) per phase; ref_du (p*n_g) dual reference window per
- * phase in g-order; C (nh*nz), c (nh); term_idx (nx_term); relax0 (nh) 1 = row dropped at stage 0 (pmpc.py:293-294) */
+ * phase in g-order; C (nh*nz), c (nh); term_idx (nx_term); relax0 (nh) 1 = row dropped at stage 0 (pmpc.py:293-294:
+ * h_x_idx + h_us_idx, the caller computes the lists with the reference's formulas).  With slacks the tables are nz wide:
+ * the usc entries of wref and the usc rows / columns of H are zero (the reference's wref and H have none, pmpc.py:186-208)
+ * and the usc entries of q carry scost (pmpc.py:338-339: J += scost'usc). */
 int tmpc_set_tables(tmpc_handle* h, const double* wref, const double* H, const double* q, const double* ref_du,
                     const double* C, const double* c, const int32_t* term_idx, const int32_t* relax0);
 

@@ -30,7 +30,7 @@ def _p(a):
     return a.ctypes.data_as(_dp) if a is not None else None
 
 
-def build(models=("lq", "cstr", "unicycle", "evaporation", "chain", "dims9")):
+def build(models=("lq", "cstr", "unicycle", "evaporation", "chain", "dims9", "awe9")):
     """compile the C restatement (and oracle/_ref when the reference tree is present)."""
     subprocess.check_call(["make", "-s", "-C", _HERE, "MODELS=" + " ".join(models)])
 
@@ -190,32 +190,71 @@ def qp_dense(H, g, A, lba, uba, tol=1e-11):
 # ------------------------------------------------------------------------------------------------------
 #  NLP of the tuned tracking MPC (tunempc/pmpc.py:162-369), dense
 # ------------------------------------------------------------------------------------------------------
+class GnlFuns:
+    """the slacked nonlinear path constraints h_nl(x,u) of a model card (tunempc/preprocessing.py:78-118), lambdified
+    straight from the sympy expressions: value (ns,), Jacobian (ns, nx+nu), second derivatives (ns, nx+nu, nx+nu).
+    Independent of the generated C the device uses."""
+
+    def __init__(self, model):
+        import sympy as sp
+        z = list(model.x) + list(model.u)
+        g = sp.Matrix([sp.sympify(e) for e in model.gnl])
+        self.ns = len(model.gnl)
+        self._v = sp.lambdify([z], g, "numpy")
+        self._j = sp.lambdify([z], g.jacobian(z), "numpy")
+        self._h = [sp.lambdify([z], sp.hessian(e, z), "numpy") for e in g]
+
+    def val(self, z):
+        return np.asarray(self._v(list(z)), dtype=np.float64).ravel()
+
+    def jac(self, z):
+        return np.asarray(self._j(list(z)), dtype=np.float64).reshape(self.ns, len(z))
+
+    def hess(self, z):
+        return np.array([np.asarray(h(list(z)), dtype=np.float64) for h in self._h])
+
+
 class TrackingNlp:
-    def __init__(self, pb, stage=None):
+    def __init__(self, pb, stage=None, gnl=None):
         self.pb = pb
         self.stage = stage if stage is not None else StageLib(pb.name)
         assert self.stage.nx == pb.nx and self.stage.nu == pb.nu
         self.lbg, self.ubg = pb.bounds()
+        self.gnl = gnl
+        if pb.ns and gnl is None:
+            from tunempc_b200 import configs            # the model card's expressions (not the generated code)
+            self.gnl = GnlFuns(configs.CONFIGS[pb.name]()["model"])
+        self.nzm = pb.nx + pb.nu
 
     # parameter vector p = (x0, wref window, H window, q window)   (pmpc.py:186-208, 380-391)
     def _split(self, w):
         pb = self.pb
         Z = w[: pb.N * pb.nz].reshape(pb.N, pb.nz)
-        return Z, Z[:, : pb.nx], Z[:, pb.nx:], w[pb.N * pb.nz:]
+        return Z, Z[:, : pb.nx], Z[:, pb.nx: pb.nx + pb.nu], w[pb.N * pb.nz:]
+
+    def _dZ(self, w, p):
+        """(x,u,us)_k - reference: the tracking cost's argument (pmpc.py:305-313); the reference window has no usc entries"""
+        pb = self.pb
+        Z, _, _, _ = self._split(w)
+        return Z[:, : pb.nzr] - p["wref"][: pb.N * pb.nz].reshape(pb.N, pb.nz)[:, : pb.nzr]
 
     def f(self, w, p):
         pb = self.pb
-        Z, _, _, _ = self._split(w)
-        dZ = Z - p["wref"][: pb.N * pb.nz].reshape(pb.N, pb.nz)
-        return float(sum(0.5 * dZ[k] @ p["H"][k] @ dZ[k] + p["q"][k] @ dZ[k] for k in range(pb.N)))  # mtools.py:54-55
+        dZ = self._dZ(w, p)
+        J = float(sum(0.5 * dZ[k] @ p["H"][k] @ dZ[k] + p["q"][k] @ dZ[k] for k in range(pb.N)))  # mtools.py:54-55
+        if pb.nsc:                                                                                # pmpc.py:338-339
+            Z, _, _, _ = self._split(w)
+            J += float(sum(pb.scost @ Z[k, pb.nzr:] for k in range(pb.N)))
+        return J
 
     def jacf(self, w, p):
         pb = self.pb
-        Z, _, _, _ = self._split(w)
-        dZ = Z - p["wref"][: pb.N * pb.nz].reshape(pb.N, pb.nz)
+        dZ = self._dZ(w, p)
         gr = np.zeros(pb.n_w)
         for k in range(pb.N):
-            gr[pb.iz(k)] = 0.5 * (p["H"][k] + p["H"][k].T) @ dZ[k] + p["q"][k]
+            gr[pb.izr(k)] = 0.5 * (p["H"][k] + p["H"][k].T) @ dZ[k] + p["q"][k]
+            if pb.nsc:
+                gr[pb.iusc(k)] = pb.scost
         return gr
 
     def g(self, w, p, order=0):
@@ -227,8 +266,11 @@ class TrackingNlp:
         g = np.zeros(pb.n_g)
         g[pb.g_init()] = X[0] - p["x0"]
         Xn = np.vstack([X[1:], xN[None, :]])
+        nzm = self.nzm
         for k in range(pb.N):
             g[pb.g_dyn(k)] = xf[k] - Xn[k]
+            if pb.ns:                                                     # g_k = h_nl(x_k,u_k) - us_k (preprocessing.py:107-108)
+                g[pb.g_g(k)] = self.gnl.val(Z[k, :nzm]) - Z[k, nzm: nzm + pb.ns]
             if pb.nh:
                 g[pb.g_h(k)] = pb.C @ Z[k] + pb.c
         g[pb.g_term()] = pb.T @ (xN - p["wref"][pb.N * pb.nz:])
@@ -238,8 +280,11 @@ class TrackingNlp:
         J = np.zeros((pb.n_g, pb.n_w))
         J[pb.g_init(), pb.ix(0)] = np.eye(pb.nx)
         for k in range(pb.N):
-            J[pb.g_dyn(k), pb.iz(k)] = S[k]
+            J[pb.g_dyn(k), k * pb.nz: k * pb.nz + nzm] = S[k]
             J[pb.g_dyn(k), pb.ix(k + 1)] = -np.eye(pb.nx)
+            if pb.ns:
+                J[pb.g_g(k), k * pb.nz: k * pb.nz + nzm] = self.gnl.jac(Z[k, :nzm])
+                J[pb.g_g(k), pb.ius(k)] = -np.eye(pb.ns)
             if pb.nh:
                 J[pb.g_h(k), pb.iz(k)] = pb.C
         J[pb.g_term(), pb.ix(pb.N)] = pb.T
@@ -252,11 +297,15 @@ class TrackingNlp:
         pb = self.pb
         Hm = np.zeros((pb.n_w, pb.n_w))
         for k in range(pb.N):
-            Hm[pb.iz(k), pb.iz(k)] = 0.5 * (p["H"][k] + p["H"][k].T)
+            Hm[pb.izr(k), pb.izr(k)] = 0.5 * (p["H"][k] + p["H"][k].T)     # usc rows / columns stay zero (pmpc.py:327-333)
         if mode == "exact":
             _, _, T2 = self.g(w, p, order=2)
+            Z, _, _, _ = self._split(w)
             for k in range(pb.N):
-                Hm[pb.iz(k), pb.iz(k)] += np.einsum("a,aij->ij", lam[pb.g_dyn(k)], T2[k])
+                zs = slice(k * pb.nz, k * pb.nz + self.nzm)
+                Hm[zs, zs] += np.einsum("a,aij->ij", lam[pb.g_dyn(k)], T2[k])
+                if pb.ns:
+                    Hm[zs, zs] += np.einsum("a,aij->ij", lam[pb.g_g(k)], self.gnl.hess(Z[k, : self.nzm]))
         return Hm
 
 
@@ -474,12 +523,18 @@ class Pmpc:
             ws[pb.ix(i)] = w[pb.ix(i + 1)]
             if i < N - 1:
                 ws[pb.iu(i)] = w[pb.iu(i + 1)]
+                ws[pb.ius(i)] = w[pb.ius(i + 1)]                          # :881-884
+                ws[pb.iusc(i)] = w[pb.iusc(i + 1)]
                 ls[pb.g_dyn(i)] = lam[pb.g_dyn(i + 1)]
+                ls[pb.g_g(i)] = lam[pb.g_g(i + 1)]                        # :888-890
                 if pb.nh:
                     ls[pb.g_h(i)] = lam[pb.g_h(i + 1)]
         ws[pb.ix(N)] = ws[pb.ix(N - 1)]
         ws[pb.iu(N - 1)] = ws[pb.iu(N - 2)]
+        ws[pb.ius(N - 1)] = ws[pb.ius(N - 2)]                             # :895-898
+        ws[pb.iusc(N - 1)] = ws[pb.iusc(N - 2)]
         ls[pb.g_dyn(N - 1)] = ls[pb.g_dyn(N - 2)]
+        ls[pb.g_g(N - 1)] = ls[pb.g_g(N - 2)]
         if pb.nh:
             ls[pb.g_h(N - 1)] = ls[pb.g_h(N - 2)]
         ls[pb.g_term()] = lam[pb.g_term()]

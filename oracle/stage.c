@@ -18,8 +18,13 @@
 #include TMPC_MODEL_HEADER
 
 #define NX TMPC_NX
+#ifdef TMPC_NUM               /* model dimensions: the slack variables of the MPC do not enter the dynamics */
+#define NU TMPC_NUM
+#define NZ TMPC_NZM
+#else
 #define NU TMPC_NU
 #define NZ TMPC_NZ
+#endif
 
 static const int hA[] = TMPC_HESS_A, hB[] = TMPC_HESS_B, hC[] = TMPC_HESS_C;
 

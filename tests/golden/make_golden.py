@@ -153,6 +153,72 @@ def unicycle_economic():
     print("unicycle economic: iter hist", np.bincount(np.array(Icl).ravel()))
 
 
+def _awe9_single(args):
+    i, x0, tol = args
+    pb = rp_problem("awe9")
+    ctrl = rp.Pmpc(pb, qp="qpoases", sqp_options={"tol": tol})
+    u = ctrl.step(x0)
+    lg = ctrl.log
+    return (i, u, ctrl.w_sol, ctrl.lam_g, lg["iter"][-1], lg["status"][-1], lg["f"][-1], lg["nAS"][-1], lg["nACtot"][-1], lg["nAC"][-1])
+
+
+def _awe9_loop(args):
+    b, x0, nsteps = args
+    pb = rp_problem("awe9")
+    st = rp.StageLib("awe9")
+    ctrl = rp.Pmpc(pb, qp="qpoases")
+    x = x0.copy()
+    xs_, us_, it_ = [x.copy()], [], []
+    for _ in range(nsteps):
+        u = ctrl.step(x)
+        assert ctrl.log["status"][-1] == 0
+        x = st.F(x[None, :], u[None, :])[0]
+        xs_.append(x.copy()); us_.append(u.copy()); it_.append(ctrl.log["iter"][-1])
+    return b, np.array(xs_), np.array(us_), np.array(it_)
+
+
+def rp_problem(name):
+    from tunempc_b200.problem import MpcProblem
+    return MpcProblem.load(os.path.join(HERE, "problem_%s.npz" % name))
+
+
+def awe9(B=24, Bcl=6, nsteps=8, Blarge=512):
+    """slack formulation (us, usc, g rows, scost; configs.awe9: nx = 9, nu = 3, ns = 3, nsc = 3, nh = 17, N = 20, p = 40):
+    single solves at two tolerances, closed loops over the periodic reference, and a larger batch of compact results"""
+    import multiprocessing as mp
+    st = rp.StageLib("awe9")
+    pb, info = configs.make_problem("awe9", st.F)
+    pb.save(os.path.join(HERE, "problem_awe9.npz"))
+    X0 = sample_x0("awe9", pb, B)
+    out = {"X0": X0}
+    cores = len(os.sched_getaffinity(0))
+    with mp.get_context("fork").Pool(cores) as pool:
+        for tag, tol in (("t6", 1e-6), ("t9", 1e-9)):
+            res = sorted(pool.map(_awe9_single, [(i, X0[i], tol) for i in range(B)]), key=lambda r: r[0])
+            assert all(r[5] == 0 for r in res)
+            out.update({"u0_" + tag: np.array([r[1] for r in res]), "w_" + tag: np.array([r[2] for r in res]),
+                        "lam_" + tag: np.array([r[3] for r in res]), "iter_" + tag: np.array([r[4] for r in res]),
+                        "f_" + tag: np.array([r[6] for r in res]), "nAS_" + tag: np.array([r[7] for r in res]),
+                        "nACtot_" + tag: np.array([r[8] for r in res]), "nAC_" + tag: np.array([r[9] for r in res])})
+            print("awe9", tag, "iter hist", np.bincount(out["iter_" + tag]), "nAS", np.bincount(out["nAS_" + tag]), flush=True)
+        Xc = sample_x0("awe9", pb, Bcl, 5)
+        res = sorted(pool.map(_awe9_loop, [(b, Xc[b], nsteps) for b in range(Bcl)]), key=lambda r: r[0])
+        out.update({"cl_X": np.array([r[1] for r in res]), "cl_U": np.array([r[2] for r in res]), "cl_iter": np.array([r[3] for r in res])})
+        print("awe9 closed loop iter hist", np.bincount(out["cl_iter"].ravel()), flush=True)
+        np.savez_compressed(os.path.join(HERE, "golden_awe9.npz"), **out)
+        XL = sample_x0("awe9", pb, Blarge, 2024)
+        res = sorted(pool.map(_awe9_single, [(i, XL[i], 1e-6) for i in range(Blarge)], chunksize=4), key=lambda r: r[0])
+        nI = pb.N * pb.nh
+        act = np.array([np.packbits(np.array([r[3][pb.g_h(k)][j] != 0 for k in range(pb.N) for j in range(pb.nh)], dtype=bool)) for r in res])
+        np.savez_compressed(os.path.join(HERE, "large_awe9.npz"), seed=2024, B=Blarge, qp_backend="qpoases_e (oracle/_ref)",
+                            u0=np.array([r[1] for r in res]), x1=np.array([r[2][pb.ix(1)] for r in res]),
+                            iter=np.array([r[4] for r in res], dtype=np.int32), status=np.array([r[5] for r in res], dtype=np.int32),
+                            f=np.array([r[6] for r in res]), nAS=np.array([r[7] for r in res], dtype=np.int32),
+                            nACtot=np.array([r[8] for r in res], dtype=np.int32), nAC=np.array([r[9] for r in res], dtype=np.int32),
+                            active=act)
+        print("awe9 large: status", np.bincount(np.array([r[5] for r in res])), "iter", np.bincount(np.array([r[4] for r in res])), flush=True)
+
+
 def chain(name="chain", B=32):
     """synthetic models (configs.chain nz = 8, configs.dims9 nz = 12 with the AWE config's dimensions): generic-dimension paths"""
     st = rp.StageLib(name)
@@ -174,6 +240,9 @@ def chain(name="chain", B=32):
 
 def main():
     rp.build()
+    if len(sys.argv) > 1 and sys.argv[1] == "awe9":
+        awe9()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "chain":
         chain()
         return

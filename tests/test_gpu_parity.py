@@ -365,6 +365,76 @@ def test_economic_controller(torch_mod, name):
     assert 3.5 < d2 / d1 < 4.5, (d1, d2)                                         # the difference is second order in alpha
 
 
+@pytest.mark.parametrize("qpmode", [None, "t"])
+def test_awe9_slack_formulation(torch_mod, qpmode, monkeypatch):
+    """config #5 stand-in (configs.awe9: nx = 9, nu = 3, ns = 3, nsc = 3, nh = 17, N = 20, p = 40, nx_term = 7): slack variables,
+    nonlinear equality rows, L1 slack cost and the bug-compatible stage-0 relaxation on the device, against the oracle"""
+    torch = torch_mod
+    if qpmode is not None:
+        monkeypatch.setenv("TMPC_QP_MODE", qpmode)
+        monkeypatch.setenv("TMPC_QP_THREAD_MIN", "1")
+    ctrl, pb = _ctrl("awe9")
+    gold = load_golden("awe9")
+    U = ctrl.step(torch.tensor(pb.wref[0, :pb.nx][None], device="cuda:0")).cpu().numpy()
+    assert ctrl.status.cpu().numpy()[0] == 0 and np.allclose(U[0], pb.wref[0, pb.nx:pb.nx + pb.nu], atol=1e-10)
+    ctrl.reset()
+    U = ctrl.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
+    assert U.shape == (gold["X0"].shape[0], 3)
+    assert (ctrl.status.cpu().numpy() == 0).all()
+    assert np.array_equal(ctrl.log["iter"][-1].cpu().numpy(), gold["iter_t6"])
+    assert _relerr(U, gold["u0_t6"]) < 1e-8 and _relerr(ctrl.w_sol.cpu().numpy(), gold["w_t6"]) < 1e-8
+    lam = ctrl.lam_g.cpu().numpy()
+    assert _relerr(lam, gold["lam_t6"]) < 1e-6
+    for b in range(lam.shape[0]):
+        for k in range(pb.N):
+            assert np.array_equal(lam[b][pb.g_h(k)] != 0, gold["lam_t6"][b][pb.g_h(k)] != 0), (b, k)
+    for key in ("nAS", "nACtot", "nAC"):
+        assert np.array_equal(ctrl.log[key][-1].cpu().numpy(), gold[key + "_t6"]), key
+    assert _relerr(ctrl.log["f"][-1].cpu().numpy(), gold["f_t6"]) < 1e-8
+    g = ctrl.g_sol.cpu().numpy()
+    for k in range(pb.N):                                                     # g rows: h_nl(x,u) - us = 0 at the solution
+        assert np.abs(g[:, pb.g_g(k)]).max() < 1e-6
+    c9, _ = _ctrl("awe9", tol=1e-9)
+    U9 = c9.step(torch.tensor(gold["X0"], device="cuda:0")).cpu().numpy()
+    assert (c9.status.cpu().numpy() == 0).all() and _relerr(U9, gold["u0_t9"]) < 1e-8
+    assert _relerr(c9.w_sol.cpu().numpy(), gold["w_t9"]) < 1e-8
+    # closed loop over the periodic reference (plant = model)
+    ctrl.reset()
+    X = torch.tensor(gold["cl_X"][:, 0].copy(), device="cuda:0")
+    for s in range(gold["cl_U"].shape[1]):
+        U = ctrl.step(X)
+        assert (ctrl.status.cpu().numpy() == 0).all()
+        assert np.array_equal(ctrl.log["iter"][-1].cpu().numpy(), gold["cl_iter"][:, s]), s
+        assert _relerr(U.cpu().numpy(), gold["cl_U"][:, s]) < 1e-7, s
+        X = ctrl.plant_step(X, U)
+    assert _relerr(X.cpu().numpy(), gold["cl_X"][:, -1]) < 1e-7
+
+
+def test_awe9_large_fixture(torch_mod):
+    """512 seeded x0 of the config #5 stand-in against the committed oracle fixture: u0, x_1, iteration counts, f, nAS / nACtot /
+    nAC and the active set of every instance"""
+    torch = torch_mod
+    import os
+    from tunempc_b200 import configs
+    ctrl, pb = _ctrl("awe9")
+    L = np.load(os.path.join(os.path.dirname(__file__), "golden", "large_awe9.npz"))
+    X0 = configs.sample_x0("awe9", pb, int(L["B"]), int(L["seed"]))
+    U = ctrl.step(torch.tensor(X0, device="cuda:0")).cpu().numpy()
+    ok = L["status"] == 0
+    st = ctrl.status.cpu().numpy()
+    assert np.array_equal(st[ok], L["status"][ok]), np.bincount(st)
+    assert _relerr(U[ok], L["u0"][ok]) < 1e-6
+    w = ctrl.w_sol.cpu().numpy()
+    assert _relerr(w[ok][:, pb.ix(1)], L["x1"][ok]) < 1e-6
+    assert np.array_equal(ctrl.log["iter"][-1].cpu().numpy()[ok], L["iter"][ok])
+    lam = ctrl.lam_g.cpu().numpy()
+    act = np.array([np.packbits(np.array([lam[b][pb.g_h(k)][j] != 0 for k in range(pb.N) for j in range(pb.nh)], dtype=bool)) for b in range(lam.shape[0])])
+    assert np.array_equal(act[ok], L["active"][ok])
+    for key in ("nAS", "nACtot", "nAC"):
+        assert np.array_equal(ctrl.log[key][-1].cpu().numpy()[ok], L[key][ok]), key
+    assert _relerr(ctrl.log["f"][-1].cpu().numpy()[ok], L["f"][ok]) < 1e-7
+
+
 def test_economic_periodic_unicycle(torch_mod):
     """economic MPC on the periodic unicycle reference (pmpc.py:97-107,709-767, p = N = 30): closed loops of the oracle"""
     torch = torch_mod

@@ -65,3 +65,54 @@ def test_tables_identity_terminal():
         assert np.array_equal(tab.ref_du[k][pb.g_init()], -pb.lam_dyn_ref[(k - 1) % 2])
         for j in range(3):
             assert np.array_equal(tab.ref_du[k][pb.g_dyn(j)], pb.lam_dyn_ref[(k + j) % 2])
+
+
+def test_tables_slack_formulation_hand_case():
+    """us / usc / g rows (pmpc.py:217-235,242-256,289-294,692-720,930-937): p = 2, N = 2, nx = 1, nu = 1, ns = 1, nsc = 1.
+    h before the soft slack = [u + 1 >= 0 ; us >= 0] (preprocessing.py:110-112); row 0 is softened: [u + 1 + usc ; us ; usc]
+    (preprocessing.py:140-150).  Layouts, bounds and both tables written out by hand."""
+    nx, nu, ns, nsc, N, P = 1, 1, 1, 1, 2, 2
+    C = np.array([[0.0, 1.0, 0.0, 1.0],      # u + 1 + usc
+                  [0.0, 0.0, 1.0, 0.0],      # us
+                  [0.0, 0.0, 0.0, 1.0]])     # usc
+    c = np.array([1.0, 0.0, 0.0])
+    wref = np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])                # (p, nzr): x | u | us -- no usc entry (pmpc.py:186-196)
+    H = np.stack([np.diag([1.0, 2.0, 3.0]), np.diag([4.0, 5.0, 6.0])])
+    q = np.array([[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]])
+    pb = MpcProblem(name="hand", nx=nx, nu=nu, N=N, p=P, wref=wref, H=H, q=q, C=C, c=c,
+                    lam_h_ref=np.array([[-0.5, 0.0], [0.0, -0.25]]), lam_dyn_ref=np.zeros((P, nx)), term_idx=[0],
+                    ns=ns, nsc=nsc, scost=np.array([500.0]), lam_g_ref=np.array([[0.7], [-0.9]]), gnl_x_idx=[0])
+    assert (pb.nz, pb.nzr, pb.nh, pb.n_w, pb.n_g) == (4, 3, 3, 2 * 4 + 1, 1 + 2 * (1 + 1 + 3) + 1)
+    # g order [init | dyn_0 g_0 h_0(3) | dyn_1 g_1 h_1(3) | term]  (pmpc.py:242-256, 279-287)
+    assert (pb.g_dyn(0), pb.g_g(0), pb.g_h(0)) == (slice(1, 2), slice(2, 3), slice(3, 6))
+    assert (pb.g_dyn(1), pb.g_g(1), pb.g_h(1), pb.g_term()) == (slice(6, 7), slice(7, 8), slice(8, 11), slice(11, 12))
+    # stage-0 relaxation (pmpc.py:293-294): no row of h depends on x only; h_us_idx = idx + nh - ns = 0 + 3 - 1 = 2 (pmpc.py:1116)
+    # -- with the usc row appended after the us row that is the row `usc >= 0`, not `us >= 0` (bug-compatible)
+    assert pb.h_x_idx == [] and pb.h_us_idx == [2] and pb.relax0 == [2]
+    lbg, ubg = pb.bounds()
+    assert np.array_equal(lbg, np.array([0, 0, 0, 0, 0, -np.inf, 0, 0, 0, 0, 0, 0.0]))
+    assert np.array_equal(ubg, np.array([0, 0, 0, np.inf, np.inf, np.inf, 0, 0, np.inf, np.inf, np.inf, 0.0]))
+    tab = build_tables(pb)
+    # primal window: (x, u, us) of wref[(k+j)%p], usc = 0 (w0['usc'] stays 0, pmpc.py:930-937), then x of wref[(k+N)%p]
+    assert np.array_equal(tab.ref[0], np.array([1.0, 2.0, 3.0, 0.0, 4.0, 5.0, 6.0, 0.0, 1.0]))
+    assert np.array_equal(tab.ref[1], np.array([4.0, 5.0, 6.0, 0.0, 1.0, 2.0, 3.0, 0.0, 4.0]))
+    # dual window (pmpc.py:709-721): g rows lam_g_ref, h rows [lam_h_ref ; -scost]
+    assert np.array_equal(tab.ref_du[0], np.array([0, 0, 0.7, -0.5, 0.0, -500.0, 0, -0.9, 0.0, -0.25, -500.0, 0.0]))
+    assert np.array_equal(tab.ref_du[1], np.array([0, 0, -0.9, 0.0, -0.25, -500.0, 0, 0.7, -0.5, 0.0, -500.0, 0.0]))
+    assert tab.Href.shape == (2, 2, 3, 3) and np.array_equal(tab.Href[1, 1], H[0]) and np.array_equal(tab.qref[1, 0], q[1])
+    # tables as the C ABI takes them: nz wide, scost in the usc entry of q (J += scost'usc, pmpc.py:338-339)
+    wd, Hd, qd = pb.device_tables()
+    assert np.array_equal(wd[1], np.array([4.0, 5.0, 6.0, 0.0])) and np.array_equal(qd[0], np.array([0.1, 0.2, 0.3, 500.0]))
+    assert np.array_equal(Hd[0], np.diag([1.0, 2.0, 3.0, 0.0]))
+
+
+def test_problem_roundtrip_with_slacks(tmp_path):
+    from conftest import load_problem
+    pb = load_problem("awe9")
+    assert (pb.nx, pb.nu, pb.ns, pb.nsc, pb.nh, pb.N, pb.p, pb.nx_term) == (9, 3, 3, 3, 17, 20, 40, 7)     # SURVEY.md 8.0, config #5
+    assert (pb.n_w, pb.n_g) == (369, 596)
+    f = str(tmp_path / "pb.npz")
+    pb.save(f)
+    pb2 = MpcProblem.load(f)
+    assert pb2.ns == 3 and pb2.nsc == 3 and np.array_equal(pb2.scost, pb.scost) and pb2.gnl_x_idx == pb.gnl_x_idx
+    assert pb2.relax0 == pb.relax0 == sorted(set(pb.h_x_idx + [0 + 17 - 3]))

@@ -210,6 +210,40 @@ def test_twin_economic_periodic_unicycle(env):
     assert _relerr(x, gold["cl_X"][:, -1]) < 1e-9
 
 
+def test_twin_awe9_slack_formulation(env):
+    """config #5 stand-in (configs.awe9): slack variables us / usc, nonlinear equality rows g, L1 slack cost, bug-compatible
+    stage-0 relaxation, p = 40 periodic reference, 7-row projected terminal constraint -- the device routines against the
+    oracle's dense restatement (pmpc.py:217-294,338-339,709-721)"""
+    rp, build_tables, Twin = env
+    pb, gold = load_problem("awe9"), load_golden("awe9")
+    tw = Twin(pb, build_tables(pb))
+    tw.reset(1)
+    o = tw.step(pb.wref[0, :pb.nx][None])                                   # P1: step(x_ref) = u_ref in one iteration
+    assert o["status"][0] == 0 and o["iter"][0] == 1 and np.allclose(o["u0"][0], pb.wref[0, pb.nx:pb.nx + pb.nu], atol=1e-10)
+    n = 8
+    tw.reset(n)
+    o = tw.step(gold["X0"][:n])
+    assert (o["status"] == 0).all() and np.array_equal(o["iter"], gold["iter_t6"][:n])
+    assert _relerr(o["u0"], gold["u0_t6"][:n]) < 1e-9 and _relerr(o["w"], gold["w_t6"][:n]) < 1e-9
+    assert _relerr(o["lam"], gold["lam_t6"][:n]) < 1e-7
+    for key in ("nAS", "nACtot", "nAC"):
+        assert np.array_equal(o[key], gold[key + "_t6"][:n]), key
+    assert _relerr(o["f"], gold["f_t6"][:n]) < 1e-9
+    for b in range(n):                                                      # identical active sets (inequality rows)
+        for k in range(pb.N):
+            assert np.array_equal(o["lam"][b][pb.g_h(k)] != 0, gold["lam_t6"][b][pb.g_h(k)] != 0), (b, k)
+    # closed loop over the periodic reference: phase tables, warm-start shift with slacks (pmpc.py:867-906)
+    st = rp.StageLib("awe9")
+    nb = 3
+    tw.reset(nb)
+    x = gold["cl_X"][:nb, 0].copy()
+    for s in range(gold["cl_U"].shape[1]):
+        o = tw.step(x)
+        assert (o["status"] == 0).all() and np.array_equal(o["iter"], gold["cl_iter"][:nb, s]), s
+        assert _relerr(o["u0"], gold["cl_U"][:nb, s]) < 1e-8, s
+        x = st.F(x, o["u0"])
+
+
 def test_twin_generic_dimensions_chain(env):
     """synthetic nx = 6, nu = 2 model (configs.chain, not in the reference): nothing in the device code is tied to the
     dimensions of the four reference configs"""

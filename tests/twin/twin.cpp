@@ -11,18 +11,21 @@
 
 extern "C" {
 
-void twin_model_info(int* nx, int* nu) { *nx = NX; *nu = NU; }
+void twin_model_info(int* nx, int* nu) { *nx = NX; *nu = NUM; }
 
 // stage evaluation through the pair-wise integrator (same code path as tmpc_stage_eval_host)
 void twin_stage_eval(int n, const double* x, const double* u, int order, double* xf, double* S, double* T) {
   for (int s = 0; s < n; ++s) {
     const double* xs = x + (size_t)s * NX;
-    const double* us = u + (size_t)s * NU;
+    const double* us = u + (size_t)s * NUM;
     if (order == 0) {
       double t1[NX], t2[NX], t3[NX];
       tm_integrate<0>(xs, us, 0, 0, xf + (size_t)s * NX, t1, t2, t3);
       continue;
     }
+#pragma push_macro("NZ")
+#undef NZ
+#define NZ TMPC_NZM
     for (int i = 0; i < NZ; ++i)
       for (int j = i; j < NZ; ++j) {
         if (order == 1 && j != i) continue;
@@ -38,13 +41,14 @@ void twin_stage_eval(int n, const double* x, const double* u, int order, double*
           }
         }
       }
+#pragma pop_macro("NZ")
   }
 }
 
 // forward / adjoint stage linearisation (tmpc_lin3.cuh): record xf | S | W for n stage points with multipliers lam (n x nx)
 int twin_lin_adjoint(int n, const double* x, const double* u, const double* lam, int order, double* rec) {
 #if TMPC_RK4
-  for (int s = 0; s < n; ++s) tm_lin_adjoint(x + (size_t)s * NX, u + (size_t)s * NU, order, lam + (size_t)s * NX, rec + (size_t)s * TM_LSZ);
+  for (int s = 0; s < n; ++s) tm_lin_adjoint(x + (size_t)s * NX, u + (size_t)s * NUM, order, lam + (size_t)s * NX, rec + (size_t)s * TM_LSZ);
   return 0;
 #else
   (void)n; (void)x; (void)u; (void)lam; (void)order; (void)rec;
@@ -61,7 +65,7 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
   TmProb P;
   P.N = dims[0]; P.nh = dims[1]; P.nxt = dims[2]; P.p = dims[3];
   P.n_w = P.N * NZ + NX;
-  P.n_g = NX + P.N * (NX + P.nh) + P.nxt;
+  P.n_g = NX + P.N * (NX + NS + P.nh) + P.nxt;
   P.hessian_exact = iopts[0];
   P.filter_cap = 64;
   P.max_iter = iopts[1];

@@ -51,7 +51,8 @@ class Twin:
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, pb.nx)
         u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, pb.nu)
         n = x.shape[0]
-        xf = np.zeros((n, pb.nx)); S = np.zeros((n, pb.nx, pb.nz)); T = np.zeros((n, pb.nx, pb.nz, pb.nz))
+        nzm = pb.nx + pb.nu
+        xf = np.zeros((n, pb.nx)); S = np.zeros((n, pb.nx, nzm)); T = np.zeros((n, pb.nx, nzm, nzm))
         self.lib.twin_stage_eval(n, _p(x), _p(u), order, _p(xf), _p(S), _p(T))
         return (xf, S, T)[: order + 1] if order else xf
 
@@ -62,7 +63,8 @@ class Twin:
         u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, pb.nu)
         lam = np.ascontiguousarray(lam, dtype=np.float64).reshape(-1, pb.nx)
         n = x.shape[0]
-        lsz = pb.nx + pb.nx * pb.nz + pb.nz * (pb.nz + 1) // 2
+        nzm = pb.nx + pb.nu
+        lsz = pb.nx + pb.nx * nzm + nzm * (nzm + 1) // 2
         rec = np.zeros((n, lsz))
         if self.lib.twin_lin_adjoint(n, _p(x), _p(u), _p(lam), order, _p(rec)):
             return None
@@ -78,9 +80,10 @@ class Twin:
         iopts = np.array([1 if hm == "exact" else 0, pb.max_iter, 300, self.maxact,
                           1 if getattr(pb, "mpc_type", "tuned") == "economic" else 0, self.reg_mode, self.nonconvex_after], dtype=np.int32)
         dopts = np.array([pb.tol if tol is None else tol, 1e-8, 0.8, 1e-8, self.rho_rel], dtype=np.float64)
-        Hs = np.ascontiguousarray(0.5 * (pb.H + np.transpose(pb.H, (0, 2, 1))))
+        wref_d, H_d, q_d = pb.device_tables()
+        Hs = np.ascontiguousarray(0.5 * (H_d + np.transpose(H_d, (0, 2, 1))))
         relax0 = np.zeros(max(pb.nh, 1), dtype=np.int32)
-        for i in pb.h_x_idx:
+        for i in pb.relax0:
             relax0[i] = 1
         tidx = np.array(pb.term_idx, dtype=np.int32)
         G = np.zeros((B, pb.n_g)); st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
@@ -90,7 +93,7 @@ class Twin:
         cnt = np.zeros(24, dtype=np.int64)
         C = np.ascontiguousarray(pb.C if pb.nh else np.zeros((1, pb.nz)))
         c = np.ascontiguousarray(pb.c if pb.nh else np.zeros(1))
-        wref = np.ascontiguousarray(pb.wref); q = np.ascontiguousarray(pb.q); rdu = np.ascontiguousarray(self.tab.ref_du)
+        wref = np.ascontiguousarray(wref_d); q = np.ascontiguousarray(q_d); rdu = np.ascontiguousarray(self.tab.ref_du)
         ret = self.lib.twin_step(_i(dims), _i(iopts), _p(dopts), _p(wref), _p(Hs), _p(q), _p(rdu), _p(C), _p(c),
                                  _i(tidx), _i(relax0), ctypes.c_int(self.index % pb.p), ctypes.c_longlong(B), _p(X0),
                                  _p(self.W), _p(self.LAM), _p(G), _i(st), _i(it), _i(fl), _p(fv), _i(nAS), _i(nACt),
@@ -99,7 +102,7 @@ class Twin:
         if ret:
             raise RuntimeError("twin_step returned %d" % ret)
         out = dict(w=self.W.copy(), lam=self.LAM.copy(), g=G, status=st, iter=it, flags=fl, f=fv, nAS=nAS,
-                   nACtot=nACt, nAC=nAC, u0=self.W[:, pb.nx:pb.nz].copy(), counters=cnt)
+                   nACtot=nACt, nAC=nAC, u0=self.W[:, pb.nx:pb.nx + pb.nu].copy(), counters=cnt)
         self.W, self.LAM = Wsh, Lsh
         self.index += 1
         return out

@@ -186,6 +186,115 @@ def dims9():
     return dict(model=model, cost=cost, C=C, c=cc, w_guess=w_guess, period=1, N=20, term_idx=[1, 2, 4, 5, 6, 7, 8])
 
 
+def awe9():
+    """SYNTHETIC stand-in for config #5 (examples/awe_system: nx = 9, nu = 3, ns = 3, nsc = 3, 14 rows of h before the soft-
+    constraint slacks, N = 20, p = 40, 7-row projected terminal constraint x[1:3], x[4:]) -- the
+    reference's kite model is an opaque CasADi pickle.  Dynamics of `dims9`; three NONLINEAR path constraints (one of them
+    state-only) that `preprocessing.input_formatting` would slack into g = h_nl(x,u) - us = 0, us >= 0
+    (tunempc/preprocessing.py:78-118); eleven linear rows; `add_mpc_slacks(..., 'active')` (preprocessing.py:120-155) softens
+    the three rows that are active somewhere along the reference.  The periodic reference is a forced periodic response of
+    the model (inputs riding two bounds and one nonlinear constraint), tracked with a user tuning -- create_mpc('tracking')."""
+    card = dims9()
+    m = card["model"]
+    p, v, a, u = m.x[0:4], m.x[4:8], m.x[8], m.u
+    gnl = [12.0 - p[3] ** 2 - 0.5 * v[3] ** 2,                 # state only  -> gnl_x_idx = [0] (pmpc.py:1107-1114)
+           1.25 - u[0] * (1 + 0.3 * p[0]),
+           3.0 - u[1] ** 2 - 0.5 * a ** 2]
+    model = OdeModel("awe9", m.x, m.u, m.xdot, rk_steps=10, tf=0.3, cost=card["cost"], gnl=gnl, nsc=3)
+    nzm, ns, nsc = 12, 3, 3
+    nz = nzm + ns + nsc
+    rows = []
+    def row(coefs, const):
+        r = np.zeros(nz)
+        for idx, val in coefs:
+            r[idx] = val
+        rows.append((r, const))
+    for j, (lo, hi) in zip((9, 10, 11), ((-1.0, 1.5), (-0.3, 2.0), (-1.5, 1.5))):      # input bounds (rows 0..5)
+        row([(j, 1.0)], -lo)
+        row([(j, -1.0)], hi)
+    row([(8, 1.0)], 1.2)                                                               # actuator state bounds (rows 6, 7; state only)
+    row([(8, -1.0)], 1.2)
+    row([(9, -1.0), (0, -0.5)], 1.7)                                                   # mixed row 8: u1 + 0.5 p1 <= 1.7
+    row([(7, 1.0)], 1.5)                                                               # |v4| <= 1.5 (rows 9, 10)
+    row([(7, -1.0)], 1.5)
+    for i in range(ns):                                                                # us >= 0 (rows 11..13; preprocessing.py:110-112)
+        row([(nzm + i, 1.0)], 0.0)
+    slacked = [7, 2, 12]                                                               # a <= 1.2, u2 >= -0.3, us_1 >= 0: active on the reference
+    for j, i in enumerate(slacked):                                                    # h_i + usc_j >= 0 (preprocessing.py:140-150)
+        rows[i][0][nzm + ns + j] = 1.0
+    for j in range(nsc):                                                               # usc >= 0 (rows 14..16)
+        row([(nzm + ns + j, 1.0)], 0.0)
+    C = np.array([r for r, _ in rows])
+    cc = np.array([c0 for _, c0 in rows])
+    return dict(model=model, cost=card["cost"], C=C, c=cc, period=40, N=20, term_idx=[1, 2, 4, 5, 6, 7, 8], slacked=slacked,
+                gnl_x_idx=[0], w_guess=card["w_guess"])
+
+
+def awe9_problem(stage_F, N=None, hessian_approximation="exact"):
+    """Reference trajectory, tuning and multipliers of the awe9 stand-in (see `awe9`): simulate the forced response until it is
+    periodic, then pick multipliers on the active rows and the gradient q that makes the reference a KKT point."""
+    import sympy as sp
+    from .problem import MpcProblem
+    cfg = awe9()
+    model = cfg["model"]
+    nx, nu, ns, nsc, P = 9, 3, 3, 3, cfg["period"]
+    nzm, nzr = nx + nu, nx + nu + ns
+    z = list(model.x) + list(model.u)
+    gf = sp.lambdify([z], sp.Matrix(model.gnl), "numpy")
+    gj = sp.lambdify([z], sp.Matrix(model.gnl).jacobian(z), "numpy")
+    # a+ = (1 - gam) a + gam u3 exactly (the actuator state is a decoupled linear lag)
+    _, S0 = stage_F(np.zeros((1, nx)), np.zeros((1, nu)), 1)
+    gam = S0[0][8, 11]
+    x = np.array([0.3, 0.6, 0.8, 1.0, 0, 0, 0, 0, 0.3])
+    ph = 2 * np.pi * np.arange(P) / P
+    for per in range(80):
+        X, U = [], []
+        for k in range(P):
+            u1 = min(0.75 + 0.6 * np.sin(ph[k]), 1.25 / (1 + 0.3 * x[0]))             # rides the nonlinear constraint n1
+            u2 = max(0.4 * np.sin(ph[k] + 2.0), -0.3)                                  # rides its lower bound
+            u3 = 0.45 + 1.0 * np.sin(ph[k] + 4.0)
+            if (1 - gam) * x[8] + gam * u3 > 1.2:                                      # a rides its upper bound
+                u3 = (1.2 - (1 - gam) * x[8]) / gam
+            uk = np.array([u1, u2, u3])
+            X.append(x.copy()); U.append(uk)
+            x = stage_F(x[None, :], uk[None, :], 0)[0]
+        if per > 20 and np.max(np.abs(x - X[0])) < 1e-13:
+            break
+    X, U = np.array(X), np.array(U)
+    us = np.array([np.asarray(gf(list(np.concatenate([X[k], U[k]]))), dtype=np.float64).ravel() for k in range(P)])
+    us[np.abs(us) < 1e-12] = 0.0
+    wref = np.hstack([X, U, us])
+    C, c = cfg["C"], cfg["c"]
+    nh = C.shape[0]
+    # active rows on the reference and their multipliers (CasADi sign: active lower bound -> negative)
+    hval = np.array([C[:, :nzr] @ wref[k] + c for k in range(P)])
+    act = np.abs(hval[:, : nh - nsc]) < 1e-9
+    mu = {7: 0.5, 2: 0.3, 12: 0.4}
+    lam_h = np.zeros((P, nh - nsc))
+    for i, m_ in mu.items():
+        lam_h[act[:, i], i] = -m_ * (1.0 + 0.25 * np.cos(ph[act[:, i]]))
+    assert sorted(np.nonzero(act.any(axis=0))[0]) == sorted(cfg["slacked"]), np.nonzero(act.any(axis=0))[0]
+    lam_g = np.zeros((P, ns))
+    lam_g[:, 1] = lam_h[:, 12]                                # d/d us_1:  -lam_g + lam_(us>=0) = 0
+    q = np.zeros((P, nzr))
+    for k in range(P):
+        Jg = np.asarray(gj(list(wref[k, :nzm])), dtype=np.float64).reshape(ns, nzm)
+        q[k, :nzm] = -(Jg.T @ lam_g[k] + C[: nh - nsc, :nzm].T @ lam_h[k])
+    scost = np.array([1e3 * np.max(-lam_h[:, i]) for i in cfg["slacked"]])            # preprocessing.py:145
+    # tuning: positive definite, phase dependent
+    d0 = np.array([2, 2, 2, 4, .5, .5, .5, .5, .2, .2, .2, .1, .05, .05, .05])
+    vv = np.cos(0.7 * np.arange(nzr))
+    H = np.array([(1 + 0.2 * np.sin(ph[k])) * np.diag(d0) + 0.02 * np.outer(vv, vv) for k in range(P)])
+    xs, Ss = stage_F(X, U, 1)
+    N = cfg["N"] if N is None else N
+    pb = MpcProblem(name="awe9", nx=nx, nu=nu, N=N, p=P, wref=wref, H=H, q=q, C=C, c=c, lam_h_ref=lam_h,
+                    lam_dyn_ref=np.zeros((P, nx)), term_idx=list(cfg["term_idx"]), S_A=np.array(Ss[:, :, :nx]),
+                    S_B=np.array(Ss[:, :, nx:]), hessian_approximation=hessian_approximation, mpc_type="tuned",
+                    ns=ns, nsc=nsc, scost=scost, lam_g_ref=lam_g, gnl_x_idx=list(cfg["gnl_x_idx"]))
+    info = {"cfg": cfg, "periodicity_error": float(np.max(np.abs(x - X[0]))), "active": act, "hval": hval}
+    return pb, info
+
+
 def sample_x0(name, pb, B, seed=0):
     """synthetic initial states of SURVEY.md section 8(d): the reference examples' own perturbation recipes, seeded"""
     rng = np.random.default_rng(seed)
@@ -207,10 +316,13 @@ def sample_x0(name, pb, B, seed=0):
         return xs + np.array([0.4] * 4 + [0.6] * 4 + [0.3]) * rng.uniform(-1, 1, (B, pb.nx))
     if name == "unicycle":
         return xs + np.array([0.5, 0.1, 0.0, 0.0]) * rng.uniform(-1, 1, (B, pb.nx))   # examples/unicycle/main.py:172
+    if name == "awe9":
+        return xs + np.array([0.15] * 4 + [0.2] * 4 + [0.1]) * rng.uniform(-1, 1, (B, pb.nx))
     raise KeyError(name)
 
 
-CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle, "evaporation": evaporation, "chain": chain, "dims9": dims9}
+CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle, "evaporation": evaporation, "chain": chain, "dims9": dims9,
+           "awe9": awe9}
 
 
 def make_problem(name, stage_F, N=None, hessian_approximation="exact", mpc_type="tuned"):
@@ -223,6 +335,8 @@ def make_problem(name, stage_F, N=None, hessian_approximation="exact", mpc_type=
     from . import tuning
     from .problem import MpcProblem
 
+    if name == "awe9":
+        return awe9_problem(stage_F, N=N, hessian_approximation=hessian_approximation)
     cfg = CONFIGS[name]()
     model = cfg["model"]
     nx, nu = model.nx, model.nu

@@ -21,6 +21,13 @@
 #include <vector>
 #include "tmpc.h"
 #include "tmpc_core.cuh"
+// model-dimension region (see tmpc_core.cuh): NZ, NU = NZM, NUM for the linearisation kernels
+#pragma push_macro("NZ")
+#pragma push_macro("NU")
+#undef NZ
+#undef NU
+#define NZ TMPC_NZM
+#define NU TMPC_NUM
 #include "tmpc_lin2.cuh"
 
 // thread-per-instance QP kernel (tmpc_qp_thread.cu)
@@ -111,14 +118,14 @@ __global__ void __launch_bounds__(LIN3_THREADS, LIN3_MINB) k_lin3(TmProb P, TmSt
   const int64_t slot = t / P.N;
   const int64_t inst = list ? list[slot] : slot;
   if (trial && S.qpstat[inst] != 0) return;          // failed QP: keep LIN at W for the final statistics
-  const double* w = S.W + inst * P.n_w + (int64_t)k * NZ;
+  const double* w = S.W + inst * P.n_w + (int64_t)k * TM_NZS;
   double x[NX], u[NU], lam[NX];
 #pragma unroll
   for (int a = 0; a < NX; ++a) x[a] = w[a];
 #pragma unroll
   for (int b = 0; b < NU; ++b) u[b] = w[NX + b];
   if (trial) {
-    const double* d = S.D + inst * P.n_w + (int64_t)k * NZ;
+    const double* d = S.D + inst * P.n_w + (int64_t)k * TM_NZS;
 #pragma unroll
     for (int a = 0; a < NX; ++a) x[a] += d[a];
 #pragma unroll
@@ -130,6 +137,9 @@ __global__ void __launch_bounds__(LIN3_THREADS, LIN3_MINB) k_lin3(TmProb P, TmSt
   tm_lin_adjoint(x, u, EXACT ? 2 : 1, lam, S.LIN + (inst * P.N + k) * (int64_t)TM_LSZ);
 }
 #endif
+
+#pragma pop_macro("NU")
+#pragma pop_macro("NZ")
 
 __global__ void k_prefilter(TmProb P, TmState S) {
   const int64_t inst = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
@@ -267,8 +277,8 @@ __global__ void k_shift(TmProb P, TmState S, double* Ws, double* Ls) {
 
 __global__ void k_gather_u0(TmProb P, TmState S, double* U0) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= S.B * NU) return;
-  U0[t] = S.W[(t / NU) * P.n_w + NX + (t % NU)];
+  if (t >= S.B * NUM) return;
+  U0[t] = S.W[(t / NUM) * P.n_w + NX + (t % NUM)];
 }
 
 __global__ void k_bcast(double* dst, const double* row, int64_t B, int n) {
@@ -280,11 +290,11 @@ __global__ void k_bcast(double* dst, const double* row, int64_t B, int n) {
 __global__ void k_plant(const double* X, const double* U, int64_t B, double* Xn) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  double x[NX], u[NU], xf[NX], t1[NX], t2[NX], t3[NX];
+  double x[NX], u[NUM], xf[NX], t1[NX], t2[NX], t3[NX];
 #pragma unroll
   for (int a = 0; a < NX; ++a) x[a] = X[b * NX + a];
 #pragma unroll
-  for (int a = 0; a < NU; ++a) u[a] = U[b * NU + a];
+  for (int a = 0; a < NUM; ++a) u[a] = U[b * NUM + a];
   tm_integrate<0>(x, u, 0, 0, xf, t1, t2, t3);
 #pragma unroll
   for (int a = 0; a < NX; ++a) Xn[b * NX + a] = xf[a];
@@ -298,9 +308,14 @@ __global__ void k_stage_log(const double* X, const double* U, int64_t B, const d
   if (b >= B) return;
   double z[NZ];
 #pragma unroll
+  for (int a = 0; a < NZ; ++a) z[a] = 0.0;
+#pragma unroll
   for (int a = 0; a < NX; ++a) z[a] = X[b * NX + a];
 #pragma unroll
-  for (int a = 0; a < NU; ++a) z[NX + a] = U[b * NU + a];
+  for (int a = 0; a < NUM; ++a) z[NX + a] = U[b * NUM + a];
+#if NS > 0
+  tmpc_gnl(z, z + NX, z + NZM);                     // us = h_nl(x,u): the logged rows us >= 0 are the nonlinear constraints themselves
+#endif
   if (l_out) l_out[b] = tmpc_stage_cost(z, z + NX);
   if (h_out) {
     for (int i = 0; i < nh; ++i) {
@@ -399,10 +414,15 @@ void tmpc_default_opts(tmpc_opts* o) {
 
 const char* tmpc_model_info(int32_t* nx, int32_t* nu, int32_t* rk_steps, double* dt) {
   if (nx) *nx = NX;
-  if (nu) *nu = NU;
+  if (nu) *nu = NUM;
   if (rk_steps) *rk_steps = TMPC_DISCRETE ? 0 : TMPC_RK_STEPS;
   if (dt) *dt = TMPC_RK_DT;
   return TMPC_MODEL_NAME;
+}
+
+void tmpc_model_slacks(int32_t* ns, int32_t* nsc) {
+  if (ns) *ns = NS;
+  if (nsc) *nsc = NSC;
 }
 
 const char* tmpc_last_error(const tmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -414,9 +434,14 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
   h->device = device;
   h->dims = *dims;
   if (opts) h->opts = *opts; else tmpc_default_opts(&h->opts);
-  if (dims->nx != NX || dims->nu != NU) {
-    fprintf(stderr, "tmpc_create: dims (%d,%d) do not match compiled model %s (%d,%d)\n", dims->nx, dims->nu,
-            TMPC_MODEL_NAME, NX, NU);
+  if (dims->nx != NX || dims->nu != NUM || dims->ns != NS || dims->nsc != NSC) {
+    fprintf(stderr, "tmpc_create: dims (nx %d, nu %d, ns %d, nsc %d) do not match compiled model %s (%d, %d, %d, %d)\n", dims->nx,
+            dims->nu, dims->ns, dims->nsc, TMPC_MODEL_NAME, NX, NUM, NS, NSC);
+    delete h;
+    return 2;
+  }
+  if (opts && opts->economic && (NS > 0 || NSC > 0)) {
+    fprintf(stderr, "tmpc_create: the economic stage cost is defined on (x,u) only: no slack variables\n");
     delete h;
     return 2;
   }
@@ -432,7 +457,7 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
   TmProb& P = h->P;
   P.N = dims->N; P.nh = dims->nh; P.nxt = dims->nx_term; P.p = dims->p;
   P.n_w = dims->N * NZ + NX;
-  P.n_g = NX + dims->N * (NX + dims->nh) + dims->nx_term;
+  P.n_g = NX + dims->N * (NX + NS + dims->nh) + dims->nx_term;
   P.economic = h->opts.economic ? 1 : 0;
   P.hessian_exact = (h->opts.hessian_exact || P.economic) ? 1 : 0;   // economic MPC: exact Hessian forced (pmpc.py:97-107)
   P.filter_cap = 64;                      // rows of the pruned filter (tm_post): bounds memory, not the iteration count
@@ -610,7 +635,7 @@ int tmpc_set_tables(tmpc_handle* h, const double* wref, const double* H, const d
     for (int k = 0; k < P.N; ++k)
       for (int i = 0; i < P.nh; ++i) {
         if (k == 0 && relax0[i]) continue;
-        if (fabs(ref_du[(size_t)ph * P.n_g + NX + (size_t)k * (NX + P.nh) + NX + i]) >= h->opts.lam_tresh) h->phase_clean[ph] = 0;
+        if (fabs(ref_du[(size_t)ph * P.n_g + tm_gh(P, k) + i]) >= h->opts.lam_tresh) h->phase_clean[ph] = 0;
       }
   h->tables_set = true;
   return 0;
@@ -819,7 +844,7 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   }
   // outputs, then the warm-start shift (pmpc.py:410-423)
   const size_t b = (size_t)B;
-  if (U0_dev) { k_gather_u0<<<(unsigned)((B * NU + 255) / 256), 256, 0, st>>>(P, S, U0_dev); ++launches; }
+  if (U0_dev) { k_gather_u0<<<(unsigned)((B * NUM + 255) / 256), 256, 0, st>>>(P, S, U0_dev); ++launches; }
   if (W_dev) CK(cudaMemcpyAsync(W_dev, S.W, b * P.n_w * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if (LAM_dev) CK(cudaMemcpyAsync(LAM_dev, S.LAM, b * P.n_g * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if (G_dev) CK(cudaMemcpyAsync(G_dev, S.G, b * P.n_g * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -869,7 +894,7 @@ int tmpc_step_host(tmpc_handle* h, const double* X0_host, int64_t B, double* U0_
   double *Wsol = h->S.W, *Lsol = h->S.LAM;
   if (tmpc_step(h, h->X0buf, B, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) return 1;
   // after the swap the solution buffers are h->Wsh / h->Lsh (== Wsol / Lsol)
-  if (U0_host) CK(cudaMemcpy2D(U0_host, NU * sizeof(double), Wsol + NX, P.n_w * sizeof(double), NU * sizeof(double), b,
+  if (U0_host) CK(cudaMemcpy2D(U0_host, NUM * sizeof(double), Wsol + NX, P.n_w * sizeof(double), NUM * sizeof(double), b,
                                cudaMemcpyDeviceToHost));
   if (W_host) CK(cudaMemcpy(W_host, Wsol, b * P.n_w * sizeof(double), cudaMemcpyDeviceToHost));
   if (LAM_host) CK(cudaMemcpy(LAM_host, Lsol, b * P.n_g * sizeof(double), cudaMemcpyDeviceToHost));
@@ -927,12 +952,15 @@ int tmpc_get_timing(const tmpc_handle* h, double out_ms[4]) {
 int tmpc_stage_eval_host(int32_t n, const double* x, const double* u, int32_t order, double* xf, double* S, double* T) {
   for (int s = 0; s < n; ++s) {
     const double* xs = x + (size_t)s * NX;
-    const double* us = u + (size_t)s * NU;
+    const double* us = u + (size_t)s * NUM;
     if (order == 0) {
       double t1[NX], t2[NX], t3[NX];
       tm_integrate<0>(xs, us, 0, 0, xf + (size_t)s * NX, t1, t2, t3);
       continue;
     }
+#pragma push_macro("NZ")
+#undef NZ
+#define NZ TMPC_NZM
     for (int i = 0; i < NZ; ++i)
       for (int j = i; j < NZ; ++j) {
         if (order == 1 && j != i) continue;
@@ -948,6 +976,7 @@ int tmpc_stage_eval_host(int32_t n, const double* x, const double* u, int32_t or
           }
         }
       }
+#pragma pop_macro("NZ")
   }
   return 0;
 }

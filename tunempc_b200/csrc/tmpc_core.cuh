@@ -87,11 +87,26 @@ TM_HD TmP tm_mkp(double* base, size_t off) { return base + off; }
 #endif
 typedef double* TmL;    // plain pointer in every mode (shared memory / host memory / thread-local scratch)
 
+// Stage variables z_k = (x, u, us, usc) (tunempc/pmpc.py:217-235).  NU / NZ count every free variable of a stage block; the
+// dynamics and the slacked nonlinear constraints depend on (x, u) only: NUM model inputs, NZM = NX + NUM.  Without slacks
+// (NS = NSC = 0) the two coincide.  The linearisation code below is written against the model dimensions (NZ, NU are
+// re-defined to NZM, NUM inside that region); TM_NZS is the stride of a stage block in W / D everywhere.
+#ifndef TMPC_NUM
+#define TMPC_NUM TMPC_NU
+#define TMPC_NZM TMPC_NZ
+#define TMPC_NS 0
+#define TMPC_NSC 0
+#endif
 #define NX TMPC_NX
 #define NU TMPC_NU
 #define NZ TMPC_NZ
-#define TM_NPAIR (NZ * (NZ + 1) / 2)
-#define TM_LSZ (NX + NX * NZ + TM_NPAIR)   /* per-stage linearisation record: xf | S row-major nx*nz | W packed i<=j */
+#define NUM TMPC_NUM
+#define NZM TMPC_NZM
+#define NS TMPC_NS
+#define NSC TMPC_NSC
+#define TM_NZS TMPC_NZ
+#define TM_NPAIR (NZM * (NZM + 1) / 2)
+#define TM_LSZ (NX + NX * NZM + TM_NPAIR)   /* per-stage linearisation record: xf | S row-major nx*nzm | W packed i<=j (model variables) */
 #define TM_INF 1e300
 #define TM_NCNT 24
 #define TM_ALW 12  /* words of the augmented-Lagrangian row mask: supports N*nh <= 384 */
@@ -135,9 +150,20 @@ struct TmState {
   unsigned long long* counters;   // TM_NCNT: [0] iterations [4] ls dynamics evals [5] QP attempts [6] active-set iterations [7] Riccati solves [8..19] attempt histogram
 };
 
-TM_HD int tm_gdyn(const TmProb& P, int k) { return NX + k * (NX + P.nh); }
-TM_HD int tm_gh(const TmProb& P, int k) { return NX + k * (NX + P.nh) + NX; }
-TM_HD int tm_gterm(const TmProb& P) { return NX + P.N * (NX + P.nh); }
+// g = [init(nx) | k < N: dyn_k(nx), g_k(ns), h_k(nh) | term(nx_term)]   (tunempc/pmpc.py:242-256,279-287)
+#define TM_GS(P) (NX + NS + (P).nh)     /* rows per stage */
+TM_HD int tm_gdyn(const TmProb& P, int k) { return NX + k * TM_GS(P); }
+TM_HD int tm_gg(const TmProb& P, int k) { return NX + k * TM_GS(P) + NX; }
+TM_HD int tm_gh(const TmProb& P, int k) { return NX + k * TM_GS(P) + NX + NS; }
+TM_HD int tm_gterm(const TmProb& P) { return NX + P.N * TM_GS(P); }
+
+// ---- model-dimension region: NZ, NU mean NZM, NUM down to the matching pop_macro ------------------------------------
+#pragma push_macro("NZ")
+#pragma push_macro("NU")
+#undef NZ
+#undef NU
+#define NZ TMPC_NZM
+#define NU TMPC_NUM
 
 TM_HD void tm_pair_ij(int pr, int& i, int& j) {   // packed upper-triangular index -> (i<=j), row-major
   int r = 0, rem = pr;
@@ -662,7 +688,7 @@ TM_HD int tm_lin_tasks_per_stage(int hessian_exact) { return hessian_exact ? TM_
 
 // one linearisation task.  trial = 1: evaluate at (W + D, LAMQ), else at (W, LAM).  g = group id.
 TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, int g, int trial) {
-  const double* w = S.W + inst * P.n_w + (int64_t)k * NZ;
+  const double* w = S.W + inst * P.n_w + (int64_t)k * TM_NZS;
   double x[NX], u[NU];
 #pragma unroll
   for (int a = 0; a < NX; ++a) x[a] = w[a];
@@ -670,7 +696,7 @@ TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, i
   for (int b = 0; b < NU; ++b) u[b] = w[NX + b];
   if (trial && S.qpstat[inst] != 0) return;   // failed QP: keep LIN at W for the final statistics
   if (trial) {
-    const double* d = S.D + inst * P.n_w + (int64_t)k * NZ;
+    const double* d = S.D + inst * P.n_w + (int64_t)k * TM_NZS;
 #pragma unroll
     for (int a = 0; a < NX; ++a) x[a] += d[a];
 #pragma unroll
@@ -755,22 +781,26 @@ TM_HD void tm_lin_task(const TmProb& P, const TmState& S, int64_t inst, int k, i
   } else {
     switch (g) {
       case 0: tm_lin_group_gn<0>(x, u, rec); break;
-#if (TMPC_NZ > 3)
+#if (TMPC_NZM > 3)
       case 1: tm_lin_group_gn<1>(x, u, rec); break;
 #endif
-#if (TMPC_NZ > 6)
+#if (TMPC_NZM > 6)
       case 2: tm_lin_group_gn<2>(x, u, rec); break;
 #endif
-#if (TMPC_NZ > 9)
+#if (TMPC_NZM > 9)
       case 3: tm_lin_group_gn<3>(x, u, rec); break;
 #endif
-#if (TMPC_NZ > 12)
+#if (TMPC_NZM > 12)
 #error "more than 4 Gauss-Newton groups: extend the dispatch in tm_lin_task"
 #endif
       default: break;
     }
   }
 }
+
+#pragma pop_macro("NU")
+#pragma pop_macro("NZ")
+// ---- end of the model-dimension region ----------------------------------------------------------------------------
 
 #include "tmpc_qp.cuh"
 
@@ -825,6 +855,18 @@ TM_HD void tm_eval_point(const TmProb& P, const TmState& S, int64_t inst, double
       viol = fmax(viol, fabs(rdy));
       if (gout) gout[tm_gdyn(P, k) + a] = rdy;
     }
+#if NS > 0
+    {                                                     // g_k = h_nl(x_k, u_k) - us_k = 0   (preprocessing.py:107-108, pmpc.py:270-271)
+      double gv[NS];
+      tmpc_gnl(z, z + NX, gv);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const double v = gv[i] - z[NZM + i];
+        viol = fmax(viol, fabs(v));
+        if (gout) gout[tm_gg(P, k) + i] = v;
+      }
+    }
+#endif
     for (int i = 0; i < nh; ++i) {
       double v = P.c[i];
 #pragma unroll
@@ -875,9 +917,19 @@ TM_HD double tm_dual_infeas(const TmProb& P, const TmState& S, int64_t inst) {
     if (P.economic) {
       double z[NZ];
 #pragma unroll
-      for (int b = 0; b < NZ; ++b) z[b] = w[k * NZ + b];
+      for (int b = 0; b < NZ; ++b) { z[b] = w[k * NZ + b]; gl[b] = 0.0; }
       tmpc_cost_grad(z, z + NX, gl);
     }
+#if NS > 0
+    double Jg[NS * NZM];
+    const double* lg = lam + tm_gg(P, k);
+    {
+      double z[NZ], gv[NS];
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) z[b] = w[k * NZ + b];
+      tmpc_gnl_jac(z, z + NX, gv, Jg);
+    }
+#endif
 #pragma unroll
     for (int a = 0; a < NZ; ++a) {
       double v = P.economic ? gl[a] : qk[a];
@@ -885,8 +937,16 @@ TM_HD double tm_dual_infeas(const TmProb& P, const TmState& S, int64_t inst) {
 #pragma unroll
         for (int b = 0; b < NZ; ++b) v += Hk[a * NZ + b] * dz[b];
       }
+      if (a < NZM) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) v += AB[i * NZ + a] * ld[i];
+        for (int i = 0; i < NX; ++i) v += AB[i * NZM + a] * ld[i];
+      }
+#if NS > 0
+      if (a < NZM) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) v += Jg[i * NZM + a] * lg[i];
+      } else if (a < NZM + NS) v -= lg[a - NZM];
+#endif
       for (int i = 0; i < nh; ++i) v += P.C[(size_t)i * NZ + a] * lh[i];
       if (a < NX) v += (k == 0) ? lam[a] : -lam[tm_gdyn(P, k - 1) + a];
       mx = fmax(mx, fabs(v));
@@ -1057,7 +1117,7 @@ TM_HD void tm_post(const TmProb& P, const TmState& S, int64_t inst) {
 
 // warm-start shift (pmpc.py:867-906): (W, LAM) -> (Ws, Ls); one warp per instance
 TM_HD void tm_shift(const TmProb& P, const double* w, const double* lam, double* ws, double* ls) {
-  const int N = P.N, nh = P.nh;
+  const int N = P.N;
   const int lane = TM_LANE;
   for (int e = lane; e < P.n_w; e += TM_NL) {
     int k = e / NZ, o = e % NZ;
@@ -1072,9 +1132,9 @@ TM_HD void tm_shift(const TmProb& P, const double* w, const double* lam, double*
     if (e < NX) v = lam[tm_gdyn(P, 0) + e];                          // init <- dyn_0
     else if (e >= tm_gterm(P)) v = lam[e];                           // term kept
     else {
-      int k = (e - NX) / (NX + nh), o = (e - NX) % (NX + nh);
+      int k = (e - NX) / TM_GS(P), o = (e - NX) % TM_GS(P);
       int ksrc = (k < N - 1) ? k + 1 : N - 1;                        // last stage duplicated
-      v = lam[NX + ksrc * (NX + nh) + o];
+      v = lam[NX + ksrc * TM_GS(P) + o];
     }
     ls[e] = v;
   }
@@ -1299,6 +1359,7 @@ TM_HD void tm_pd_check(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     if (k == 0 && P.relax0[i]) continue;
     if (lam[tm_gh(P, k) + i] != 0.0) tm_mask_set(mask, e);
   }
+  tm_pin_soft_slacks(P, mask);
   tm_qp_setup(P, S, inst, ws, P.hessian_exact);
   double qmax = 0.0;
   for (int e = TM_LANE; e < P.N * NZ; e += TM_NL) { const int k = e / NZ, i = e % NZ; qmax = fmax(qmax, fabs(ws.Q[(size_t)k * NZ * NZ + i * NZ + i])); }

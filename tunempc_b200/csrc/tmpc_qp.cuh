@@ -39,6 +39,7 @@ struct TmQpWs {
   TmP kk, d, y, rhs;                      // feed-forward of the current sweep; step, correction, right-hand side
   TmP sl, Mc, Lf, cA, rv, nu, acts, acte, sc;   // dual active set: row values, dual-Hessian columns, Schur factor, members
   TmP Ew, tr, lh, sl0;                    // scratch: elimination rows; terminal residual; row multipliers; row values of a held solution
+  TmP Cg, gv;                             // slacked nonlinear rows g_k = h_nl(x,u) - us = 0: Jacobian w.r.t. (x,u) N*NS*NZM, values N*NS
   TmL F, f, PAB, pv;                      // per-stage scratch of the factorisation: KKT block, gradient, products, vectors (thread mode: thread-local)
 };
 
@@ -57,7 +58,8 @@ TM_HD size_t tm_qpws_doubles(int N, int nh, int nxt, int M) {
   n += (size_t)(N + 1) * NX * NX + (size_t)(N + 1) * NX + (size_t)(N + 1);                             // Gc gc ncs
   n += (size_t)N * NV + 3 * (size_t)(N + 1) * NZ;                                                      // kk d y rhs
   n += NI + (size_t)(M + 1) * NI + (size_t)M * (M + 1) / 2 + 5 * (size_t)M + 8;                                  // sl Mc Lf cA rv nu acts acte sc
-  n += (size_t)(NX + nh) * TM_ES + NZ * NZ + NZ + NX * NZ + 4 * NX + (nxt > 0 ? nxt : 1) + 2 * NI;     // Ew F f PAB pv tr lh sl0
+  n += (size_t)(NX + NS + nh) * TM_ES + NZ * NZ + NZ + NX * NZ + 4 * NX + (nxt > 0 ? nxt : 1) + 2 * NI;     // Ew F f PAB pv tr lh sl0
+  n += (size_t)N * NS * NZM + (size_t)N * NS;                                                         // Cg gv
   return n;
 }
 
@@ -96,7 +98,7 @@ TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s,
   TM_CARVE(acts, M);
   TM_CARVE(acte, M);
   TM_CARVE(sc, 8);
-  TM_CARVE(Ew, (size_t)(NX + nh) * TM_ES);
+  TM_CARVE(Ew, (size_t)(NX + NS + nh) * TM_ES);
 #ifndef TM_WS_STRIDE
   TM_CARVE(F, NZ * NZ);
   TM_CARVE(f, NZ);
@@ -108,6 +110,8 @@ TM_HD void tm_qpws_carve(double* base, int N, int nh, int nxt, int M, TmQpWs& s,
   TM_CARVE(tr, (nxt > 0 ? nxt : 1));
   TM_CARVE(lh, NI);
   TM_CARVE(sl0, NI);
+  TM_CARVE(Cg, (size_t)N * NS * NZM);
+  TM_CARVE(gv, (size_t)N * NS);
 #undef TM_CARVE
 }
 
@@ -449,6 +453,14 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
       s.Ew[i * TM_ES + c] = v;
     }
     int nr = ncn;
+#if NS > 0
+    for (int i = 0; i < NS; ++i) {                    // equality rows  Jg_k,i (dx,du) - dus_i + g_k,i = 0: always held
+      TM_UNROLL_T
+      for (int c = lane; c <= NZ; c += TM_NL)
+        s.Ew[nr * TM_ES + c] = (c == NZ) ? s.gv[k * NS + i] : (c < NZM ? s.Cg[((size_t)k * NS + i) * NZM + c] : (c == NZM + i ? -1.0 : 0.0));
+      ++nr;
+    }
+#endif
     for (int i = 0; i < nh; ++i) {
       if (!tm_mask_get(amask, k * nh + i)) continue;
       TM_UNROLL_T
@@ -1118,6 +1130,12 @@ TM_HD void tm_qp_recover_stage(const TmProb& P, TmQpWs& s, const unsigned* amask
     }
     rid[nr++] = -1 - q;
   }
+#if NS > 0
+  for (int i = 0; i < NS && nr < NZ; ++i) {
+    for (int c = 0; c < NZ; ++c) Er[nr * NZ + c] = c < NZM ? s.Cg[((size_t)k * NS + i) * NZM + c] : (c == NZM + i ? -1.0 : 0.0);
+    rid[nr++] = 100000 + i;
+  }
+#endif
   for (int i = 0; i < nh && nr < NZ; ++i) {
     if (!tm_mask_get(amask, k * nh + i)) continue;
     for (int c = 0; c < NZ; ++c) Er[nr * NZ + c] = P.C[(size_t)i * NZ + c];
@@ -1184,6 +1202,7 @@ TM_HD void tm_qp_recover_stage(const TmProb& P, TmQpWs& s, const unsigned* amask
   for (int q = 0; q < NX; ++q) nu_next[q] = 0.0;
   for (int i = 0; i < nr; ++i) {
     if (rid[i] < 0) nu_next[-1 - rid[i]] = et[i];
+    else if (rid[i] >= 100000) lq[tm_gg(P, k) + rid[i] - 100000] = et[i];
     else lq[tm_gh(P, k) + rid[i]] = et[i];
   }
   for (int i = 0; i < NX; ++i) {                      // lam_{k+1} = multiplier of dynamics row k
@@ -1233,7 +1252,10 @@ TM_HD void tm_qp_setup(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   const int lane = TM_LANE;
   const double* w = S.W + inst * P.n_w;
   const double* lin = S.LIN + inst * P.N * (int64_t)TM_LSZ;
-  for (int e = lane; e < N * NX * NZ; e += TM_NL) { int k = e / (NX * NZ), o = e % (NX * NZ); s.AB[e] = lin[(size_t)k * TM_LSZ + NX + o]; }
+  for (int e = lane; e < N * NX * NZ; e += TM_NL) {   // [A B 0]: the slack columns of the dynamics are zero
+    int k = e / (NX * NZ), o = e % (NX * NZ), i = o / NZ, c = o % NZ;
+    s.AB[e] = c < NZM ? lin[(size_t)k * TM_LSZ + NX + i * NZM + c] : 0.0;
+  }
   for (int e = lane; e < N * NX; e += TM_NL) { int k = e / NX, a = e % NX; s.b[e] = lin[(size_t)k * TM_LSZ + a] - w[(k + 1) * NZ + a]; }
   if (P.economic) {
     // economic stage cost: Q_k = d2l/dz2 (+ lam' d2F), r_k = dl/dz at the iterate
@@ -1246,7 +1268,7 @@ TM_HD void tm_qp_setup(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
       for (int i = 0; i < NZ; ++i) {
         for (int j = 0; j < NZ; ++j) {
           double v = 0.5 * (Hl[i * NZ + j] + Hl[j * NZ + i]);
-          if (use_exact) v += lin[(size_t)k * TM_LSZ + NX + NX * NZ + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
+          if (use_exact) v += lin[(size_t)k * TM_LSZ + NX + NX * NZM + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
           s.Q[(size_t)k * NZ * NZ + i * NZ + j] = v;
         }
         s.r[k * NZ + i] = gl[i];
@@ -1257,7 +1279,7 @@ TM_HD void tm_qp_setup(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
       int k = e / (NZ * NZ), o = e % (NZ * NZ), i = o / NZ, j = o % NZ;
       int ph = (S.phase + k) % P.p;
       double v = P.H[(size_t)ph * NZ * NZ + o];
-      if (use_exact) v += lin[(size_t)k * TM_LSZ + NX + NX * NZ + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
+      if (use_exact && i < NZM && j < NZM) v += lin[(size_t)k * TM_LSZ + NX + NX * NZM + (i <= j ? tm_pair_idx(i, j) : tm_pair_idx(j, i))];
       s.Q[e] = v;
     }
     for (int e = lane; e < N * NZ; e += TM_NL) {
@@ -1272,6 +1294,24 @@ TM_HD void tm_qp_setup(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
     }
   }
   for (int a = lane; a < NZ; a += TM_NL) s.r[N * NZ + a] = 0.0;
+#if NS > 0
+  // slacked nonlinear rows at the iterate: value h_nl(x_k,u_k) - us_k, Jacobian, and (exact Hessian) lam_g' d2 h_nl added to Q
+  TM_SYNC();
+  for (int k = lane; k < N; k += TM_NL) {
+    double z[NZ], gvl[NS], Jg[NS * NZM];
+#pragma unroll
+    for (int b = 0; b < NZ; ++b) z[b] = w[k * NZ + b];
+    tmpc_gnl_jac(z, z + NX, gvl, Jg);
+    for (int i = 0; i < NS; ++i) s.gv[k * NS + i] = gvl[i] - z[NZM + i];
+    for (int e = 0; e < NS * NZM; ++e) s.Cg[(size_t)k * NS * NZM + e] = Jg[e];
+    if (use_exact) {
+      double Hg[NZM * NZM];
+      tmpc_gnl_hess(z, z + NX, S.LAM + inst * P.n_g + tm_gg(P, k), Hg);
+      for (int i = 0; i < NZM; ++i)
+        for (int j = 0; j < NZM; ++j) s.Q[(size_t)k * NZ * NZ + i * NZ + j] += 0.5 * (Hg[i * NZM + j] + Hg[j * NZM + i]);
+    }
+  }
+#endif
   for (int e = lane; e < N * nh; e += TM_NL) {
     int k = e / nh, i = e % nh;
     double v = P.c[i];
@@ -1288,16 +1328,49 @@ TM_HD void tm_qp_setup(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   TM_SYNC();
 }
 
+// Soft-constraint slacks have no curvature (pmpc.py:327-339: zero Hessian block, linear cost scost > 0), so every QP solution
+// has, per stage and slack j, the row usc_j >= 0 or the softened row h_i + usc_j >= 0 active.  The base problem must be
+// strictly convex on its null space: where the multipliers hold neither of the two (the dual reference after the stage-0
+// relaxation pmpc.py:293-294 with its h_us_idx pointing into the usc rows, the shifted warm start, an emptied working set),
+// one of them is added to the base -- usc_j >= 0, or the softened row where usc_j >= 0 is relaxed.  Its multiplier comes
+// back with the right sign (-scost), or the usual release / re-solve logic takes over.
+TM_HD void tm_pin_soft_slacks(const TmProb& P, unsigned* mask) {
+#if NSC > 0
+  const int nh = P.nh;
+  for (int j = 0; j < NSC; ++j) {
+    const int es = nh - NSC + j;
+    int er = -1;
+    for (int i = 0; i < nh - NSC; ++i) if (P.C[(size_t)i * NZ + NZM + NS + j] != 0.0) { er = i; break; }
+    for (int k = 0; k < P.N; ++k) {
+      const int rel_s = (k == 0 && P.relax0[es]), rel_r = (er < 0) || (k == 0 && P.relax0[er]);
+      const int has_s = !rel_s && tm_mask_get(mask, k * nh + es), has_r = !rel_r && tm_mask_get(mask, k * nh + er);
+      if (has_s || has_r) continue;
+      if (!rel_s) tm_mask_set(mask, k * nh + es);
+      else if (!rel_r) tm_mask_set(mask, k * nh + er);
+    }
+  }
+#else
+  (void)P; (void)mask;
+#endif
+}
+
 // One QP with the base rows in amask.  returns 0 ok (step and multipliers in dout / lq, wrong-sign base rows reported
 // in nwrong / amask_next), 2 infeasible, 3 base not positive definite, 6 base rows inconsistent, 7 working-set overflow.
 // amask_next = base rows with a correctly signed multiplier + the rows the dual active set added: the working set a
 // re-solve starts from.
-TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& s, const unsigned* amask,
+TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& s, const unsigned* amask_in,
                        unsigned* amask_next, int& nwrong, int& n_gi_out, const TmQpPert* pert = nullptr, int eq_only = 0,
                        double rho_scale = 1.0) {
   const int N = P.N, nh = P.nh, nxt = P.nxt;
   const int lane = TM_LANE;
   const int NI = N * nh;
+#if NSC > 0
+  unsigned amask[TM_ALW];
+  for (int wd = 0; wd < TM_ALW; ++wd) amask[wd] = amask_in[wd];
+  tm_pin_soft_slacks(P, amask);
+#else
+  const unsigned* amask = amask_in;
+#endif
   TmL e0 = s.pv + 2 * NX;
   if (pert) {
     if (pert->homog) {

@@ -20,14 +20,14 @@ _ip = ctypes.POINTER(ctypes.c_int32)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-shared", "-Xcompiler", "-fPIC",
               "-std=c++17"]
 
-EXPORTS = ["tmpc_default_opts", "tmpc_model_info", "tmpc_create", "tmpc_destroy", "tmpc_last_error",
+EXPORTS = ["tmpc_default_opts", "tmpc_model_info", "tmpc_model_slacks", "tmpc_create", "tmpc_destroy", "tmpc_last_error",
            "tmpc_set_tables", "tmpc_reset", "tmpc_get_index", "tmpc_step", "tmpc_step_host", "tmpc_plant_step", "tmpc_stage_log",
            "tmpc_get_log", "tmpc_get_counters", "tmpc_get_timing", "tmpc_stage_eval_host", "tmpc_fp64_peak"]
 
 
 class TmpcDims(ctypes.Structure):
     _fields_ = [("nx", ctypes.c_int32), ("nu", ctypes.c_int32), ("nh", ctypes.c_int32), ("nx_term", ctypes.c_int32),
-                ("N", ctypes.c_int32), ("p", ctypes.c_int32)]
+                ("N", ctypes.c_int32), ("p", ctypes.c_int32), ("ns", ctypes.c_int32), ("nsc", ctypes.c_int32)]
 
 
 class TmpcOpts(ctypes.Structure):
@@ -46,7 +46,7 @@ def build_model_lib(name, force=False, verbose=False):
     out = lib_path(name)
     srcs = [os.path.join(_PKG, "csrc", "tmpc.cu"), os.path.join(_PKG, "csrc", "tmpc_qp_thread.cu"),
             os.path.join(_PKG, "csrc", "tmpc_core.cuh"), os.path.join(_PKG, "csrc", "tmpc_lin2.cuh"),
-            os.path.join(_PKG, "csrc", "tmpc_qp.cuh"),
+            os.path.join(_PKG, "csrc", "tmpc_qp.cuh"), os.path.join(_PKG, "csrc", "tmpc_lin3.cuh"),
             os.path.join(_PKG, "csrc", "gen", "model_%s.h" % name), os.path.join(_ROOT, "include", "tmpc.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
         return out
@@ -92,8 +92,13 @@ class ModelLib:
         nx, nu, st = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         dt = ctypes.c_double()
         self.model_name = L.tmpc_model_info(ctypes.byref(nx), ctypes.byref(nu), ctypes.byref(st), ctypes.byref(dt)).decode()
-        self.nx, self.nu, self.nz = nx.value, nu.value, nx.value + nu.value
+        self.nx, self.nu, self.nz = nx.value, nu.value, nx.value + nu.value       # model dimensions (x, u)
         self.rk_steps, self.dt = st.value, dt.value
+        ns, nsc = ctypes.c_int32(), ctypes.c_int32()
+        L.tmpc_model_slacks.argtypes = [_ip, _ip]
+        L.tmpc_model_slacks.restype = None
+        L.tmpc_model_slacks(ctypes.byref(ns), ctypes.byref(nsc))
+        self.ns, self.nsc = ns.value, nsc.value
 
     def default_opts(self):
         o = TmpcOpts()

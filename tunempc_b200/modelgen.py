@@ -58,6 +58,10 @@ class OdeModel:
     integrator: str = "rk4"  # 'rk4' (CasADi 'rk') or 'collocation' (CasADi 'collocation': Radau IIA, 3 nodes per element)
     hess_nz: List[tuple] = field(default_factory=list)
     cost: object = None      # economic stage cost l(x,u) (sympy), emitted as tmpc_stage_cost for the closed-loop log
+    gnl: Sequence[sp.Expr] = ()   # nonlinear path constraints h_nl(x,u) >= 0: each gets a slack us_i and the equality row
+                                  # h_nl,i(x,u) - us_i = 0 (tunempc/preprocessing.py:78-118); ns = len(gnl)
+    nsc: int = 0             # soft-constraint slacks usc of the MPC (tunempc/preprocessing.py:120-155); stage variables
+                             # are (x, u, us, usc), the dynamics and gnl depend on (x, u) only
 
     @property
     def nx(self):
@@ -66,6 +70,10 @@ class OdeModel:
     @property
     def nu(self):
         return len(self.u)
+
+    @property
+    def ns(self):
+        return len(self.gnl)
 
 
 def _count_ops(exprs) -> int:
@@ -208,7 +216,11 @@ def generate_header(model: OdeModel, out_path: str) -> dict:
     L.append("#include <math.h>")
     L.append("#ifndef TMPC_HD\n#ifdef __CUDACC__\n#define TMPC_HD __host__ __device__ __forceinline__\n#else\n#define TMPC_HD static inline\n#endif\n#endif")
     L.append('#define TMPC_MODEL_NAME "%s"' % model.name)
-    L.append("#define TMPC_NX %d\n#define TMPC_NU %d\n#define TMPC_NZ %d" % (nx, nu, nz))
+    # stage variables z = (x, u, us, usc): TMPC_NU / TMPC_NZ count every free variable of a stage block, TMPC_NUM / TMPC_NZM
+    # only what the dynamics (and gnl) depend on -- equal when the problem has no slacks
+    ns, nsc = model.ns, int(model.nsc)
+    L.append("#define TMPC_NX %d\n#define TMPC_NUM %d\n#define TMPC_NZM %d\n#define TMPC_NS %d\n#define TMPC_NSC %d" % (nx, nu, nz, ns, nsc))
+    L.append("#define TMPC_NU %d\n#define TMPC_NZ %d" % (nu + ns + nsc, nz + ns + nsc))
     L.append("#define TMPC_DISCRETE %d" % (1 if model.discrete else 0))
     L.append("#define TMPC_COLLOCATION %d" % (1 if (model.integrator == "collocation" and not model.discrete) else 0))
     L.append("#define TMPC_RK_STEPS %d" % model.rk_steps)
@@ -333,6 +345,25 @@ def generate_header(model: OdeModel, out_path: str) -> dict:
     else:
         L.append("  for (int i = 0; i < %d; ++i) H[i] = 0.0;" % (nz * nz))
     L.append("}")
+    # slacked nonlinear path constraints (tunempc/preprocessing.py:78-118): value, Jacobian (row-major [NS][NZM]) and the
+    # Hessian of lam'gnl w.r.t. (x,u) (row-major [NZM][NZM])
+    if ns:
+        gn = [sp.sympify(e) for e in model.gnl]
+        L.append("TMPC_HD void tmpc_gnl(const double* x, const double* u, double* g) {")
+        L.append("  (void)x; (void)u;")
+        _emit_block(L, None, [("g[%d]" % i, S(gn[i])) for i in range(ns)])
+        L.append("}")
+        L.append("TMPC_HD void tmpc_gnl_jac(const double* x, const double* u, double* g, double* J) {")
+        L.append("  (void)x; (void)u;")
+        _emit_block(L, None, [("g[%d]" % i, S(gn[i])) for i in range(ns)] +
+                    [("J[%d]" % (i * nz + b), S(sp.diff(gn[i], z[b]))) for i in range(ns) for b in range(nz)])
+        L.append("}")
+        lam_s = [sp.Symbol("lam[%d]" % i) for i in range(ns)]
+        lg = sum(lam_s[i] * gn[i] for i in range(ns))
+        L.append("TMPC_HD void tmpc_gnl_hess(const double* x, const double* u, const double* lam, double* H) {")
+        L.append("  (void)x; (void)u; (void)lam;")
+        _emit_block(L, None, [("H[%d]" % (i * nz + j), S(sp.diff(lg, z[i], z[j]))) for i in range(nz) for j in range(nz)])
+        L.append("}")
     c_B = sum(3 if b == c else 5 for _, b, c, _ in hess)
     L.append("#define TMPC_OPS_F %d\n#define TMPC_OPS_J %d\n#define TMPC_OPS_H %d\n#define TMPC_OPS_BILIN %d" % (c_f, c_J, c_H, c_B))
     L.append("#endif")

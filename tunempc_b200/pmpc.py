@@ -32,8 +32,10 @@ def default_options():
 def problem_from_reference_args(N, sys, cost, wref, tuning, lam_g_ref, sensitivities, options):
     """The reference constructor's arguments (tunempc/pmpc.py:39-147) -> the problem IR.
 
-    sys            model card: {'f': OdeModel or compiled-model name, 'vars': {'x': .., 'u': ..}, 'h': (C, c) with
-                   h(x,u) = C z + c >= 0} -- what Tuner.sys returns (tuner.py:201-207 hands CasADi Functions here)
+    sys            model card: {'f': OdeModel or compiled-model name, 'vars': {'x': .., 'u': .. [, 'us': .., 'usc': ..]},
+                   'h': (C, c) with h = C z + c >= 0 over z = (x, u, us, usc) [, 'g': the compiled model's nonlinear rows
+                   h_nl(x,u) - us = 0, 'scost': (nsc,), 'gnl_x_idx': state-only rows of g]} -- what Tuner.sys returns after
+                   preprocessing (tuner.py:201-207, preprocessing.py:35-155 hand CasADi Functions here)
     cost           'tracking' / 'economic', or a callable: two arguments l(x,u) -> economic, otherwise tracking
                    (the reference tells them apart by cost.n_in(), pmpc.py:97-118)
     wref           {'x': [p arrays (nx,)], 'u': [p arrays (nu,)]} or an array (p, nz)   (pmpc.py:692-706)
@@ -45,21 +47,32 @@ def problem_from_reference_args(N, sys, cost, wref, tuning, lam_g_ref, sensitivi
     f = sys["f"]
     name = f if isinstance(f, str) else f.name
     nx, nu = len(sys["vars"]["x"]), len(sys["vars"]["u"])
-    nz = nx + nu
-    if "us" in sys["vars"] or "usc" in sys["vars"] or "g" in sys:
-        raise NotImplementedError("slack variables us/usc and nonlinear rows g (pmpc.py:50-76) are not built")
+    ns = len(sys["vars"]["us"]) if "us" in sys["vars"] else 0                                # pmpc.py:50-55
+    nsc = len(sys["vars"]["usc"]) if "usc" in sys["vars"] else 0                             # pmpc.py:57-62
+    scost = np.asarray(sys["scost"], dtype=np.float64).ravel() if nsc else None
+    if (ns > 0) != ("g" in sys):
+        raise ValueError("slacks us and the nonlinear rows g come together (tunempc/preprocessing.py:78-118)")
+    # state-only nonlinear constraints (pmpc.py:1107-1114): from the model card's expressions, or given explicitly
+    gnl_x_idx = list(sys.get("gnl_x_idx", []))
+    if ns and not isinstance(f, str) and "gnl_x_idx" not in sys:
+        usym = set(f.u)
+        gnl_x_idx = [i for i, e in enumerate(f.gnl) if not (set(getattr(e, "free_symbols", ())) & usym)]
+    nzr, nz = nx + nu + ns, nx + nu + ns + nsc
     if isinstance(cost, str):
         economic = cost == "economic"
     else:
         economic = callable(cost) and len(inspect.signature(cost).parameters) == 2          # pmpc.py:97
     assert wref is not None, "Provide reference trajectory!"                                 # pmpc.py:134
     if isinstance(wref, dict):
-        w = np.array([np.concatenate([np.ravel(wref["x"][k]), np.ravel(wref["u"][k])]) for k in range(len(wref["u"]))])
+        w = np.array([np.concatenate([np.ravel(wref["x"][k]), np.ravel(wref["u"][k])] + ([np.ravel(wref["us"][k])] if ns else []))
+                      for k in range(len(wref["u"]))])                                         # pmpc.py:692-704
     else:
         w = np.atleast_2d(np.asarray(wref, dtype=np.float64))
     P = w.shape[0]
+    if economic and (ns or nsc):
+        raise NotImplementedError("economic MPC with slack variables is not built (the device evaluates l on (x,u) only)")
     if economic:
-        H, q = np.zeros((P, nz, nz)), np.zeros((P, nz))                                        # pmpc.py:103: no tuning required
+        H, q = np.zeros((P, nzr, nzr)), np.zeros((P, nzr))                                     # pmpc.py:103: no tuning required
     else:
         assert tuning is not None, "Provide tuning matrices for tracking MPC!"                # pmpc.py:118
         Hs = [np.asarray(h, dtype=np.float64) for h in tuning["H"]]
@@ -71,14 +84,19 @@ def problem_from_reference_args(N, sys, cost, wref, tuning, lam_g_ref, sensitivi
     nh = C.shape[0]
     lam_dyn = (np.zeros((P, nx)) if lam_g_ref is None
                else np.array([np.ravel(v) for v in lam_g_ref["dyn"]], dtype=np.float64).reshape(P, nx))
-    lam_h = (np.zeros((P, nh)) if lam_g_ref is None or "h" not in lam_g_ref
-             else np.array([np.ravel(v) for v in lam_g_ref["h"]], dtype=np.float64).reshape(P, nh))
+    lam_h = (np.zeros((P, nh - nsc)) if lam_g_ref is None or "h" not in lam_g_ref                # the usc >= 0 rows get -scost (pmpc.py:716-720)
+             else np.array([np.ravel(v) for v in lam_g_ref["h"]], dtype=np.float64).reshape(P, nh - nsc))
+    lam_g = None
+    if ns:
+        lam_g = (np.zeros((P, ns)) if lam_g_ref is None or "g" not in lam_g_ref
+                 else np.array([np.ravel(v) for v in lam_g_ref["g"]], dtype=np.float64).reshape(P, ns))
     term = (options or {}).get("p_operator")
     pb = MpcProblem(name=name, nx=nx, nu=nu, N=int(N), p=P, wref=w, H=H, q=q, C=C, c=c, lam_h_ref=lam_h, lam_dyn_ref=lam_dyn,
                     term_idx=list(range(nx)) if term is None else [int(i) for i in term],
                     S_A=None if sensitivities is None else np.array(sensitivities["A"], dtype=np.float64),
                     S_B=None if sensitivities is None else np.array(sensitivities["B"], dtype=np.float64),
-                    mpc_type="economic" if economic else "tuned")
+                    mpc_type="economic" if economic else "tuned", ns=ns, nsc=nsc, scost=scost, lam_g_ref=lam_g,
+                    gnl_x_idx=[int(i) for i in gnl_x_idx])
     if economic:
         pb.hessian_approximation = "exact"                                                     # pmpc.py:105-107
     return pb
@@ -104,8 +122,8 @@ class Pmpc:
                 raise ValueError('Unknown option for Pmpc class instance: "{}"'.format(k))   # pmpc.py:94
         if opts["ipopt_presolve"]:
             raise NotImplementedError("ipopt_presolve is a host-side IPOPT call in the reference (pmpc.py:394-404); not available")
-        if opts["slack_flag"] != "none":
-            raise NotImplementedError("slack_flag != 'none' (usc slacks) is not built yet")
+        # opts['slack_flag'] is consumed by Tuner.create_mpc, which softens the rows before this constructor runs
+        # (tuner.py:171-177, preprocessing.py:120-155); here the softened rows arrive in sys['h'] / sys['vars']['usc'] / sys['scost']
         problem = copy.copy(problem)                                     # the caller's problem object is never modified
         if options and "hessian_approximation" in options:
             problem.hessian_approximation = opts["hessian_approximation"]
@@ -120,9 +138,9 @@ class Pmpc:
         self.__tab = build_tables(problem)
         self.__lib = ModelLib(problem.name)
         L = self.__lib.lib
-        if (self.__lib.nx, self.__lib.nu) != (problem.nx, problem.nu):
+        if (self.__lib.nx, self.__lib.nu, self.__lib.ns, self.__lib.nsc) != (problem.nx, problem.nu, problem.ns, problem.nsc):
             raise ValueError("problem dimensions do not match compiled model '%s'" % problem.name)
-        dims = TmpcDims(problem.nx, problem.nu, problem.nh, problem.nx_term, problem.N, problem.p)
+        dims = TmpcDims(problem.nx, problem.nu, problem.nh, problem.nx_term, problem.N, problem.p, problem.ns, problem.nsc)
         o = self.__lib.default_opts()
         o.hessian_exact = 1 if problem.hessian_approximation == "exact" else 0
         o.economic = 1 if problem.mpc_type == "economic" else 0          # pmpc.py:97-107: exact Hessian forced
@@ -139,12 +157,12 @@ class Pmpc:
         self.__device = int(device)
         pb = problem
         relax0 = np.zeros(max(pb.nh, 1), dtype=np.int32)
-        for i in pb.h_x_idx:
+        for i in pb.relax0:                                               # pmpc.py:293-294: h_us_idx + h_x_idx
             relax0[i] = 1
         tidx = np.ascontiguousarray(np.array(pb.term_idx, dtype=np.int32))
         C = np.ascontiguousarray(pb.C if pb.nh else np.zeros((1, pb.nz)), dtype=np.float64)
         c = np.ascontiguousarray(pb.c if pb.nh else np.zeros(1), dtype=np.float64)
-        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (pb.wref, pb.H, pb.q, self.__tab.ref_du)]
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in pb.device_tables() + (self.__tab.ref_du,)]
         p = lambda a: a.ctypes.data_as(_dp)
         self.__check(L.tmpc_set_tables(self.__h, p(arrs[0]), p(arrs[1]), p(arrs[2]), p(arrs[3]), p(C), p(c),
                                        tidx.ctypes.data_as(_ip), relax0.ctypes.data_as(_ip)))
