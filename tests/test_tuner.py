@@ -102,5 +102,19 @@ def test_reference_constructor_arguments():
     eco = problem_from_reference_args(20, card, lambda x, u: 0.0, wref, None, {"dyn": [np.ones(4)], "h": [pb.lam_h_ref[0]]}, None,
                                       {"hessian_approximation": "gauss_newton"})
     assert eco.mpc_type == "economic" and eco.hessian_approximation == "exact"                # pmpc.py:97-107
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                                                           # g rows and their slacks us come together
         problem_from_reference_args(20, dict(card, g="g"), "tracking", wref, {"H": [pb.H[0]], "q": [pb.q[0]]}, None, None, {})
+    # model card with slacks (pmpc.py:50-76: sys['vars']['us'], ['usc'], sys['g'], sys['scost']) -> the committed awe9 problem
+    from tunempc_b200 import configs
+    pa = load_problem("awe9")
+    model = configs.CONFIGS["awe9"]()["model"]
+    card = {"f": model, "vars": {"x": [0] * 9, "u": [0] * 3, "us": [0] * 3, "usc": [0] * 3}, "h": (pa.C, pa.c), "g": "compiled",
+            "scost": pa.scost}
+    wref = {"x": [pa.wref[k, :9] for k in range(pa.p)], "u": [pa.wref[k, 9:12] for k in range(pa.p)], "us": [pa.wref[k, 12:] for k in range(pa.p)]}
+    lam = {"dyn": list(pa.lam_dyn_ref), "g": list(pa.lam_g_ref), "h": list(pa.lam_h_ref)}
+    pb2 = problem_from_reference_args(pa.N, card, "tracking", wref, {"H": list(pa.H), "q": list(pa.q)}, lam, {"A": pa.S_A, "B": pa.S_B},
+                                      {"p_operator": pa.term_idx})
+    assert (pb2.ns, pb2.nsc, pb2.nz, pb2.n_w, pb2.n_g) == (3, 3, 18, 369, 596) and pb2.gnl_x_idx == [0] == pa.gnl_x_idx
+    assert pb2.relax0 == pa.relax0 and np.array_equal(pb2.scost, pa.scost)
+    ta, tb = build_tables(pa), build_tables(pb2)
+    assert np.array_equal(ta.ref, tb.ref) and np.array_equal(ta.ref_du, tb.ref_du) and np.array_equal(ta.Href, tb.Href)

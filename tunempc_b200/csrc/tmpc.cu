@@ -572,6 +572,7 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
   }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
   h->ev_ok = true;
+  if (cudaMalloc(&P.prof_counters, 4 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(P.prof_counters, 0, 4 * sizeof(unsigned long long));
   *out = h;
   return 0;
 }
@@ -594,6 +595,7 @@ void tmpc_destroy(tmpc_handle* h) {
   if (h->q0.SLPHI) cudaFree(h->q0.SLPHI);
   if (h->q0.MCOL) cudaFree(h->q0.MCOL);
   if (h->q0.bad) cudaFree(h->q0.bad);
+  if (h->P.prof_counters) cudaFree(h->P.prof_counters);
   if (h->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
   delete h;
 }
@@ -875,8 +877,12 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
     fprintf(stderr, "[tmpc] qp attempts %llu gi %llu ricc %llu | fresh ok/inf/npd/mask %llu %llu %llu %llu | retry %llu %llu %llu %llu | gn %llu %llu %llu %llu\n",
             cnt_host[5], cnt_host[6], cnt_host[7], cnt_host[8], cnt_host[9], cnt_host[10], cnt_host[11], cnt_host[12],
             cnt_host[13], cnt_host[14], cnt_host[15], cnt_host[16], cnt_host[17], cnt_host[18], cnt_host[19]);
-    if (cnt_host[20]) fprintf(stderr, "[tmpc] warp-kernel cycles per attempt: factor %.0f  dual active set %.0f  correction solve %.0f  multiplier recovery %.0f\n",
-                              (double)cnt_host[20] / cnt_host[5], (double)cnt_host[21] / cnt_host[5], (double)cnt_host[22] / cnt_host[5], (double)cnt_host[23] / cnt_host[5]);
+    if (cnt_host[20]) {
+      unsigned long long pc[4] = {0, 0, 0, 0};
+      if (P.prof_counters) { cudaMemcpy(pc, P.prof_counters, sizeof pc, cudaMemcpyDeviceToHost); cudaMemset(P.prof_counters, 0, sizeof pc); }
+      fprintf(stderr, "[tmpc] warp-kernel cycles per attempt: factor %.0f (of which the block products P[A B], Q + [A B]'P[A B]: %.0f)  dual active set %.0f  correction solve %.0f  multiplier recovery %.0f\n",
+              (double)cnt_host[20] / cnt_host[5], (double)pc[0] / cnt_host[5], (double)cnt_host[21] / cnt_host[5], (double)cnt_host[22] / cnt_host[5], (double)cnt_host[23] / cnt_host[5]);
+    }
   }
   return 0;
 }

@@ -428,6 +428,9 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
     const TmP AB = ABw, Pn = Pnw;
     const TmP bk = s.b + k * NX;
 #endif
+#if defined(TM_PROF_W) && defined(__CUDA_ARCH__)
+    long long tq0 = clock64(), tq1 = 0;       // profiling build: cycles of the two block products P [A B] and Q + [A B]'(P [A B])
+#endif
     TM_UNROLL_T
     for (int e = lane; e < NX * NZ; e += TM_NL) {
       const int i = e / NZ, c = e % NZ;
@@ -436,6 +439,9 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
       for (int l = 0; l < NX; ++l) v += Pn[i * NX + l] * AB[l * NZ + c];
       sPAB[e] = v;
     }
+#if defined(TM_PROF_W) && defined(__CUDA_ARCH__)
+    tq1 = clock64() - tq0;
+#endif
     TM_UNROLL_T
     for (int i = lane; i < NX; i += TM_NL) {           // vv = P b + p
       double v = s.pm[(k + 1) * NX + i];
@@ -468,6 +474,9 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
       ++nr;
     }
     TM_SYNC();
+#if defined(TM_PROF_W) && defined(__CUDA_ARCH__)
+    tq0 = clock64();
+#endif
     TM_UNROLL_T
     for (int e = lane; e < NZ * NZ; e += TM_NL) {
       const int a = e / NZ, c = e % NZ;
@@ -476,6 +485,10 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
       for (int i = 0; i < NX; ++i) v += AB[i * NZ + a] * sPAB[i * NZ + c];
       sF[e] = v;
     }
+#if defined(TM_PROF_W) && defined(__CUDA_ARCH__)
+    tq1 += clock64() - tq0;
+    if (lane == 0) atomicAdd(P.prof_counters + 0, (unsigned long long)tq1);
+#endif
     TM_UNROLL_T
     for (int c = lane; c < NZ; c += TM_NL) {
       double v = s.r[k * NZ + c];
