@@ -97,7 +97,7 @@ def closed_loop_sim(controllers, cost, h, F, x0, N, flag="tunempc", disturbance=
             if disturbance is not None:
                 X = disturbance(i, X)
                 log["x"][name][-1] = X
-            U = ctrl.step(X)                                            # :95
+            U = ctrl.step(X, outputs="u0")                              # :95 (the (B,n_w) / (B,n_g) solution tensors are not kept per step)
             log["u"][name].append(U)
             log["status"][name].append(ctrl.status)
             if cost is None or h is None:

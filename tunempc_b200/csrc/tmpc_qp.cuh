@@ -125,7 +125,82 @@ TM_HD void tm_mask_clr(unsigned* m, int e) { m[e >> 5] &= ~(1u << (e & 31)); }
 //      stage's own active rows)
 // out: K, Wm, kkm of stage k; constraint-to-go (Gc, gc, ncs) of stage k; s.f <- f + F[:,u] ku
 // returns 0 ok, 3 projected block not positive definite, 6 rows inconsistent
+// Stage without candidate rows (no constraint-to-go from later stages, no held row of its own) -- most stages of most QPs:
+// the plain Riccati step  W = Fuu^-1,  K = -W Fux,  kk = -W f_u.  Same operations in the same order as the general routine
+// below performs for nr = 0 (whose elimination loops then only move zeros and unit vectors around), with constant trip
+// counts: everything stays in registers.
+TM_HD int tm_stage_factor_free(const TmProb& P, TmQpWs& s, int k, const double* F, const double* fv) {
+  constexpr int NVV = NV > 0 ? NV : 1;
+  double Rt[NVV * NVV], Y[NVV * NVV], Wl[NVV * NVV];
+#pragma unroll
+  for (int c = 0; c < NV; ++c)
+#pragma unroll
+    for (int e = 0; e <= c; ++e) Rt[c * NVV + e] = 0.5 * (F[(NX + c) * NZ + NX + e] + F[(NX + e) * NZ + NX + c]);
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    double dg = Rt[c * NVV + c];
+#pragma unroll
+    for (int l = 0; l < c; ++l) dg -= Rt[c * NVV + l] * Rt[c * NVV + l];
+    if (!(dg > P.reg_tol)) return 3;
+    const double ld = sqrt(dg);
+    Rt[c * NVV + c] = ld;
+#pragma unroll
+    for (int i = c + 1; i < NV; ++i) {
+      double v = Rt[i * NVV + c];
+#pragma unroll
+      for (int l = 0; l < c; ++l) v -= Rt[i * NVV + l] * Rt[c * NVV + l];
+      Rt[i * NVV + c] = v / ld;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NV; ++a)
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      double v = (a == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int l = 0; l < c; ++l) v -= Rt[c * NVV + l] * Y[l * NVV + a];
+      Y[c * NVV + a] = v / Rt[c * NVV + c];
+    }
+  const TmP Wk = s.Wm + (size_t)k * NV * NV;
+#pragma unroll
+  for (int a = 0; a < NV; ++a)
+#pragma unroll
+    for (int b2 = 0; b2 < NV; ++b2) {
+      double v = 0.0;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) v += Y[c * NVV + a] * Y[c * NVV + b2];
+      Wl[a * NVV + b2] = v;
+      Wk[a * NV + b2] = v;
+    }
+  const TmP Kk = s.K + (size_t)k * NV * NX;
+#pragma unroll
+  for (int j = 0; j < NX; ++j) {
+    double t[NVV];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) t[a] = 0.5 * (F[(NX + a) * NZ + j] + F[j * NZ + NX + a]);
+#pragma unroll
+    for (int a = 0; a < NV; ++a) {
+      double v = 0.0;
+#pragma unroll
+      for (int b2 = 0; b2 < NV; ++b2) v -= Wl[a * NVV + b2] * t[b2];
+      Kk[a * NX + j] = v;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NV; ++a) {
+    double v = 0.0;
+#pragma unroll
+    for (int b2 = 0; b2 < NV; ++b2) v -= Wl[a * NVV + b2] * fv[NX + b2];
+    s.kkm[k * NV + a] = v;
+  }
+  s.ncs[k] = 0.0;
+  return 0;
+}
+
 TM_HD int tm_stage_factor(const TmProb& P, TmQpWs& s, int k, int nr, double* F, double* fv) {
+#if NV > 0 && NV <= 4 && !defined(TM_NO_FREE_STAGE)
+  if (nr == 0) return tm_stage_factor_free(P, s, k, F, fv);
+#endif
   const TmP E = s.Ew;
   const double tolp = 1e-9, tolc = 1e-7;
   int colrow[NV > 0 ? NV : 1];
