@@ -967,6 +967,229 @@ TM_HD void tm_ricc_col(const TmProb& P, TmQpWs& s, int qe, TmP mq) {
   TM_SYNC();
 }
 
+// Dual-Hessian columns of ALL terminal rows (they enter the working set first, unconditionally): TM_TG columns share one pass
+// over the stage blocks (A, B, K, W are read once per group instead of once per column, and the independent recursions
+// overlap their memory latency).  Column of terminal row t goes to slot t of Mc.  Per column the same operations in the same
+// order as tm_ricc_col: bitwise identical results.
+#ifndef TM_TG
+#if TMPC_NZ <= 8
+#define TM_TG 2
+#else
+#define TM_TG 1            /* wide stages: the second set of recursion vectors would only spill */
+#endif
+#endif
+TM_HD void tm_ricc_cols_term(const TmProb& P, TmQpWs& s, int E) {
+  const int N = P.N, nh = P.nh, NI = N * nh, nxt = P.nxt;
+  const int lane = TM_LANE;
+#if TM_NL > 1
+  if (N <= TM_NL) {                                   // lane <-> stage: one load of the stage blocks, TM_TG chains per pass
+    const bool mine = lane < N;
+    TmLaneStage L;
+    tm_lane_stage_load(s, lane, mine, L);
+    for (int t0 = 0; t0 < nxt; t0 += TM_TG) {
+      const int ng = (nxt - t0 < TM_TG) ? nxt - t0 : TM_TG;
+      double rk[NZ], pin[TM_TG][NX], pn[TM_TG][NX], kk[TM_TG][NV > 0 ? NV : 1];
+#pragma unroll
+      for (int c = 0; c < NZ; ++c) rk[c] = 0.0;
+#pragma unroll
+      for (int g = 0; g < TM_TG; ++g) {
+        const int ti = g < ng ? P.term_idx[t0 + g] : -1;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { pin[g][i] = (i == ti && lane == N - 1) ? -1.0 : 0.0; pn[g][i] = 0.0; }
+#pragma unroll
+        for (int a = 0; a < NV; ++a) kk[g][a] = 0.0;
+      }
+      for (int step = N - 1; step >= 0; --step) {
+        if (lane == step) {
+#pragma unroll
+          for (int g = 0; g < TM_TG; ++g) tm_lane_bwd(L, rk, pin[g], pn[g], kk[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g)
+#pragma unroll
+          for (int j = 0; j < NX; ++j) { const double t = tm_shfl(pn[g][j], step); if (lane == step - 1) pin[g][j] = t; }
+      }
+      double z[TM_TG][NZ], xo[TM_TG][NX];
+#pragma unroll
+      for (int g = 0; g < TM_TG; ++g) {
+#pragma unroll
+        for (int b = 0; b < NZ; ++b) z[g][b] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xo[g][i] = 0.0;
+      }
+      for (int step = 0; step < N; ++step) {
+        if (lane == step) {
+#pragma unroll
+          for (int g = 0; g < TM_TG; ++g) tm_lane_fwd(L, kk[g], z[g], nullptr, z[g] + NX, xo[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g)
+#pragma unroll
+          for (int i = 0; i < NX; ++i) { const double t = tm_shfl(xo[g][i], step); if (lane == step + 1) z[g][i] = t; }
+      }
+      for (int g = 0; g < ng; ++g) {
+        const TmP mq = s.Mc + (size_t)(t0 + g) * E;
+        if (mine) {
+          for (int i = 0; i < nh; ++i) {
+            const double* Ci = P.C + (size_t)i * NZ;
+            double t = 0.0;
+#pragma unroll
+            for (int b = 0; b < NZ; ++b) t += Ci[b] * z[g][b];
+            mq[lane * nh + i] = t;
+          }
+        }
+        for (int t = 0; t < nxt; ++t) {
+          const int ti = P.term_idx[t];
+          double v = 0.0;
+#pragma unroll
+          for (int a = 0; a < NX; ++a) if (a == ti) v = xo[g][a];
+          v = tm_shfl(v, N - 1);
+          if (lane == 0) mq[NI + t] = v;
+        }
+      }
+      TM_SYNC();
+    }
+    return;
+  }
+#endif
+  for (int t0 = 0; t0 < nxt; t0 += TM_TG) {
+    const int ng = (nxt - t0 < TM_TG) ? nxt - t0 : TM_TG;
+    double pv[TM_TG][NX];
+#pragma unroll
+    for (int g = 0; g < TM_TG; ++g) {
+      const int ti = g < ng ? P.term_idx[t0 + g] : -1;
+#pragma unroll
+      for (int a = 0; a < NX; ++a) pv[g][a] = (a == ti) ? -1.0 : 0.0;
+    }
+    for (int k = N - 1; k >= 0; --k) {
+      const TmP AB = s.AB + (size_t)k * NX * NZ;
+      const TmP Kk = s.K + (size_t)k * NV * NX;
+      const TmP Wk = s.Wm + (size_t)k * NV * NV;
+      double fu[TM_TG][NV > 0 ? NV : 1], pn[TM_TG][NX];
+#pragma unroll
+      for (int a = 0; a < NV; ++a) {
+        double v[TM_TG];
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g) v[g] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          const double ab = AB[i * NZ + NX + a];
+#pragma unroll
+          for (int g = 0; g < TM_TG; ++g) v[g] += ab * pv[g][i];
+        }
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g) fu[g][a] = v[g];
+      }
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        double v[TM_TG];
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g) v[g] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          const double ab = AB[i * NZ + j];
+#pragma unroll
+          for (int g = 0; g < TM_TG; ++g) v[g] += ab * pv[g][i];
+        }
+#pragma unroll
+        for (int a = 0; a < NV; ++a) {
+          const double kv = Kk[a * NX + j];
+#pragma unroll
+          for (int g = 0; g < TM_TG; ++g) v[g] += kv * fu[g][a];
+        }
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g) pn[g][j] = v[g];
+      }
+      for (int a = lane; a < NV; a += TM_NL) {
+        double v[TM_TG];
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g) v[g] = 0.0;
+#pragma unroll
+        for (int b2 = 0; b2 < NV; ++b2) {
+          const double wv = Wk[a * NV + b2];
+#pragma unroll
+          for (int g = 0; g < TM_TG; ++g) v[g] -= wv * fu[g][b2];
+        }
+        s.kk[k * NV + a] = v[0];                       // feed-forward of column g: kk (g = 0), y (g = 1; free until the correction solve)
+#if TM_TG > 1
+        s.y[k * NV + a] = v[1];
+#endif
+      }
+#pragma unroll
+      for (int g = 0; g < TM_TG; ++g)
+#pragma unroll
+        for (int j = 0; j < NX; ++j) pv[g][j] = pn[g][j];
+    }
+    TM_SYNC();
+    double z[TM_TG][NZ];
+#pragma unroll
+    for (int g = 0; g < TM_TG; ++g)
+#pragma unroll
+      for (int b = 0; b < NZ; ++b) z[g][b] = 0.0;
+    for (int k = 0; k < N; ++k) {
+      const TmP AB = s.AB + (size_t)k * NX * NZ;
+      const TmP Kk = s.K + (size_t)k * NV * NX;
+#pragma unroll
+      for (int a = 0; a < NV; ++a) {
+        double v[TM_TG];
+        v[0] = s.kk[k * NV + a];
+#if TM_TG > 1
+        v[1] = s.y[k * NV + a];
+#endif
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          const double kv = Kk[a * NX + j];
+#pragma unroll
+          for (int g = 0; g < TM_TG; ++g) v[g] += kv * z[g][j];
+        }
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g) z[g][NX + a] = v[g];
+      }
+      for (int i = lane; i < nh; i += TM_NL) {
+        const double* Ci = P.C + (size_t)i * NZ;
+        double t[TM_TG];
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g) t[g] = 0.0;
+#pragma unroll
+        for (int b = 0; b < NZ; ++b) {
+          const double cv = Ci[b];
+#pragma unroll
+          for (int g = 0; g < TM_TG; ++g) t[g] += cv * z[g][b];
+        }
+        for (int g = 0; g < ng; ++g) s.Mc[(size_t)(t0 + g) * E + k * nh + i] = t[g];
+      }
+      double xn[TM_TG][NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double v[TM_TG];
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g) v[g] = 0.0;
+#pragma unroll
+        for (int b = 0; b < NZ; ++b) {
+          const double ab = AB[i * NZ + b];
+#pragma unroll
+          for (int g = 0; g < TM_TG; ++g) v[g] += ab * z[g][b];
+        }
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g) xn[g][i] = v[g];
+      }
+#pragma unroll
+      for (int g = 0; g < TM_TG; ++g)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) z[g][i] = xn[g][i];
+    }
+    for (int g = 0; g < ng; ++g)
+      for (int t = lane; t < nxt; t += TM_NL) {
+        const int ti = P.term_idx[t];
+        double v = 0.0;
+#pragma unroll
+        for (int a = 0; a < NX; ++a) if (a == ti) v = z[g][a];
+        s.Mc[(size_t)(t0 + g) * E + NI + t] = v;
+      }
+    TM_SYNC();
+  }
+}
+
 TM_HD double tm_erow_dot(const TmProb& P, int e, TmP v) {       // n_e' v: e < N*nh inequality row k*nh + i, else terminal row
   if (e >= P.N * P.nh) return v[P.N * NZ + P.term_idx[e - P.N * P.nh]];
   const int k = e / P.nh, i = e % P.nh;
@@ -1033,6 +1256,7 @@ TM_HD int tm_qp_gi(const TmProb& P, TmQpWs& s, const unsigned* amask, int& m_out
   TM_SYNC();
   int m = 0, ret = 0, eq_next = 0;
   const int maxit = 4 * NI + 8 + neq;
+  if (neq > 0) { tm_ricc_cols_term(P, s, E); n_ricc += neq; }   // the terminal rows' columns, slot t = row t
   for (int it = 0; it < maxit && !ret; ++it) {
     int qe, is_eq = 0;
     double sval;
@@ -1069,9 +1293,17 @@ TM_HD int tm_qp_gi(const TmProb& P, TmQpWs& s, const unsigned* amask, int& m_out
     }
     if (m >= M) { ret = 7; break; }
     TmP mq = s.Mc + (size_t)m * E;            // candidate column, becomes member m when added
-    tm_ricc_col(P, s, qe, mq);
-    if (!is_eq) ++n_gi;
-    ++n_ricc;
+    if (is_eq) {                              // precomputed (slot qe - NI); an earlier terminal row was skipped as redundant: move it down
+      const int q = qe - NI;
+      if (q != m) {
+        for (int e = lane; e < E; e += TM_NL) mq[e] = s.Mc[(size_t)q * E + e];
+        TM_SYNC();
+      }
+    } else {
+      tm_ricc_col(P, s, qe, mq);
+      ++n_gi;
+      ++n_ricc;
+    }
     const double yq = mq[qe];
     double nq = 0.0;
     int added = 0;

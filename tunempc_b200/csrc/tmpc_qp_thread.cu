@@ -13,6 +13,11 @@
 #include "tmpc_core.cuh"
 
 #define QT_THREADS 128
+#if !defined(QT_MINB) && TMPC_NZ > 12
+#define QT_MINB 2          /* wide stages (config #5: nz = 18): the per-stage blocks no longer fit 64 registers by far (32 KB of stack,
+                              75 KB of spill loads); with 255 registers the 2^14-instance closed loop runs 25 % faster
+                              (profiles/r02_summary.md, capture Q) -- at that batch the grid is one CTA per SM anyway */
+#endif
 #ifndef QT_MINB
 #define QT_MINB 8          /* resident CTAs / SM the register allocation aims for: 64 registers, 1024 threads / SM.  The kernel
                               waits on its workspace (DRAM latency), so resident warps matter more than spills: measured

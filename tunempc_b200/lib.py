@@ -18,7 +18,7 @@ _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-shared", "-Xcompiler", "-fPIC",
-              "-std=c++17"]
+              "-std=c++17", "--threads", "2"]      # the two translation units of a model library compile side by side
 
 EXPORTS = ["tmpc_default_opts", "tmpc_model_info", "tmpc_model_slacks", "tmpc_create", "tmpc_destroy", "tmpc_last_error",
            "tmpc_set_tables", "tmpc_reset", "tmpc_get_index", "tmpc_step", "tmpc_step_host", "tmpc_plant_step", "tmpc_stage_log",
