@@ -78,6 +78,14 @@ int twin_step(const int* dims, const int* iopts, const double* dopts, const doub
   if (P.economic) P.hessian_exact = 1;
   P.tol = dopts[0]; P.lam_tresh = dopts[1]; P.beta = dopts[2]; P.reg_tol = dopts[3]; P.rho_rel = dopts[4];
   P.wref = wref; P.H = H; P.q = q; P.ref_du = ref_du; P.C = C; P.c = c; P.term_idx = term_idx; P.relax0 = relax0;
+  std::vector<int> rowpin((size_t)(P.nh > 0 ? P.nh : 1), -1);
+  for (int i = 0; i < P.nh; ++i) {
+    int cnt = 0, jc = -1;
+    for (int cidx = 0; cidx < NZ; ++cidx) if (C[(size_t)i * NZ + cidx] != 0.0) { ++cnt; jc = cidx; }
+    if (cnt == 1 && jc >= NX) rowpin[i] = jc - NX;
+  }
+  P.rowpin = rowpin.data();
+  P.prof_counters = nullptr;
   TmState S;
   memset(&S, 0, sizeof S);
   S.B = B; S.phase = phase; S.X0 = X0; S.W = W; S.LAM = LAM; S.G = G;

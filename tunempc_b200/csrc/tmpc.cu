@@ -632,6 +632,15 @@ int tmpc_set_tables(tmpc_handle* h, const double* wref, const double* H, const d
   if (upload(h, h->tab_allocs, c, (size_t)P.nh, &P.c)) return 1;
   if (upload(h, h->tab_allocs, (const int*)term_idx, (size_t)P.nxt, &P.term_idx)) return 1;
   if (upload(h, h->tab_allocs, (const int*)relax0, (size_t)P.nh, &P.relax0)) return 1;
+  {
+    std::vector<int> rowpin((size_t)(P.nh > 0 ? P.nh : 1), -1);    // rows that bound a single input (fast path of the stage elimination)
+    for (int i = 0; i < P.nh; ++i) {
+      int cnt = 0, jc = -1;
+      for (int cidx = 0; cidx < NZ; ++cidx) if (C[(size_t)i * NZ + cidx] != 0.0) { ++cnt; jc = cidx; }
+      if (cnt == 1 && jc >= NX) rowpin[i] = jc - NX;
+    }
+    if (upload(h, h->tab_allocs, rowpin.data(), rowpin.size(), &P.rowpin)) return 1;
+  }
   h->phase_clean.assign(P.p, 1);
   for (int ph = 0; ph < P.p; ++ph)
     for (int k = 0; k < P.N; ++k)

@@ -124,6 +124,7 @@ struct TmProb {
   double tol, lam_tresh, beta, reg_tol, rho_rel;
   const double *wref, *H, *q, *ref_du, *C, *c;   // wref p*nz | H p*nz*nz (symmetric) | q p*nz | ref_du p*n_g | C nh*nz | c nh
   const int *term_idx, *relax0;
+  const int* rowpin;      // nh: input index j if row i of C has its only non-zero on input j (a bound on one input), else -1
   unsigned long long* prof_counters;   // profiling builds (-DTM_PROF_W): [0] cycles of the Riccati block products inside the factorisation
 };
 

@@ -125,23 +125,28 @@ TM_HD void tm_mask_clr(unsigned* m, int e) { m[e >> 5] &= ~(1u << (e & 31)); }
 //      stage's own active rows)
 // out: K, Wm, kkm of stage k; constraint-to-go (Gc, gc, ncs) of stage k; s.f <- f + F[:,u] ku
 // returns 0 ok, 3 projected block not positive definite, 6 rows inconsistent
-// Stage without candidate rows (no constraint-to-go from later stages, no held row of its own) -- most stages of most QPs:
-// the plain Riccati step  W = Fuu^-1,  K = -W Fux,  kk = -W f_u.  Same operations in the same order as the general routine
-// below performs for nr = 0 (whose elimination loops then only move zeros and unit vectors around), with constant trip
-// counts: everything stays in registers.
-TM_HD int tm_stage_factor_free(const TmProb& P, TmQpWs& s, int k, const double* F, const double* fv) {
+// Fast path of the stage elimination -- most stages of most QPs: no constraint-to-go from later stages, and the held rows of
+// the stage (if any) each bound ONE input (P.rowpin), distinct inputs.  Those inputs are pinned (u_j = ku_j), the others are
+// free: the plain Riccati step on the free inputs,  W = Zu (Zu'Fuu Zu)^-1 Zu',  K = -W Fux,  kk = ku - W (f_u + Fuu ku).
+// Written with constant trip counts over all NV inputs (a pinned input is an identity row / column of the projected block), so
+// everything stays in registers; per entry the same operations in the same order as the general routine below, whose
+// elimination loops in this case only move zeros and unit vectors around: equal results.
+TM_HD int tm_stage_factor_pinned(const TmProb& P, TmQpWs& s, int k, unsigned pinmask, const double* ku, const double* F, double* fv) {
   constexpr int NVV = NV > 0 ? NV : 1;
   double Rt[NVV * NVV], Y[NVV * NVV], Wl[NVV * NVV];
 #pragma unroll
   for (int c = 0; c < NV; ++c)
 #pragma unroll
-    for (int e = 0; e <= c; ++e) Rt[c * NVV + e] = 0.5 * (F[(NX + c) * NZ + NX + e] + F[(NX + e) * NZ + NX + c]);
+    for (int e = 0; e <= c; ++e) {
+      const bool pc = (pinmask >> c) & 1u, pe = (pinmask >> e) & 1u;
+      Rt[c * NVV + e] = (pc || pe) ? ((c == e) ? 1.0 : 0.0) : 0.5 * (F[(NX + c) * NZ + NX + e] + F[(NX + e) * NZ + NX + c]);
+    }
 #pragma unroll
   for (int c = 0; c < NV; ++c) {
     double dg = Rt[c * NVV + c];
 #pragma unroll
     for (int l = 0; l < c; ++l) dg -= Rt[c * NVV + l] * Rt[c * NVV + l];
-    if (!(dg > P.reg_tol)) return 3;
+    if (!((pinmask >> c) & 1u) && !(dg > P.reg_tol)) return 3;
     const double ld = sqrt(dg);
     Rt[c * NVV + c] = ld;
 #pragma unroll
@@ -156,10 +161,10 @@ TM_HD int tm_stage_factor_free(const TmProb& P, TmQpWs& s, int k, const double* 
   for (int a = 0; a < NV; ++a)
 #pragma unroll
     for (int c = 0; c < NV; ++c) {
-      double v = (a == c) ? 1.0 : 0.0;
+      double v = (a == c && !((pinmask >> a) & 1u)) ? 1.0 : 0.0;
 #pragma unroll
       for (int l = 0; l < c; ++l) v -= Rt[c * NVV + l] * Y[l * NVV + a];
-      Y[c * NVV + a] = v / Rt[c * NVV + c];
+      Y[c * NVV + a] = ((pinmask >> c) & 1u) ? 0.0 : v / Rt[c * NVV + c];
     }
   const TmP Wk = s.Wm + (size_t)k * NV * NV;
 #pragma unroll
@@ -187,8 +192,15 @@ TM_HD int tm_stage_factor_free(const TmProb& P, TmQpWs& s, int k, const double* 
     }
   }
 #pragma unroll
+  for (int c = 0; c < NZ; ++c) {                      // ftil = f + F[:,u] ku
+    double v = fv[c];
+#pragma unroll
+    for (int b2 = 0; b2 < NV; ++b2) v += 0.5 * (F[c * NZ + NX + b2] + F[(NX + b2) * NZ + c]) * ku[b2];
+    fv[c] = v;
+  }
+#pragma unroll
   for (int a = 0; a < NV; ++a) {
-    double v = 0.0;
+    double v = ku[a];
 #pragma unroll
     for (int b2 = 0; b2 < NV; ++b2) v -= Wl[a * NVV + b2] * fv[NX + b2];
     s.kkm[k * NV + a] = v;
@@ -197,9 +209,17 @@ TM_HD int tm_stage_factor_free(const TmProb& P, TmQpWs& s, int k, const double* 
   return 0;
 }
 
+#if defined(TM_COUNT_STAGES) && !defined(__CUDA_ARCH__)
+static long long tm_stage_counts[4] = {0, 0, 0, 0};   // twin diagnostics: stages without rows / with rows / total rows / with constraint-to-go
+#endif
 TM_HD int tm_stage_factor(const TmProb& P, TmQpWs& s, int k, int nr, double* F, double* fv) {
+#if defined(TM_COUNT_STAGES) && !defined(__CUDA_ARCH__)
+  tm_stage_counts[nr == 0 ? 0 : 1] += 1; tm_stage_counts[2] += nr; tm_stage_counts[3] += ((int)s.ncs[k + 1] > 0);
+  if ((tm_stage_counts[0] + tm_stage_counts[1]) % 20000 == 0)
+    fprintf(stderr, "[stages] free %lld with-rows %lld rows %lld ctg-stages %lld\n", tm_stage_counts[0], tm_stage_counts[1], tm_stage_counts[2], tm_stage_counts[3]);
+#endif
 #if NV > 0 && NV <= 4 && !defined(TM_NO_FREE_STAGE)
-  if (nr == 0) return tm_stage_factor_free(P, s, k, F, fv);
+  if (nr == 0) { double ku0[NV]; for (int a = 0; a < NV; ++a) ku0[a] = 0.0; return tm_stage_factor_pinned(P, s, k, 0u, ku0, F, fv); }
 #endif
   const TmP E = s.Ew;
   const double tolp = 1e-9, tolc = 1e-7;
@@ -542,8 +562,30 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
       ++nr;
     }
 #endif
+#if NV > 0 && NV <= 4 && NS == 0 && !defined(TM_NO_FREE_STAGE)
+    int simple = (ncn == 0);                          // every held row of the stage bounds one input of its own: fast path
+    unsigned pinmask = 0u;
+    double kuv[NV];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) kuv[a] = 0.0;
+#endif
     for (int i = 0; i < nh; ++i) {
       if (!tm_mask_get(amask, k * nh + i)) continue;
+#if NV > 0 && NV <= 4 && NS == 0 && !defined(TM_NO_FREE_STAGE)
+      {
+        const int rp = P.rowpin[i];
+        if (simple && rp >= 0 && !((pinmask >> rp) & 1u)) {
+          // the general elimination's arithmetic on this row: scale to max-abs 1, divide by the pivot, ku = -offset
+          const double cf = P.C[(size_t)i * NZ + NX + rp];
+          const double inv = 1.0 / fabs(cf);
+          const double ip = 1.0 / (cf * inv);
+          const double kv = -((s.hv[k * nh + i] * inv) * ip);
+          pinmask |= (1u << rp);
+#pragma unroll
+          for (int a = 0; a < NV; ++a) if (a == rp) kuv[a] = kv;
+        } else simple = 0;
+      }
+#endif
       TM_UNROLL_T
       for (int c = lane; c <= NZ; c += TM_NL) s.Ew[nr * TM_ES + c] = (c == NZ) ? s.hv[k * nh + i] : P.C[(size_t)i * NZ + c];
       ++nr;
@@ -572,7 +614,11 @@ TM_HD int tm_qp_factor(const TmProb& P, TmQpWs& s, const unsigned* amask, const 
       sf[c] = v;
     }
     TM_SYNC();
+#if NV > 0 && NV <= 4 && NS == 0 && !defined(TM_NO_FREE_STAGE)
+    if (lane == 0) s.sc[2] = (double)(simple ? tm_stage_factor_pinned(P, s, k, pinmask, kuv, sF, sf) : tm_stage_factor(P, s, k, nr, sF, sf));
+#else
     if (lane == 0) s.sc[2] = (double)tm_stage_factor(P, s, k, nr, sF, sf);
+#endif
     TM_SYNC();
     if (s.sc[2] != 0.0) return (int)s.sc[2];
     // P_k = [I;K]' F [I;K] (symmetrised), p_k = ftil_x + K' ftil_u
@@ -982,6 +1028,12 @@ TM_HD void tm_ricc_cols_term(const TmProb& P, TmQpWs& s, int E) {
   const int N = P.N, nh = P.nh, NI = N * nh, nxt = P.nxt;
   const int lane = TM_LANE;
 #if TM_NL > 1
+#ifdef TM_NO_FUSED_LANES
+  if (N <= TM_NL) {
+    for (int t = 0; t < nxt; ++t) tm_ricc_col_lanes(P, s, NI + t, s.Mc + (size_t)t * E);
+    return;
+  }
+#endif
   if (N <= TM_NL) {                                   // lane <-> stage: one load of the stage blocks, TM_TG chains per pass
     const bool mine = lane < N;
     TmLaneStage L;
@@ -1027,7 +1079,9 @@ TM_HD void tm_ricc_cols_term(const TmProb& P, TmQpWs& s, int E) {
 #pragma unroll
           for (int i = 0; i < NX; ++i) { const double t = tm_shfl(xo[g][i], step); if (lane == step + 1) z[g][i] = t; }
       }
-      for (int g = 0; g < ng; ++g) {
+#pragma unroll
+      for (int g = 0; g < TM_TG; ++g) {               // static g: the recursion vectors stay in registers
+        if (g >= ng) continue;
         const TmP mq = s.Mc + (size_t)(t0 + g) * E;
         if (mine) {
           for (int i = 0; i < nh; ++i) {
@@ -1156,7 +1210,8 @@ TM_HD void tm_ricc_cols_term(const TmProb& P, TmQpWs& s, int E) {
 #pragma unroll
           for (int g = 0; g < TM_TG; ++g) t[g] += cv * z[g][b];
         }
-        for (int g = 0; g < ng; ++g) s.Mc[(size_t)(t0 + g) * E + k * nh + i] = t[g];
+#pragma unroll
+        for (int g = 0; g < TM_TG; ++g) if (g < ng) s.Mc[(size_t)(t0 + g) * E + k * nh + i] = t[g];
       }
       double xn[TM_TG][NX];
 #pragma unroll
@@ -1178,7 +1233,9 @@ TM_HD void tm_ricc_cols_term(const TmProb& P, TmQpWs& s, int E) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) z[g][i] = xn[g][i];
     }
-    for (int g = 0; g < ng; ++g)
+#pragma unroll
+    for (int g = 0; g < TM_TG; ++g) {
+      if (g >= ng) continue;
       for (int t = lane; t < nxt; t += TM_NL) {
         const int ti = P.term_idx[t];
         double v = 0.0;
@@ -1186,6 +1243,7 @@ TM_HD void tm_ricc_cols_term(const TmProb& P, TmQpWs& s, int E) {
         for (int a = 0; a < NX; ++a) if (a == ti) v = z[g][a];
         s.Mc[(size_t)(t0 + g) * E + NI + t] = v;
       }
+    }
     TM_SYNC();
   }
 }
