@@ -103,9 +103,21 @@ int tmpc_get_index(const tmpc_handle* h, int64_t* index);
 /* One batched Pmpc.step: X0_dev (B*nx) -> U0_dev (B*nu).  Optional outputs (may be NULL): W_dev (B*n_w) primal
  * solution, LAM_dev (B*n_g) multipliers, G_dev (B*n_g) constraint values at the solution, status/iter/flags (B).
  * Side effects as in the reference: index += 1, warm start <- shifted solution (pmpc.py:415-421, 867-906).
- * Runs on `cuda_stream` (cudaStream_t, NULL = default) and returns after the SQP loop has finished. */
+ * Runs on `cuda_stream` (cudaStream_t, NULL = default) and returns after the SQP loop has finished (the host reads two device
+ * counters per SQP iteration); tmpc_step_async below is the stream-ordered, non-blocking form. */
 int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, double* W_dev, double* LAM_dev,
               double* G_dev, int32_t* status_dev, int32_t* iter_dev, int32_t* flags_dev, void* cuda_stream);
+/* The same step as a NON-BLOCKING call: returns at once, the SQP loop is driven by a host worker thread of the handle on an
+ * internal stream.  Work the caller enqueued on `cuda_stream` BEFORE the call (the producer of X0_dev) is waited for on the
+ * device; the outputs are complete -- visible to every stream -- once tmpc_wait has returned (it blocks the host and returns the
+ * step's code, 0 = ok, message via tmpc_last_error).  Until then no other call on the handle except tmpc_busy; one step in
+ * flight per handle.  Use: overlap host work or other handles (tuned and economic controller, several devices) with the solve.
+ * A device-side hold of the caller's stream (cuStreamWaitValue32 on a ticket the worker releases) was tried and deadlocked on the
+ * test box, see DESIGN.md section 1. */
+int tmpc_step_async(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, double* W_dev, double* LAM_dev,
+                    double* G_dev, int32_t* status_dev, int32_t* iter_dev, int32_t* flags_dev, void* cuda_stream);
+int tmpc_wait(tmpc_handle* h);
+int tmpc_busy(tmpc_handle* h, int32_t* busy);
 /* same call with HOST buffers (pinned or pageable): H2D of X0, solve, D2H of the requested outputs */
 int tmpc_step_host(tmpc_handle* h, const double* X0_host, int64_t B, double* U0_host, double* W_host,
                    double* LAM_host, double* G_host, int32_t* status_host, int32_t* iter_host, int32_t* flags_host);

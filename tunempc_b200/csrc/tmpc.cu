@@ -17,8 +17,12 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
 #include "tmpc.h"
 #include "tmpc_core.cuh"
 // model-dimension region (see tmpc_core.cuh): NZ, NU = NZM, NUM for the linearisation kernels
@@ -77,6 +81,16 @@ struct tmpc_handle {
   bool q0_ok = false;          // allocated and applicable (nh > 0, smem fits)
   int64_t q0_min = 1024;       // smallest batch for which tabulating (1 + nx + N*nh warp-level QP solves) pays off
   std::vector<char> phase_clean;   // per phase: no reference multiplier on an inequality row (empty convexification mask)
+  // ---- asynchronous step (tmpc_step_async / tmpc_wait): a host worker thread drives the SQP loop on an internal stream
+  struct AsyncJob { const double* X0; int64_t B; double *U0, *W, *LAM, *G; int32_t *status, *iter, *flags; } job{};
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv;
+  bool has_job = false, busy = false, quit = false, async_ready = false;
+  int job_rc = 0;
+  void* host_pinned = nullptr;      // 4 + TM_NCNT words: per-iteration counts and the counters of the step
+  cudaStream_t istream = nullptr;
+  cudaEvent_t ev_in = nullptr;
 };
 
 static int fail(tmpc_handle* h, const char* what, cudaError_t e) {
@@ -572,6 +586,11 @@ int tmpc_create(tmpc_handle** out, const tmpc_dims* dims, const tmpc_opts* opts,
   }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&h->ev[i]);
   h->ev_ok = true;
+  if (cudaHostAlloc(&h->host_pinned, (4 + TM_NCNT) * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) {
+    fprintf(stderr, "tmpc_create: cannot allocate pinned host memory\n");
+    delete h;
+    return 5;
+  }
   if (cudaMalloc(&P.prof_counters, 4 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(P.prof_counters, 0, 4 * sizeof(unsigned long long));
   *out = h;
   return 0;
@@ -584,7 +603,16 @@ static void free_list(std::vector<void*>& v) {
 
 void tmpc_destroy(tmpc_handle* h) {
   if (!h) return;
+  if (h->worker.joinable()) {
+    { std::lock_guard<std::mutex> lk(h->mu); h->quit = true; }
+    h->cv.notify_all();
+    h->worker.join();
+  }
   cudaSetDevice(h->device);
+  if (h->host_pinned) cudaFreeHost(h->host_pinned);
+  if (h->istream) cudaStreamDestroy(h->istream);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+
   free_list(h->tab_allocs);
   free_list(h->ws_allocs);
   if (h->qp_ws) cudaFree(h->qp_ws);
@@ -763,7 +791,9 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   const int* cur = nullptr;   // nullptr = identity list (all instances)
   const int* src = nullptr;   // the list the previous iteration produced (list_a / list_b), before sorting
   int64_t nact = B;
-  int hc[2];
+  // pinned host words for the per-iteration counters: a D2H copy into pageable memory is not truly asynchronous (it may
+  // synchronise with the legacy default stream, which tmpc_step_async holds on its ticket)
+  int* hc = (int*)h->host_pinned;
   int iter_guard = 0;
   while (nact > 0) {
     const unsigned wb = (unsigned)((nact + QP_WARPS - 1) / QP_WARPS);
@@ -866,8 +896,8 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
   ++launches;
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev[7], st));
-  unsigned long long cnt_host[TM_NCNT];
-  CK(cudaMemcpyAsync(cnt_host, S.counters, sizeof cnt_host, cudaMemcpyDeviceToHost, st));
+  unsigned long long* cnt_host = (unsigned long long*)h->host_pinned + 4;
+  CK(cudaMemcpyAsync(cnt_host, S.counters, TM_NCNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   { double* t = S.W; S.W = h->Wsh; h->Wsh = t; }
   { double* t = S.LAM; S.LAM = h->Lsh; h->Lsh = t; }
@@ -893,6 +923,69 @@ int tmpc_step(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, d
               (double)cnt_host[20] / cnt_host[5], (double)pc[0] / cnt_host[5], (double)cnt_host[21] / cnt_host[5], (double)cnt_host[22] / cnt_host[5], (double)cnt_host[23] / cnt_host[5]);
     }
   }
+  return 0;
+}
+
+// ---- asynchronous call -------------------------------------------------------------------------------------------------------
+static void async_worker(tmpc_handle* h) {
+  cudaSetDevice(h->device);
+  for (;;) {
+    tmpc_handle::AsyncJob j;
+    {
+      std::unique_lock<std::mutex> lk(h->mu);
+      h->cv.wait(lk, [h] { return h->has_job || h->quit; });
+      if (h->quit) return;
+      j = h->job;
+      h->has_job = false;
+    }
+    cudaStreamWaitEvent(h->istream, h->ev_in, 0);                  // inputs enqueued on the caller's stream before the call
+    const int rc = tmpc_step(h, j.X0, j.B, j.U0, j.W, j.LAM, j.G, j.status, j.iter, j.flags, (void*)h->istream);
+    cudaStreamSynchronize(h->istream);                             // every output is complete before the step reports done
+    {
+      std::lock_guard<std::mutex> lk(h->mu);
+      h->job_rc = rc;
+      h->busy = false;
+    }
+    h->cv.notify_all();
+  }
+}
+
+int tmpc_step_async(tmpc_handle* h, const double* X0_dev, int64_t B, double* U0_dev, double* W_dev, double* LAM_dev,
+                    double* G_dev, int32_t* status_dev, int32_t* iter_dev, int32_t* flags_dev, void* cuda_stream) {
+  if (!h) return 1;
+  cudaSetDevice(h->device);
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->busy) { h->err = "tmpc_step_async: a step is still in flight on this handle (call tmpc_wait first)"; return 1; }
+  }
+  if (!h->async_ready) {
+    CK(cudaStreamCreateWithFlags(&h->istream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    h->worker = std::thread(async_worker, h);
+    h->async_ready = true;
+  }
+  CK(cudaEventRecord(h->ev_in, (cudaStream_t)cuda_stream));       // the worker's stream waits for what the caller enqueued so far
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->job = {X0_dev, B, U0_dev, W_dev, LAM_dev, G_dev, status_dev, iter_dev, flags_dev};
+    h->has_job = true;
+    h->busy = true;
+  }
+  h->cv.notify_all();
+  return 0;
+}
+
+int tmpc_wait(tmpc_handle* h) {
+  if (!h) return 1;
+  std::unique_lock<std::mutex> lk(h->mu);
+  h->cv.wait(lk, [h] { return !h->busy; });
+  return h->job_rc;
+}
+
+int tmpc_busy(tmpc_handle* h, int32_t* busy) {
+  if (!h || !busy) return 1;
+  std::lock_guard<std::mutex> lk(h->mu);
+  *busy = h->busy ? 1 : 0;
   return 0;
 }
 

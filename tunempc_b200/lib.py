@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-std=c++17", "--threads", "2"]      # the two translation units of a model library compile side by side
 
 EXPORTS = ["tmpc_default_opts", "tmpc_model_info", "tmpc_model_slacks", "tmpc_create", "tmpc_destroy", "tmpc_last_error",
-           "tmpc_set_tables", "tmpc_reset", "tmpc_get_index", "tmpc_step", "tmpc_step_host", "tmpc_plant_step", "tmpc_stage_log",
+           "tmpc_set_tables", "tmpc_reset", "tmpc_get_index", "tmpc_step", "tmpc_step_async", "tmpc_wait", "tmpc_busy", "tmpc_step_host", "tmpc_plant_step", "tmpc_stage_log",
            "tmpc_get_log", "tmpc_get_counters", "tmpc_get_timing", "tmpc_stage_eval_host", "tmpc_fp64_peak"]
 
 
@@ -81,6 +81,9 @@ class ModelLib:
         L.tmpc_reset.argtypes = [vp, ctypes.c_int64]
         L.tmpc_get_index.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
         L.tmpc_step.argtypes = [vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.tmpc_step_async.argtypes = [vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.tmpc_wait.argtypes = [vp]
+        L.tmpc_busy.argtypes = [vp, _ip]
         L.tmpc_step_host.argtypes = [vp, vp, ctypes.c_int64, vp, vp, vp, vp, vp, vp, vp]
         L.tmpc_plant_step.argtypes = [vp, vp, vp, ctypes.c_int64, vp, vp]
         L.tmpc_stage_log.argtypes = [vp, vp, vp, ctypes.c_int64, vp, vp, vp]

@@ -169,6 +169,7 @@ class Pmpc:
         self.__B = 0
         self.__index = 0
         self.__out = None
+        self.__pending = None
         self.__initialize_log()
 
     # ---- plumbing ------------------------------------------------------------------------------------
@@ -267,6 +268,57 @@ class Pmpc:
         if single_shape is not None:
             return U0[0].reshape((pb.nu, 1) if len(single_shape) == 2 else (pb.nu,)).copy()
         return U0
+
+    def step_async(self, X0, outputs="u0"):
+        """`step(X0)` as a non-blocking call (C ABI: tmpc_step_async): returns the output tensor U0 (B,nu) at once while a
+        worker thread of the library drives the solve; what was enqueued on the current CUDA stream before the call (the
+        producer of X0) is waited for on the device.  `wait()` blocks the host until the solve has finished, appends the log and
+        returns U0 -- only then may U0 be read.  One step in flight per controller: call `wait()` before the next
+        `step` / `step_async` / `reset`."""
+        import torch
+        pb = self.__pb
+        if getattr(self, "_Pmpc__pending", None) is not None:
+            raise RuntimeError("step_async: a step is still in flight (call wait() first)")
+        if not (type(X0).__module__.startswith("torch") and X0.is_cuda and X0.dtype == torch.float64):
+            raise TypeError("step_async takes a float64 CUDA tensor (B, nx)")
+        if X0.dim() != 2 or X0.shape[1] != pb.nx:
+            raise ValueError("expected X0 of shape (B, %d)" % pb.nx)
+        X0 = X0.contiguous()
+        B = X0.shape[0]
+        self.__ensure_batch(B)
+        dev = X0.device
+        full = outputs == "all"
+        U0 = torch.empty((B, pb.nu), dtype=torch.float64, device=dev)
+        W = torch.empty((B, pb.n_w), dtype=torch.float64, device=dev) if full else None
+        LAM = torch.empty((B, pb.n_g), dtype=torch.float64, device=dev) if full else None
+        G = torch.empty((B, pb.n_g), dtype=torch.float64, device=dev) if full else None
+        st = torch.empty(B, dtype=torch.int32, device=dev)
+        it = torch.empty(B, dtype=torch.int32, device=dev)
+        fl = torch.empty(B, dtype=torch.int32, device=dev)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        self.__check(self.__lib.lib.tmpc_step_async(self.__h, ptr(X0), B, ptr(U0), ptr(W), ptr(LAM), ptr(G), ptr(st), ptr(it),
+                                                    ptr(fl), stream))
+        self.__pending = dict(out=dict(u0=U0, w=W, lam_g=LAM, g=G, status=st, iter=it, flags=fl), dev=dev, keep=X0)
+        return U0
+
+    def busy(self):
+        b = ctypes.c_int32()
+        self.__check(self.__lib.lib.tmpc_busy(self.__h, ctypes.byref(b)))
+        return bool(b.value)
+
+    def wait(self):
+        """block the host until the step started by `step_async` has finished; returns its U0"""
+        pend = getattr(self, "_Pmpc__pending", None)
+        if pend is None:
+            return self.__out["u0"] if self.__out else None
+        rc = self.__lib.lib.tmpc_wait(self.__h)
+        self.__pending = None
+        self.__check(rc)
+        self.__out = pend["out"]
+        self.__log_append(torch_dev=pend["dev"])
+        self.__index += 1
+        return self.__out["u0"]
 
     def __log_append(self, torch_dev=None):                           # pmpc.py:815-831
         o = self.__out
