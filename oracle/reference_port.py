@@ -30,7 +30,7 @@ def _p(a):
     return a.ctypes.data_as(_dp) if a is not None else None
 
 
-def build(models=("lq", "cstr", "unicycle", "evaporation", "chain", "dims9", "awe9")):
+def build(models=("lq", "cstr", "unicycle", "evaporation", "chain", "dims9", "awe9", "evaporation_sc1")):
     """compile the C restatement (and oracle/_ref when the reference tree is present)."""
     subprocess.check_call(["make", "-s", "-C", _HERE, "MODELS=" + " ".join(models)])
 

@@ -295,6 +295,15 @@ def awe9_problem(stage_F, N=None, hessian_approximation="exact"):
     return pb, info
 
 
+def evaporation_sc1():
+    """examples/evaporation_process with `create_mpc(..., opts={'slack_flag': 'active'})` (tuner.py:171-177): the one row that is
+    active at the steady state (X2 >= 25) is softened -> the model library variant with nsc = 1"""
+    from .constraints import soft_model
+    card = evaporation()
+    card["model"] = soft_model(card["model"], 1)
+    return card
+
+
 def sample_x0(name, pb, B, seed=0):
     """synthetic initial states of SURVEY.md section 8(d): the reference examples' own perturbation recipes, seeded"""
     rng = np.random.default_rng(seed)
@@ -307,7 +316,7 @@ def sample_x0(name, pb, B, seed=0):
         X0[:, 0] += alpha * (1.0 - xs[0])                       # dx_diehl direction, examples/cstr/main.py:126-131
         X0[:, 1:] += 1e-2 * np.abs(xs[1:]) * rng.uniform(-1, 1, (B, pb.nx - 1))
         return X0
-    if name == "evaporation":
+    if name in ("evaporation", "evaporation_sc1"):
         # X2 sits on its bound 25.0 -> perturb upward only; P2 +-1.0 (examples/evaporation_process/main.py:178-180)
         return xs + np.stack([0.5 * np.abs(rng.uniform(-1, 1, B)), 1.0 * rng.uniform(-1, 1, B)], axis=1)
     if name == "chain":
@@ -322,7 +331,7 @@ def sample_x0(name, pb, B, seed=0):
 
 
 CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle, "evaporation": evaporation, "chain": chain, "dims9": dims9,
-           "awe9": awe9}
+           "awe9": awe9, "evaporation_sc1": evaporation_sc1}
 
 
 def make_problem(name, stage_F, N=None, hessian_approximation="exact", mpc_type="tuned"):

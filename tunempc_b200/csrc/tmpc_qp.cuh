@@ -1732,6 +1732,30 @@ TM_HD void tm_pin_soft_slacks(const TmProb& P, unsigned* mask) {
 #endif
 }
 
+// Stage 0 of a softened row that depends on the state only: x_0 is fixed, so the row's value v = h_i(x0) + usc_j(iterate) is known
+// before the solve and decides which of the two rows is active there -- the softened row (usc_j = -h_i(x0) > 0) when the state
+// violates the bound, else usc_j >= 0.  Holding both (what the shifted multipliers may ask for) is inconsistent.  w: the iterate.
+TM_HD void tm_soft_stage0(const TmProb& P, const TmQpWs& s, const double* e0, const double* w, unsigned* mask) {
+#if NSC > 0
+  const int nh = P.nh;
+  for (int j = 0; j < NSC; ++j) {
+    const int es = nh - NSC + j;
+    int er = -1;
+    for (int i = 0; i < nh - NSC; ++i) if (P.C[(size_t)i * NZ + NZM + NS + j] != 0.0) { er = i; break; }
+    if (er < 0 || P.relax0[er]) continue;
+    int state_only = 1;
+    for (int c = NX; c < NZ; ++c) if (c != NZM + NS + j && P.C[(size_t)er * NZ + c] != 0.0) state_only = 0;
+    if (!state_only) continue;
+    double v = s.hv[er] - P.C[(size_t)er * NZ + NZM + NS + j] * w[NZM + NS + j];   // the row at the new x_0 with its slack at zero
+    for (int c = 0; c < NX; ++c) v += P.C[(size_t)er * NZ + c] * e0[c];
+    if (v < -1e-12 || P.relax0[es]) { tm_mask_set(mask, er); tm_mask_clr(mask, es); }
+    else { tm_mask_clr(mask, er); tm_mask_set(mask, es); }
+  }
+#else
+  (void)P; (void)s; (void)e0; (void)mask;
+#endif
+}
+
 // One QP with the base rows in amask.  returns 0 ok (step and multipliers in dout / lq, wrong-sign base rows reported
 // in nwrong / amask_next), 2 infeasible, 3 base not positive definite, 6 base rows inconsistent, 7 working-set overflow.
 // amask_next = base rows with a correctly signed multiplier + the rows the dual active set added: the working set a
@@ -1746,6 +1770,7 @@ TM_HDN int tm_qp_solve(const TmProb& P, const TmState& S, int64_t inst, TmQpWs& 
   unsigned amask[TM_ALW];
   for (int wd = 0; wd < TM_ALW; ++wd) amask[wd] = amask_in[wd];
   tm_pin_soft_slacks(P, amask);
+  if (!pert) tm_soft_stage0(P, s, s.pv + 2 * NX, S.W + inst * P.n_w, amask);
 #else
   const unsigned* amask = amask_in;
 #endif

@@ -116,14 +116,28 @@ class Tuner(object):
         if opts.get("p_operator") is None:
             opts["p_operator"] = self.__card.get("term_idx", list(range(self.__nx)))
         p = self.__p
+        mpc_sys = self.sys
+        if opts.get("slack_flag", "none") != "none":                                         # tuner.py:171-177
+            # soft constraints (preprocessing.add_mpc_slacks): rows softened by usc >= 0 with an L1 penalty; the stage width is a
+            # compile-time constant of the model library, so the controller runs on the library variant <model>_sc<nsc>
+            from . import constraints, modelgen
+            from .lib import build_model_lib
+            Cs, cs, scost, rows = constraints.soften_rows(self.__C, self.__c, self.__lam_h, opts["slack_flag"])
+            if len(rows):
+                model = constraints.soft_model(self.__model, len(rows))
+                hdr = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "gen", "model_%s.h" % model.name)
+                modelgen.generate_header(model, hdr)
+                build_model_lib(model.name)                                                  # no-op when the library is up to date
+                mpc_sys = {"f": model, "h": (Cs, cs), "scost": scost,
+                           "vars": {"x": model.x, "u": model.u, "usc": list(range(len(rows)))}}
         wref = {"x": [self.__w_sol[k, :self.__nx] for k in range(p)], "u": [self.__w_sol[k, self.__nx:] for k in range(p)]}
         sens = {"A": self.__S["A"], "B": self.__S["B"]}
         if mpc_type == "economic":                                                           # tuner.py:180-182: full lam_g
             lam_g_ref = {"dyn": list(self.__lam_dyn), "h": list(self.__lam_h)}
-            return Pmpc(N=N, sys=self.sys, cost="economic", wref=wref, lam_g_ref=lam_g_ref, sensitivities=sens,
+            return Pmpc(N=N, sys=mpc_sys, cost="economic", wref=wref, lam_g_ref=lam_g_ref, sensitivities=sens,
                         options=opts, device=device)
         lam_g0 = {"dyn": [np.zeros(self.__nx)] * p, "h": list(self.__lam_h)}                # tuner.py:186-189: lam_g0['dyn'] = 0
-        return Pmpc(N=N, sys=self.sys, cost="tracking", wref=wref, tuning=tuning, lam_g_ref=lam_g0, sensitivities=sens,
+        return Pmpc(N=N, sys=mpc_sys, cost="tracking", wref=wref, tuning=tuning, lam_g_ref=lam_g0, sensitivities=sens,
                     options=opts, device=device)
 
     # ---- properties (tuner.py:201-264) -------------------------------------------------------------------
