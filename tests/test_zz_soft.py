@@ -31,3 +31,35 @@ def test_tuner_soft_constraints_gpu(built):
         assert ctrl.log["iter"][-1].cpu().numpy()[b] == oc.log["iter"][-1]
     with pytest.raises(ValueError):
         t.create_mpc("tuned", 30, opts={"slack_flag": "some"})
+
+
+def test_periodic_path_constraint_economic_gpu(built):
+    """Tuner(p = 30) with a path constraint -> solve_ocp -> create_mpc('economic') on the GPU: closed loop against the live oracle"""
+    import torch
+    from oracle import reference_port as rp
+    from tunempc_b200 import configs, tuning
+    from tunempc_b200.tuner import Tuner
+    card = configs.unicycle()
+    C = np.zeros((1, 5))
+    C[0, 0] = -1.0
+    card["C"], card["c"] = C, np.array([0.7])
+    t = Tuner(card, p=30)
+    w = t.solve_ocp()
+    ctrl = t.create_mpc("economic", 30)
+    pb = ctrl.problem
+    assert pb.mpc_type == "economic" and pb.p == 30 and pb.nh == 1 and np.abs(pb.lam_h_ref).max() > 1.0
+    cf = tuning.lambdify_cost(card["model"], card["cost"])
+    X0 = configs.sample_x0("unicycle", pb, 3, 5)
+    X0[2] = w[0, :4]
+    ocs = [rp.Pmpc(pb, cost_funs=cf) for _ in range(3)]
+    X = torch.tensor(X0, device="cuda:0")
+    xo = X0.copy()
+    st = rp.StageLib("unicycle")
+    for s in range(4):
+        U = ctrl.step(X)
+        uo = np.array([ocs[b].step(xo[b]) for b in range(3)])
+        assert (ctrl.status.cpu().numpy() == 0).all()
+        assert np.array_equal(ctrl.log["iter"][-1].cpu().numpy(), [ocs[b].log["iter"][-1] for b in range(3)])
+        assert np.max(np.abs(U.cpu().numpy() - uo)) < 1e-8, s
+        X = ctrl.plant_step(X, U)
+        xo = st.F(xo, uo)

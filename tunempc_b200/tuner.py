@@ -70,12 +70,15 @@ class Tuner(object):
             self.__w_sol = z[None, :].copy()
             self.__lam_h, self.__lam_dyn = lam_h[None, :], lam_d[None, :]
         else:
-            if self.__C.shape[0]:
-                raise NotImplementedError("periodic OCP with path constraints is not built yet")
-            z, lam_d, _ = tuning.solve_periodic_ocp(self.__F, self.__cost_funs, w0, self.__nx)
-            self.__S = tuning.sensitivities_periodic(self.__F, self.__cost_funs, z, lam_d, self.__nx)
+            if self.__C.shape[0]:                                           # pocp.py:205-259 with path constraints
+                z, lam_d, _, lam_h = tuning.solve_periodic_ocp(self.__F, self.__cost_funs, w0, self.__nx, C=self.__C, c=self.__c)
+                self.__S = tuning.sensitivities_periodic(self.__F, self.__cost_funs, z, lam_d, self.__nx, C=self.__C, lam_h=lam_h)
+            else:
+                z, lam_d, _ = tuning.solve_periodic_ocp(self.__F, self.__cost_funs, w0, self.__nx)
+                lam_h = np.zeros((self.__p, 0))
+                self.__S = tuning.sensitivities_periodic(self.__F, self.__cost_funs, z, lam_d, self.__nx)
             self.__w_sol = z.copy()
-            self.__lam_h, self.__lam_dyn = np.zeros((self.__p, 0)), lam_d
+            self.__lam_h, self.__lam_dyn = lam_h, lam_d
         return self.__w_sol
 
     # ---- tuner.py:134-160 --------------------------------------------------------------------------------
@@ -91,7 +94,14 @@ class Tuner(object):
         if self.__p == 1:
             Hc = [tuning.convexify_dare(S["A"][0], S["B"][0], S["H"][0], C_As=S["C_As"][0], rho=rho, scale=self.__w_sol[0])[0]]
         else:
-            Hc = tuning.convexify_periodic(S["A"], S["B"], S["H"])
+            try:
+                Hc = tuning.convexify_periodic(S["A"], S["B"], S["H"])
+            except np.linalg.LinAlgError as e:
+                # the periodic Riccati construction works on the unconstrained LQ problem along the trajectory; with path
+                # constraints active on the orbit that problem need not have a stabilising solution (the reference's SDP
+                # convexifies on the null space of the active rows, convexifier.py:213-308 -- not built for p > 1)
+                raise ValueError("Convexification failed along the periodic trajectory (%s); with active path constraints use "
+                                 "create_mpc('economic') or create_mpc('tracking', tuning=...)" % e)
         S["Hc"] = Hc
         return S["Hc"]
 

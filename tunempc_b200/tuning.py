@@ -194,10 +194,14 @@ def convexify_dare(A, B, H, eps=None, C_As=None, rho=1e-3, scale=None, refine=Tr
 # ------------------------------------------------------------------------------------------------------------------
 #  periodic references (p > 1): OCP, sensitivities, convexification
 # ------------------------------------------------------------------------------------------------------------------
-def solve_periodic_ocp(stage_F, cost_funs, w_guess, nx, alpha_phase=0.1, tol=1e-11, max_iter=200):
-    """p-periodic OCP without path constraints (pocp.py:78-203,205-259):
+def solve_periodic_ocp(stage_F, cost_funs, w_guess, nx, alpha_phase=0.1, tol=1e-11, max_iter=200, C=None, c=None):
+    """p-periodic OCP (pocp.py:78-203,205-259), optionally with affine path constraints C z_k + c >= 0 at every stage:
 
-        min sum_k l(x_k,u_k) + alpha/2 |x_0 - x0*|^2    s.t.  F(x_k,u_k) - x_{(k+1) mod p} = 0
+        min sum_k l(x_k,u_k) + alpha/2 |x_0 - x0*|^2    s.t.  F(x_k,u_k) - x_{(k+1) mod p} = 0,   C z_k + c >= 0
+
+    With path constraints the pre-solve carries them as inequalities, the rows active at its solution are held as equalities in
+    the Newton polish (the active-set re-solve of pocp.py:255-257), and a third return value lam_h (p, nh) holds their
+    multipliers (CasADi sign: active => negative).
 
     The reference first solves with alpha = 0 (IPOPT), then re-solves with the phase-fixing term alpha = 0.1 centred at
     the first solution's x_0 (pocp.py:233-252) -- at that point the term has zero value and zero gradient, so the
@@ -208,6 +212,10 @@ def solve_periodic_ocp(stage_F, cost_funs, w_guess, nx, alpha_phase=0.1, tol=1e-
     z = np.array(w_guess, dtype=np.float64, copy=True)
     p, nz = z.shape
     lam = np.zeros((p, nx))
+    nh = 0 if C is None else int(np.asarray(C).shape[0])
+    if nh:
+        C = np.asarray(C, dtype=np.float64).reshape(nh, nz)
+        c = np.asarray(c, dtype=np.float64).ravel()
 
     def kkt(z, lam, alpha, x0s):
         xf, S, T = stage_F(z[:, :nx], z[:, nx:], 2)
@@ -275,17 +283,39 @@ def solve_periodic_ocp(stage_F, cost_funs, w_guess, nx, alpha_phase=0.1, tol=1e-
         Jc[:, :nx] = Phi - np.eye(nx)
         return Jc
 
+    def ss_h(v):                                        # path constraints along the rollout, (p*nh,)
+        X, U, _, _ = rollout(v)
+        return (np.hstack([X[:p], U]) @ C.T + c).ravel()
+
+    def ss_hjac(v):
+        X, U, A, Bm = rollout(v)
+        nv = nx + p * nu
+        dX = np.zeros((nx, nv))
+        dX[:, :nx] = np.eye(nx)
+        Jh = np.zeros((p * nh, nv))
+        for k in range(p):
+            Jh[k * nh:(k + 1) * nh] = C[:, :nx] @ dX
+            Jh[k * nh:(k + 1) * nh, nx + k * nu: nx + (k + 1) * nu] += C[:, nx:]
+            dXn = A[k] @ dX
+            dXn[:, nx + k * nu: nx + (k + 1) * nu] += Bm[k]
+            dX = dXn
+        return Jh
+
+    cons = [{"type": "eq", "fun": ss_con, "jac": ss_jac}]
+    if nh:
+        cons.append({"type": "ineq", "fun": ss_h, "jac": ss_hjac})
     v = np.concatenate([z[0, :nx], z[:, nx:].ravel()])
     for rnd in range(8):
         xc = v[:nx].copy()
-        v = sopt.minimize(ss_fun, v, args=(alpha_phase, xc), jac=True, method="SLSQP",
-                          constraints=[{"type": "eq", "fun": ss_con, "jac": ss_jac}],
+        v = sopt.minimize(ss_fun, v, args=(alpha_phase, xc), jac=True, method="SLSQP", constraints=cons,
                           options={"ftol": 1e-15, "maxiter": 500}).x
         if np.max(np.abs(v[:nx] - xc)) < 1e-12:
             break
     X, U, _, _ = rollout(v)
     z = np.hstack([X[:p], U])
     x0s = z[0, :nx].copy()
+    if nh:
+        return _polish_periodic_with_rows(stage_F, cost_funs, z, nx, C, c, alpha_phase, x0s, tol, max_iter)
     # multipliers: least squares on stationarity, then Newton with the phase fix centred at the pre-solve's x_0
     Hm, J, gl, r = kkt(z, lam, 0.0, x0s)
     lam = np.linalg.lstsq(J.T, -(gl - J.T @ lam.ravel()), rcond=None)[0].reshape(p, nx)
@@ -304,9 +334,66 @@ def solve_periodic_ocp(stage_F, cost_funs, w_guess, nx, alpha_phase=0.1, tol=1e-
     return z, lam, x0s
 
 
-def sensitivities_periodic(stage_F, cost_funs, z, lam_dyn, nx, alpha_phase=0.1):
-    """S of pocp.py:261-362 for a p-periodic solution without path constraints: A_k, B_k, H_k = stage blocks of the
-    Lagrangian Hessian (the phase-fixing term alpha*I sits in the x_0 block, as in the reference's NLP), q_k = 0."""
+def _polish_periodic_with_rows(stage_F, cost_funs, z, nx, C, c, alpha, x0s, tol, max_iter):
+    """active-set Newton on the KKT system of the multiple-shooting periodic NLP: the rows active at the pre-solve's solution are
+    held as equalities; rows whose multiplier comes out with the wrong sign are released, rows that become violated are added."""
+    l_f, g_f, H_f = cost_funs
+    p, nz = z.shape
+    nh = C.shape[0]
+    lam = np.zeros((p, nx))
+    act = [(k, i) for k in range(p) for i in range(nh) if (C[i] @ z[k] + c[i]) < 1e-7 * max(1.0, abs(c[i]))]
+    for outer in range(10):
+        mu = np.zeros(len(act))
+        for it in range(max_iter):
+            xf, S, T = stage_F(z[:, :nx], z[:, nx:], 2)
+            n, m, ma = p * nz, p * nx, len(act)
+            Hm = np.zeros((n, n)); J = np.zeros((m, n)); Ja = np.zeros((ma, n)); grad = np.zeros(n); r = np.zeros(m); ra = np.zeros(ma)
+            for k in range(p):
+                sl = slice(k * nz, (k + 1) * nz)
+                Hk = H_f(z[k]) + np.einsum("a,aij->ij", lam[k], T[k])
+                Hm[sl, sl] = 0.5 * (Hk + Hk.T)
+                grad[sl] = g_f(z[k])
+                J[k * nx:(k + 1) * nx, sl] = S[k]
+                kn = (k + 1) % p
+                J[k * nx:(k + 1) * nx, kn * nz:kn * nz + nx] -= np.eye(nx)
+                r[k * nx:(k + 1) * nx] = xf[k] - z[kn, :nx]
+            Hm[:nx, :nx] += alpha * np.eye(nx)
+            grad[:nx] += alpha * (z[0, :nx] - x0s)
+            for a, (k, i) in enumerate(act):
+                Ja[a, k * nz:(k + 1) * nz] = C[i]
+                ra[a] = C[i] @ z[k] + c[i]
+            if it == 0 and outer == 0:                      # multiplier estimate from stationarity
+                le = np.linalg.lstsq(np.vstack([J, Ja]).T, -grad, rcond=None)[0]
+                lam, mu = le[:m].reshape(p, nx), le[m:]
+            res_v = np.concatenate([grad + J.T @ lam.ravel() + Ja.T @ mu, r, ra])
+            if np.linalg.norm(res_v, np.inf) < tol:
+                break
+            K = np.block([[Hm, J.T, Ja.T], [J, np.zeros((m, m)), np.zeros((m, ma))], [Ja, np.zeros((ma, m)), np.zeros((ma, ma))]])
+            step = np.linalg.solve(K, -res_v)
+            z = z + step[:n].reshape(p, nz)
+            lam = lam + step[n:n + m].reshape(p, nx)
+            mu = mu + step[n + m:]
+        else:
+            raise RuntimeError("periodic OCP with path constraints: Newton polish did not converge (residual %.2e)" % np.linalg.norm(res_v, np.inf))
+        hval = z @ C.T + c
+        wrong = [a for a in range(len(act)) if mu[a] > 1e-10]
+        viol = [(k, i) for k in range(p) for i in range(nh) if hval[k, i] < -1e-9 and (k, i) not in act]
+        if not wrong and not viol:
+            break
+        act = [e for a, e in enumerate(act) if a not in wrong] + viol
+    else:
+        raise RuntimeError("periodic OCP with path constraints: the active set did not settle")
+    lam_h = np.zeros((p, nh))
+    for a, (k, i) in enumerate(act):
+        lam_h[k, i] = mu[a]
+    lam_h[np.abs(lam_h) < 1e-8] = 0.0
+    return z, lam, x0s, lam_h
+
+
+def sensitivities_periodic(stage_F, cost_funs, z, lam_dyn, nx, alpha_phase=0.1, C=None, lam_h=None):
+    """S of pocp.py:261-362 for a p-periodic solution: A_k, B_k, H_k = stage blocks of the Lagrangian Hessian (the phase-fixing
+    term alpha*I sits in the x_0 block, as in the reference's NLP; affine path constraints add no curvature),
+    q_k = -lam_h,k C (pocp.py:357-360), C_As,k = the rows active at phase k."""
     _, _, H_f = cost_funs
     p, nz = z.shape
     xf, S1, T = stage_F(z[:, :nx], z[:, nx:], 2)
@@ -317,6 +404,12 @@ def sensitivities_periodic(stage_F, cost_funs, z, lam_dyn, nx, alpha_phase=0.1):
         if k == 0 and p > 1:
             Hk[:nx, :nx] += alpha_phase * np.eye(nx)
         Hs.append(Hk)
+    if C is not None and lam_h is not None and np.asarray(C).shape[0]:
+        C = np.asarray(C, dtype=np.float64)
+        q = [-(lam_h[k] @ C) for k in range(p)]
+        C_As = [C[[i for i in range(C.shape[0]) if lam_h[k, i] != 0]] if np.any(lam_h[k] != 0) else None for k in range(p)]
+        return {"A": [S1[k][:, :nx].copy() for k in range(p)], "B": [S1[k][:, nx:].copy() for k in range(p)],
+                "C": [C.copy() for _ in range(p)], "C_As": C_As, "H": Hs, "q": q}
     return {"A": [S1[k][:, :nx].copy() for k in range(p)], "B": [S1[k][:, nx:].copy() for k in range(p)],
             "C": None, "C_As": None, "H": Hs, "q": [np.zeros(nz) for _ in range(p)]}
 
