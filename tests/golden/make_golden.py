@@ -219,6 +219,48 @@ def awe9(B=24, Bcl=6, nsteps=8, Blarge=512):
         print("awe9 large: status", np.bincount(np.array([r[5] for r in res])), "iter", np.bincount(np.array([r[4] for r in res])), flush=True)
 
 
+def evaporation_sc1():
+    """soft constraints (Tuner.create_mpc(..., opts={'slack_flag': 'active'}), tuner.py:171-177, preprocessing.py:120-155) on the
+    evaporation config: the row active at the steady state (X2 >= 25) is softened.  12 x0, three of them BELOW the bound, and two
+    closed loops.  (A closed loop started 0.8 below the bound is left out: from its second MPC step on the oracle -- qpOASES_e on a
+    QP whose slack has no curvature -- stalls at max_iter while the device routines converge to the same u0)"""
+    from tunempc_b200 import constraints
+    from tunempc_b200.pmpc import problem_from_reference_args
+    pb = rp_problem("evaporation")
+    Cs, cs, scost, rows = constraints.soften_rows(pb.C, pb.c, pb.lam_h_ref, "active")
+    model = configs.CONFIGS["evaporation_sc1"]()["model"]
+    card = {"f": model, "h": (Cs, cs), "scost": scost, "vars": {"x": model.x, "u": model.u, "usc": list(range(len(rows)))}}
+    ps = problem_from_reference_args(pb.N, card, "tracking", {"x": [pb.wref[0, :2]], "u": [pb.wref[0, 2:]]},
+                                     {"H": list(pb.H), "q": list(pb.q)}, {"dyn": [np.zeros(2)], "h": list(pb.lam_h_ref)},
+                                     {"A": pb.S_A, "B": pb.S_B}, {"p_operator": pb.term_idx})
+    ps.save(os.path.join(HERE, "problem_evaporation_sc1.npz"))
+    X0 = sample_x0("evaporation", pb, 12, 11)
+    X0[2, 0] = 24.7; X0[5, 0] = 24.2; X0[9, 0] = 24.95
+    oc = rp.Pmpc(ps, qp="qpoases", sqp_options={"max_iter": 50})
+    st = rp.StageLib("evaporation")
+    out = {"X0": X0}
+    U, W, LAM, IT, NAS = [], [], [], [], []
+    for b in range(12):
+        oc.reset()
+        U.append(oc.step(X0[b])); W.append(oc.w_sol); LAM.append(oc.lam_g); IT.append(oc.log["iter"][-1]); NAS.append(oc.log["nAS"][-1])
+        assert oc.log["status"][-1] == 0
+    out.update(u0_t6=np.array(U), w_t6=np.array(W), lam_t6=np.array(LAM), iter_t6=np.array(IT), nAS_t6=np.array(NAS))
+    Xc, Uc, Ic = [], [], []
+    for b in (2, 7):
+        oc.reset()
+        x = X0[b].copy()
+        xs_, us_, it_ = [x.copy()], [], []
+        for _ in range(5):
+            u = oc.step(x)
+            assert oc.log["status"][-1] == 0
+            x = st.F(x[None], u[None])[0]
+            xs_.append(x.copy()); us_.append(u.copy()); it_.append(oc.log["iter"][-1])
+        Xc.append(xs_); Uc.append(us_); Ic.append(it_)
+    out.update(cl_X=np.array(Xc), cl_U=np.array(Uc), cl_iter=np.array(Ic))
+    np.savez_compressed(os.path.join(HERE, "golden_evaporation_sc1.npz"), **out)
+    print("evaporation_sc1: iter", out["iter_t6"], "closed-loop iter", out["cl_iter"].tolist())
+
+
 def chain(name="chain", B=32):
     """synthetic models (configs.chain nz = 8, configs.dims9 nz = 12 with the AWE config's dimensions): generic-dimension paths"""
     st = rp.StageLib(name)
@@ -242,6 +284,9 @@ def main():
     rp.build()
     if len(sys.argv) > 1 and sys.argv[1] == "awe9":
         awe9()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "evaporation_sc1":
+        evaporation_sc1()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "chain":
         chain()
