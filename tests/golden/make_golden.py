@@ -222,8 +222,9 @@ def awe9(B=24, Bcl=6, nsteps=8, Blarge=512):
 def evaporation_sc1():
     """soft constraints (Tuner.create_mpc(..., opts={'slack_flag': 'active'}), tuner.py:171-177, preprocessing.py:120-155) on the
     evaporation config: the row active at the steady state (X2 >= 25) is softened.  12 x0, three of them BELOW the bound, and two
-    closed loops.  (A closed loop started 0.8 below the bound is left out: from its second MPC step on the oracle -- qpOASES_e on a
-    QP whose slack has no curvature -- stalls at max_iter while the device routines converge to the same u0)"""
+    closed loops.  (A closed loop started 0.8 below the bound is left out: from its second MPC step on the oracle stalls at
+    max_iter -- qpOASES_e returns its QP solution with a stationarity residual of 1.75e-6 > tol, its termination tolerance relative
+    to multipliers of size scost = 6e4 -- while the device routines converge to the same u0)"""
     from tunempc_b200 import constraints
     from tunempc_b200.pmpc import problem_from_reference_args
     pb = rp_problem("evaporation")
