@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE (oracle/): sympy restatement of `tunempc/preprocessing.py`, pinned by the known answers of the reference's own
-tests (test/test_processing.py).  Nothing in the product package imports it; the device path of this round has ns = nsc = 0.
+tests (test/test_processing.py).  Nothing in the product package imports it (the product-side counterpart, in matrix form, is tunempc_b200/constraints.py).
 
   input_formatting(sys)        preprocessing.py:35-76    split h(x,u) >= 0 into linear rows and slacked nonlinear equalities
   detect_nonlinear_inequalities  :78-118                 g(x,u,us) = h_nl(x,u) - us = 0,  h(x,u,us) = [h_lin(x,u); us] >= 0
@@ -8,9 +8,7 @@ tests (test/test_processing.py).  Nothing in the product package imports it; the
 The reference works on CasADi Functions and detects (non-)linearity with `ca.which_depends(expr, vars, 2)`; here the
 functions are sympy expressions over the model card's symbols and a row is nonlinear iff one of its second derivatives
 w.r.t. (x,u) is not identically zero.  Known answers of the reference's own tests (test/test_processing.py:98-104,
-177-184) are reproduced in tests/test_preprocessing.py.  The CUDA path of this round handles ns = nsc = 0 (all four
-reference configs it covers have linear h and slack_flag 'none'); the slack variables these functions introduce are the
-next widening step.
+177-184) are reproduced in tests/test_preprocessing.py.
 """
 from __future__ import annotations
 
