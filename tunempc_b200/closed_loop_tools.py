@@ -60,7 +60,7 @@ def check_equivalence(controllers, cost, h, x0, dx, alpha, flag="tunempc"):
         w = ctrl.w_sol
         B, N, nz, nx = w.shape[0], pb.N, pb.nz, pb.nx
         Z = w[:, : N * nz].reshape(B, N, nz)
-        Xp, Up = Z[:, :, :nx].contiguous(), Z[:, :, nx:].contiguous()
+        Xp, Up = Z[:, :, :nx].contiguous(), Z[:, :, nx:nx + pb.nu].contiguous()   # the model inputs (slack variables follow them in a stage)
         log["u"][name] = Up                                             # :62-63
         log["x"][name] = Xp
         if cost is None or h is None:
