@@ -712,8 +712,14 @@ static int ensure_capacity(tmpc_handle* h, int64_t B) {
 }
 
 extern "C" {
+static bool step_in_flight(tmpc_handle* h) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  return h->busy;
+}
+
 int tmpc_reset(tmpc_handle* h, int64_t B) {
   if (!h) return 1;
+  if (step_in_flight(h)) { h->err = "tmpc_reset: a step started by tmpc_step_async is still in flight (call tmpc_wait first)"; return 1; }
   if (!h->tables_set) { h->err = "tmpc_reset: tables not set"; return 1; }
   if (B < 0) { h->err = "tmpc_reset: negative batch size"; return 1; }
   cudaSetDevice(h->device);
@@ -992,6 +998,7 @@ int tmpc_busy(tmpc_handle* h, int32_t* busy) {
 int tmpc_step_host(tmpc_handle* h, const double* X0_host, int64_t B, double* U0_host, double* W_host,
                    double* LAM_host, double* G_host, int32_t* status_host, int32_t* iter_host, int32_t* flags_host) {
   if (!h) return 1;
+  if (step_in_flight(h)) { h->err = "tmpc_step_host: a step started by tmpc_step_async is still in flight (call tmpc_wait first)"; return 1; }
   if (h->cap < B) { h->err = "tmpc_step_host: call tmpc_reset(B) first"; return 1; }
   if (B == 0) return tmpc_step(h, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   cudaSetDevice(h->device);

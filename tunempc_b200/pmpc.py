@@ -190,6 +190,8 @@ class Pmpc:
 
     def reset(self, B=None):
         """pmpc.py:858-865: phase index <- 0, log cleared, warm start <- reference (for B instances)."""
+        if getattr(self, "_Pmpc__pending", None) is not None:
+            raise RuntimeError("reset: a step started by step_async is still in flight (call wait() first)")
         if B is not None:
             self.__B = int(B)
         self.__index = 0
@@ -213,6 +215,8 @@ class Pmpc:
         solution tensors."""
         pb = self.__pb
         L = self.__lib.lib
+        if getattr(self, "_Pmpc__pending", None) is not None:
+            raise RuntimeError("step: a step started by step_async is still in flight (call wait() first)")
         is_torch = type(x0).__module__.startswith("torch")
         if is_torch:
             import torch
