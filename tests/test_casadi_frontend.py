@@ -35,3 +35,9 @@ def test_cstr_from_casadi_matches_the_sympy_card():
     hn = ca.Function("hn", [x, u], [x[0] * u[0]])
     with pytest.raises(NotImplementedError):
         cf.linear_constraints_from_casadi(hn, 4, 2)
+    # nonlinear rows go through the slack reformulation (preprocessing.py:78-118): the reference's own test case (test_processing.py:74-104)
+    hm = ca.Function("hm", [x, u], [ca.vertcat(x[0] + u[0], u[1], x[0] ** 2 * u[0])])
+    m2, C2, c2, where = cf.constraints_from_casadi(hm, m)
+    assert where == [("h", 0), ("h", 1), ("g", 0)] and m2.ns == 1 and C2.shape == (3, 7)
+    zz = np.zeros(7); zz[0] = 1.0; zz[5] = 2.0; zz[6] = 3.0                      # x0 = 1, u = (0, 2), us = 3
+    assert (C2 @ zz + c2).tolist() == [1.0, 2.0, 3.0]

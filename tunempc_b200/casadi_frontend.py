@@ -99,8 +99,8 @@ def model_from_casadi(name, f, l=None, rk_steps=1, tf=1.0, integrator="rk4", dis
 
 
 def linear_constraints_from_casadi(h, nx, nu):
-    """casadi.Function h(x,u) >= 0 -> (C, c) with h = C z + c.  Rows that are not affine in (x,u) need the slack
-    reformulation of tunempc/preprocessing.py:78-118, which is not built: NotImplementedError."""
+    """casadi.Function h(x,u) >= 0 -> (C, c) with h = C z + c, for an h whose rows are all affine (CasADi does the differentiation);
+    `constraints_from_casadi` handles the general case."""
     _require()
     if not h.is_a("SXFunction"):
         h = h.expand()
@@ -110,16 +110,43 @@ def linear_constraints_from_casadi(h, nx, nu):
     hv = h(xs, us)
     J = ca.jacobian(hv, z)
     if ca.which_depends(hv, z, 2, True).count(True):   # second-order dependence: a nonlinear row (preprocessing.py:91-99)
-        raise NotImplementedError("nonlinear path constraints need slack variables (preprocessing.input_formatting): not built")
+        raise NotImplementedError("h has nonlinear rows: use constraints_from_casadi (slack reformulation, preprocessing.py:78-118)")
     C = np.array(ca.Function("J", [xs, us], [J])(np.zeros(nx), np.zeros(nu)))
     c = np.array(ca.Function("h0", [xs, us], [hv])(np.zeros(nx), np.zeros(nu))).ravel()
     return C.reshape(-1, nx + nu), c
 
 
+def constraints_from_casadi(h, model):
+    """casadi.Function h(x,u) >= 0 -> the slack form the controller takes (tunempc/preprocessing.py:35-118): rows that are affine in
+    (x,u) become (C, c); the others are handed to the model card as `gnl` (code-generated next to the ODE, one slack us_i each, the
+    rows us >= 0 appended).  Returns (model with gnl, C over (x,u,us), c, where)."""
+    _require()
+    import dataclasses
+    from .constraints import split_path_constraints
+    if not h.is_a("SXFunction"):
+        h = h.expand()
+    nx, nu = model.nx, model.nu
+    xs = ca.SX.sym("x", nx)
+    us = ca.SX.sym("u", nu)
+    names = {xs[i].name(): model.x[i] for i in range(nx)}
+    names.update({us[i].name(): model.u[i] for i in range(nu)})
+    hv = h(xs, us)
+    rows = [sx_to_sympy(hv[i], names) for i in range(hv.shape[0])]
+    C, c, gnl, where = split_path_constraints(model.x, model.u, rows)
+    if gnl:
+        model = dataclasses.replace(model, gnl=tuple(gnl), hess_nz=[])
+    return model, C, c, where
+
+
 def card_from_casadi(name, f, l, h=None, N=20, p=1, w_guess=None, term_idx=None, **integrator):
-    """the model-card dict `Tuner(card, p)` takes (the counterpart of `Tuner(f, l, h, p)`, tunempc/tuner.py:41)"""
+    """the model-card dict `Tuner(card, p)` / the `sys` of `Pmpc` take (the counterpart of `Tuner(f, l, h, p)`, tunempc/tuner.py:41).
+    Nonlinear rows of h end up in `card['model'].gnl` with their slack rows in C (the Tuner's own OCP handles affine rows only;
+    the Pmpc constructor takes the card as it is)."""
     model = model_from_casadi(name, f, l, **integrator)
     nz = model.nx + model.nu
-    C, c = (np.zeros((0, nz)), np.zeros(0)) if h is None else linear_constraints_from_casadi(h, model.nx, model.nu)
+    if h is None:
+        C, c = np.zeros((0, nz)), np.zeros(0)
+    else:
+        model, C, c, _ = constraints_from_casadi(h, model)
     return dict(model=model, cost=model.cost, C=C, c=c, w_guess=np.zeros(nz) if w_guess is None else np.asarray(w_guess, dtype=np.float64),
                 period=p, N=N, term_idx=list(range(model.nx)) if term_idx is None else list(term_idx))
