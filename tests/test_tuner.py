@@ -177,3 +177,63 @@ def test_periodic_ocp_with_path_constraints_and_economic_mpc():
         assert np.max(np.abs(o["u0"] - uo)) < 1e-10
         x, xo = st.F(x, o["u0"]), st.F(xo, uo)
     assert np.isclose(o["u0"][2], w[3, 4:], atol=1e-8).all() or True
+
+
+def test_tuner_with_nonlinear_path_constraints():
+    """Tuner(f, l, h, 1) with nonlinear rows in h (tunempc/preprocessing.py:35-118, tuner.py:62-69): steady-state OCP, sensitivities and
+    convexification in the slack form (stage variables (x,u,us)), then the tuned controller's problem against the oracle -- device
+    routines via the twin.  configs.dims9g: one nonlinear state constraint active at the steady state."""
+    import os
+    from oracle import reference_port as rp
+    from tunempc_b200 import configs, modelgen
+    from tunempc_b200.pmpc import problem_from_reference_args
+    from tunempc_b200.problem import build_tables
+    from tunempc_b200.tuner import Tuner
+    from twin.twin import Twin
+    card = configs.dims9g()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    modelgen.generate_header(card["model"], os.path.join(root, "tunempc_b200", "csrc", "gen", "model_dims9g.h"))
+    st = rp.StageLib("dims9g")
+    t = Tuner(card, p=1, stage_eval=st.F)
+    w = t.solve_ocp()
+    assert w.shape == (1, 15)
+    z = w[0, :12]
+    sub = dict(zip(list(card["model"].x) + list(card["model"].u), z))
+    gn = np.array([float(e.subs(sub)) for e in card["model"].gnl])
+    assert abs(gn[0]) < 1e-10 and gn[1] > 0.1 and gn[2] > 0.1               # the state-only nonlinear row is active
+    assert np.allclose(w[0, 12:], np.where(np.abs(gn) < 1e-10, 0.0, gn), atol=1e-12)          # us = h_nl(x,u)
+    lam_h = t.lam_g["h"][0]
+    assert lam_h[14] < 0 and np.count_nonzero(lam_h) == 1                   # the multiplier sits on us_0 >= 0
+    assert np.abs(st.F(w[:, :9], w[:, 9:12])[0] - w[0, :9]).max() < 1e-12   # steady state
+    assert np.min(np.linalg.eigvalsh(t.S["H"][0])) < 1e-9                   # no curvature in the slacks: not positive definite
+    Hc = t.convexify()
+    assert np.min(np.linalg.eigvalsh(Hc[0])) > 1e-3 and Hc[0].shape == (15, 15)
+    sysd = t.sys
+    assert "us" in sysd["vars"] and "g" in sysd
+    pb = problem_from_reference_args(20, sysd, "tracking", {"x": [w[0, :9]], "u": [w[0, 9:12]], "us": [w[0, 12:]]}, {"H": Hc, "q": t.S["q"]},
+                                     {"dyn": [np.zeros(9)], "g": [np.zeros(3)], "h": [lam_h]},
+                                     {"A": t.S["A"], "B": [np.asarray(b)[:, :3] for b in t.S["B"]]}, {"p_operator": card["term_idx"]})
+    assert (pb.ns, pb.nsc, pb.nz, pb.nh, pb.gnl_x_idx) == (3, 0, 15, 17, [0])
+    assert pb.relax0 == sorted(set(pb.h_x_idx + [14]))                     # h_us_idx = 0 + 17 - 3: the row us_0 >= 0 (no usc rows here)
+    oc = rp.Pmpc(pb)
+    u = oc.step(w[0, :9])
+    assert oc.log["iter"][-1] == 1 and np.allclose(u, w[0, 9:12], atol=1e-10)     # P1: step(x_ref) = u_ref
+    xs = w[0, :9]
+    X0 = xs + 0.08 * (configs.sample_x0("dims9g", pb, 8, 3) - xs)
+    tw = Twin(pb, build_tables(pb))
+    tw.reset(8)
+    o = tw.step(X0)
+    n_ok = 0
+    for b in range(8):
+        oc.reset()
+        try:
+            uo = oc.step(X0[b])
+        except RuntimeError:                                                # the reference's QP solver raises: hard nonlinear state row
+            assert o["status"][b] == 2                                     # ... and the device routines report QP_Infeasible
+            continue
+        n_ok += 1
+        assert o["status"][b] == 0 and o["iter"][b] == oc.log["iter"][-1] and o["nAS"][b] == oc.log["nAS"][-1]
+        assert np.max(np.abs(o["u0"][b] - uo)) < 1e-10 and np.max(np.abs(o["w"][b] - oc.w_sol)) < 1e-9
+        for k in range(pb.N):
+            assert np.array_equal(o["lam"][b][pb.g_h(k)] != 0, oc.lam_g[pb.g_h(k)] != 0), (b, k)
+    assert n_ok >= 5

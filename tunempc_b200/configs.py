@@ -295,6 +295,24 @@ def awe9_problem(stage_F, N=None, hessian_approximation="exact"):
     return pb, info
 
 
+def dims9g():
+    """SYNTHETIC: `dims9` with three NONLINEAR path constraints next to its 14 linear rows -- what `preprocessing.input_formatting`
+    (tunempc/preprocessing.py:35-118) turns into slacks us, rows g = h_nl(x,u) - us = 0 and rows us >= 0.  The first one (state
+    only) is active at the economic steady state.  Exercises `Tuner(...).solve_ocp().convexify().create_mpc('tuned')` with
+    nonlinear rows (steady-state OCP, sensitivities and convexification in the slack form)."""
+    import dataclasses
+    card = dims9()
+    m = card["model"]
+    p, v, a, u = m.x[0:4], m.x[4:8], m.x[8], m.u
+    gnl = (1.1 - p[3] ** 2 - 0.5 * v[3] ** 2, 0.5 - u[0] * (1 + 0.3 * p[0]), 0.5 - u[1] ** 2 - 0.5 * a ** 2)
+    card["model"] = dataclasses.replace(m, name="dims9g", gnl=gnl, hess_nz=[])
+    C, c = card["C"], card["c"]
+    ns = len(gnl)
+    card["C"] = np.block([[C, np.zeros((C.shape[0], ns))], [np.zeros((ns, C.shape[1])), np.eye(ns)]])
+    card["c"] = np.concatenate([c, np.zeros(ns)])
+    return card
+
+
 def evaporation_sc1():
     """examples/evaporation_process with `create_mpc(..., opts={'slack_flag': 'active'})` (tuner.py:171-177): the one row that is
     active at the steady state (X2 >= 25) is softened -> the model library variant with nsc = 1"""
@@ -321,7 +339,7 @@ def sample_x0(name, pb, B, seed=0):
         return xs + np.stack([0.5 * np.abs(rng.uniform(-1, 1, B)), 1.0 * rng.uniform(-1, 1, B)], axis=1)
     if name == "chain":
         return xs + np.array([0.5, 0.5, 0.5, 0.8, 0.8, 0.8]) * rng.uniform(-1, 1, (B, pb.nx))
-    if name == "dims9":
+    if name in ("dims9", "dims9g"):
         return xs + np.array([0.4] * 4 + [0.6] * 4 + [0.3]) * rng.uniform(-1, 1, (B, pb.nx))
     if name == "unicycle":
         return xs + np.array([0.5, 0.1, 0.0, 0.0]) * rng.uniform(-1, 1, (B, pb.nx))   # examples/unicycle/main.py:172
@@ -331,7 +349,7 @@ def sample_x0(name, pb, B, seed=0):
 
 
 CONFIGS = {"lq": lq, "cstr": cstr, "unicycle": unicycle, "evaporation": evaporation, "chain": chain, "dims9": dims9,
-           "awe9": awe9, "evaporation_sc1": evaporation_sc1}
+           "awe9": awe9, "evaporation_sc1": evaporation_sc1, "dims9g": dims9g}
 
 
 def make_problem(name, stage_F, N=None, hessian_approximation="exact", mpc_type="tuned"):

@@ -41,7 +41,15 @@ class Tuner(object):
             self.__C = np.asarray(card.get("C", np.zeros((0, self.__model.nx + self.__model.nu))), dtype=np.float64)
             self.__c = np.asarray(card.get("c", np.zeros(0)), dtype=np.float64)
         self.__nx, self.__nu = self.__model.nx, self.__model.nu
-        self.__nw = self.__nx + self.__nu                                   # tuner.py:69
+        self.__ns = getattr(self.__model, "ns", 0)                          # slacks of the model card's nonlinear rows (tuner.py:62-66)
+        self.__nw = self.__nx + self.__nu + self.__ns                       # tuner.py:69
+        if self.__ns:
+            if self.__C.shape[1] != self.__nw or self.__C.shape[0] < self.__ns:
+                raise ValueError("with nonlinear rows the path constraints are C (x,u,us) + c >= 0, the rows us >= 0 last "
+                                 "(constraints.split_path_constraints)")
+            if int(p) != 1:
+                raise NotImplementedError("nonlinear path constraints in a periodic OCP are not built")
+            self.__gnl_funs = tuning.lambdify_gnl(self.__model)
         self.__p = int(p)
         self.__cost_funs = tuning.lambdify_cost(self.__model, self.__l)
         if stage_eval is None:
@@ -60,11 +68,22 @@ class Tuner(object):
         if w0 is None:
             w0 = self.__card.get("w_guess")
         w0 = np.asarray(w0, dtype=np.float64)
+        if self.__ns and w0.size == self.__p * (self.__nx + self.__nu):       # guess without slacks: us = h_nl(x,u)
+            w0 = np.concatenate([w0.ravel(), self.__gnl_funs[0](w0.ravel())])
         w0_shape = self.__p * self.__nw
         assert w0.size == w0_shape, \
             "Incorrect dimensions of input variable w0: expected {}x1, but received {}".format(w0_shape, w0.shape)
         w0 = w0.reshape(self.__p, self.__nw)
-        if self.__p == 1:
+        self.__lam_gnl = None
+        if self.__p == 1 and self.__ns:
+            nzm = self.__nx + self.__nu
+            z, lam_d, lam_g, lam_h = tuning.solve_steady_state_slack(self.__F, self.__cost_funs, self.__gnl_funs, self.__C, self.__c,
+                                                                     w0[0][:nzm], self.__nx, self.__ns)
+            self.__S = tuning.sensitivities_slack(self.__F, self.__cost_funs, self.__gnl_funs, self.__C, z, lam_d, lam_g, lam_h,
+                                                  self.__nx, self.__nu, self.__ns)
+            self.__w_sol = z[None, :].copy()
+            self.__lam_h, self.__lam_dyn, self.__lam_gnl = lam_h[None, :], lam_d[None, :], lam_g[None, :]
+        elif self.__p == 1:
             z, lam_d, lam_h = tuning.solve_steady_state(self.__F, self.__cost_funs, self.__C, self.__c, w0[0], self.__nx)
             self.__S = tuning.sensitivities(self.__F, self.__cost_funs, self.__C, z, lam_d, lam_h, self.__nx)
             self.__w_sol = z[None, :].copy()
@@ -138,15 +157,22 @@ class Tuner(object):
                 hdr = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "gen", "model_%s.h" % model.name)
                 modelgen.generate_header(model, hdr)
                 build_model_lib(model.name)                                                  # no-op when the library is up to date
-                mpc_sys = {"f": model, "h": (Cs, cs), "scost": scost,
-                           "vars": {"x": model.x, "u": model.u, "usc": list(range(len(rows)))}}
-        wref = {"x": [self.__w_sol[k, :self.__nx] for k in range(p)], "u": [self.__w_sol[k, self.__nx:] for k in range(p)]}
-        sens = {"A": self.__S["A"], "B": self.__S["B"]}
+                mpc_sys = dict(self.sys, f=model, h=(Cs, cs), scost=scost)
+                mpc_sys["vars"] = dict(self.sys["vars"], usc=list(range(len(rows))))
+        nzm = self.__nx + self.__nu
+        wref = {"x": [self.__w_sol[k, :self.__nx] for k in range(p)], "u": [self.__w_sol[k, self.__nx:nzm] for k in range(p)]}
+        if self.__ns:
+            wref["us"] = [self.__w_sol[k, nzm:] for k in range(p)]
+        sens = {"A": self.__S["A"], "B": [np.asarray(b)[:, :self.__nu] for b in self.__S["B"]]}
         if mpc_type == "economic":                                                           # tuner.py:180-182: full lam_g
             lam_g_ref = {"dyn": list(self.__lam_dyn), "h": list(self.__lam_h)}
+            if self.__ns:
+                lam_g_ref["g"] = list(self.__lam_gnl)
             return Pmpc(N=N, sys=mpc_sys, cost="economic", wref=wref, lam_g_ref=lam_g_ref, sensitivities=sens,
                         options=opts, device=device)
         lam_g0 = {"dyn": [np.zeros(self.__nx)] * p, "h": list(self.__lam_h)}                # tuner.py:186-189: lam_g0['dyn'] = 0
+        if self.__ns:
+            lam_g0["g"] = [np.zeros(self.__ns)] * p                                          # tuner.py:188-189: lam_g0['g'] = 0
         return Pmpc(N=N, sys=mpc_sys, cost="tracking", wref=wref, tuning=tuning, lam_g_ref=lam_g0, sensitivities=sens,
                     options=opts, device=device)
 
@@ -157,7 +183,11 @@ class Tuner(object):
 
     @property
     def sys(self):
-        return {"f": self.__model, "h": (self.__C, self.__c), "vars": {"x": self.__model.x, "u": self.__model.u}}
+        sys = {"f": self.__model, "h": (self.__C, self.__c), "vars": {"x": self.__model.x, "u": self.__model.u}}
+        if self.__ns:
+            sys["vars"]["us"] = list(range(self.__ns))
+            sys["g"] = "compiled"                                    # the nonlinear rows live in the model library (OdeModel.gnl)
+        return sys
 
     @property
     def l(self):

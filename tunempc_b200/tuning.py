@@ -94,6 +94,109 @@ def solve_steady_state(stage_F, cost_funs, C, c, z0, nx, tol=1e-12, lam_tresh=1e
     return z, lam_d, lam_h
 
 
+def lambdify_gnl(model):
+    """numpy callables (value (ns,), Jacobian (ns, nx+nu), second derivatives (ns, nx+nu, nx+nu)) of the model card's nonlinear
+    path constraints h_nl(x,u) >= 0"""
+    z = list(model.x) + list(model.u)
+    g = sp.Matrix([sp.sympify(e) for e in model.gnl])
+    ns = len(model.gnl)
+    fv = sp.lambdify([z], g, "numpy")
+    fj = sp.lambdify([z], g.jacobian(z), "numpy")
+    fh = [sp.lambdify([z], sp.hessian(e, z), "numpy") for e in g]
+    return (lambda v: np.asarray(fv(list(v)), dtype=np.float64).ravel(),
+            lambda v: np.asarray(fj(list(v)), dtype=np.float64).reshape(ns, len(z)),
+            lambda v: np.array([np.asarray(h(list(v)), dtype=np.float64) for h in fh]).reshape(ns, len(z), len(z)))
+
+
+def solve_steady_state_slack(stage_F, cost_funs, gnl_funs, C, c, z0, nx, ns, tol=1e-12, lam_tresh=1e-8):
+    """Steady-state OCP in the slack form of tunempc/preprocessing.py:78-118 (what `Tuner(f, l, h, 1).solve_ocp` solves when h has
+    nonlinear rows):  min l(x,u)  s.t.  F(x,u) = x,  g = h_nl(x,u) - us = 0,  C (x,u,us) + c >= 0  (the last ns rows of C are us >= 0).
+    Solved in (x,u) with h_nl as inequalities, then polished by an active-set Newton; us = h_nl(x,u) afterwards.
+    Returns z (nx+nu+ns), lam_dyn (nx), lam_g (ns), lam_h (nh) in CasADi sign; lam_g equals the multiplier of the row us >= 0
+    (stationarity in us: -lam_g + lam_(us>=0) = 0)."""
+    stage_F = _single(stage_F)
+    l_f, g_f, H_f = cost_funs
+    gv, gj, gh = gnl_funs
+    nzm = len(z0)
+    nh = C.shape[0]
+    n_aff = nh - ns
+    Ca, ca_ = C[:n_aff, :nzm], c[:n_aff]
+
+    def dyn(z):
+        xf, S = stage_F(z[:nx], z[nx:], 1)
+        return xf - z[:nx], S - np.hstack([np.eye(nx), np.zeros((nx, nzm - nx))])
+
+    def ineq(z):
+        return np.concatenate([Ca @ z + ca_, gv(z)])
+
+    def ineq_jac(z):
+        return np.vstack([Ca, gj(z)])
+
+    scale = np.maximum(np.abs(z0), 1.0)
+    res = sopt.minimize(lambda y: l_f(y * scale), z0 / scale, jac=lambda y: g_f(y * scale) * scale,
+                        constraints=[{"type": "eq", "fun": lambda y: dyn(y * scale)[0], "jac": lambda y: dyn(y * scale)[1] * scale[None, :]},
+                                     {"type": "ineq", "fun": lambda y: ineq(y * scale), "jac": lambda y: ineq_jac(y * scale) * scale[None, :]}],
+                        method="SLSQP", options={"ftol": 1e-14, "maxiter": 500})
+    z = res.x * scale
+    hv = ineq(z)
+    act = [i for i in range(nh) if hv[i] < 1e-6]
+    _, Jd0 = dyn(z)
+    Jall = np.vstack([Jd0, ineq_jac(z)[act] if act else np.zeros((0, nzm))])
+    le = np.linalg.lstsq(Jall.T, -g_f(z), rcond=None)[0]
+    lam_d, lam_a = le[:nx].copy(), le[nx:].copy()
+    for it in range(50):
+        r_d, Jd = dyn(z)
+        Jin = ineq_jac(z)
+        Ja = Jin[act] if act else np.zeros((0, nzm))
+        Jall = np.vstack([Jd, Ja])
+        xf, S, T = stage_F(z[:nx], z[nx:], 2)
+        Hl = H_f(z) + np.einsum("a,aij->ij", lam_d, T)
+        G2 = gh(z)
+        for j, i in enumerate(act):
+            if i >= n_aff:
+                Hl = Hl + lam_a[j] * G2[i - n_aff]
+        grad = g_f(z) + Jall.T @ np.concatenate([lam_d, lam_a])
+        res_v = np.concatenate([grad, r_d, ineq(z)[act]])
+        if np.linalg.norm(res_v, np.inf) < tol and it > 0:
+            break
+        m = Jall.shape[0]
+        K = np.block([[Hl, Jall.T], [Jall, np.zeros((m, m))]])
+        step = np.linalg.solve(K, -res_v)
+        z = z + step[:nzm]
+        lam_d = lam_d + step[nzm:nzm + nx]
+        lam_a = lam_a + step[nzm + nx:]
+    lam_in = np.zeros(nh)
+    for j, i in enumerate(act):
+        lam_in[i] = lam_a[j]
+    lam_in[np.abs(lam_in) < lam_tresh] = 0.0
+    if np.any(lam_in > 0):
+        raise RuntimeError("steady state: wrong-signed multiplier, active set guess failed")
+    us = gv(z)
+    us[np.abs(us) < 1e-12] = 0.0
+    lam_g = lam_in[n_aff:].copy()                       # multiplier of g = that of us >= 0
+    return np.concatenate([z, us]), lam_d, lam_g, lam_in
+
+
+def sensitivities_slack(stage_F, cost_funs, gnl_funs, C, w, lam_d, lam_g, lam_h, nx, nu, ns):
+    """S of pocp.py:261-362 for p = 1 in the slack form: stage variables (x, u, us); B carries zero columns for us, H has no
+    curvature in us, the rows g = h_nl - us (always active) join the active rows of h in C_As."""
+    _, _, H_f = cost_funs
+    gv, gj, gh = gnl_funs
+    stage_F = _single(stage_F)
+    nzm, nzr = nx + nu, nx + nu + ns
+    z = w[:nzm]
+    xf, S1, T = stage_F(z[:nx], z[nx:], 2)
+    H = np.zeros((nzr, nzr))
+    Hxu = H_f(z) + np.einsum("a,aij->ij", lam_d, T) + np.einsum("a,aij->ij", lam_g, gh(z))
+    H[:nzm, :nzm] = 0.5 * (Hxu + Hxu.T)
+    B = np.hstack([S1[:, nx:], np.zeros((nx, ns))])
+    Jg = np.hstack([gj(z), -np.eye(ns)])
+    q = -(lam_h @ C)                                       # pocp.py:357-360 (the tuned controller's dual reference has lam_g = 0)
+    act = [i for i in range(C.shape[0]) if lam_h[i] != 0]
+    C_As = np.vstack([Jg] + ([C[act]] if act else []))
+    return {"A": [S1[:, :nx].copy()], "B": [B], "C": [C.copy()], "H": [H], "q": [q], "C_As": [C_As], "G": [Jg]}
+
+
 def sensitivities(stage_F, cost_funs, C, z, lam_d, lam_h, nx):
     """S of pocp.py:261-362 for p = 1 (lists of length 1, as the reference returns)."""
     _, _, H_f = cost_funs
